@@ -1,0 +1,36 @@
+# Builds the product library (libvrt.so: sm_100a kernels + C ABI), the host-side mirror (libvrt_host.so)
+# and the CPU oracle (test infrastructure).  Everything is built in-tree so it travels with the repo snapshot.
+NVCC ?= /usr/local/cuda/bin/nvcc
+CXX ?= g++
+PKG := zig_vulkan_b200
+CSRC := $(PKG)/csrc
+
+# --fmad=false is part of the numerical contract (DESIGN.md "FP discipline"), not a tuning knob.
+NVCCFLAGS := -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 --fmad=false -lineinfo \
+             -Xcompiler -fPIC,-Wall,-Wextra -Xptxas -v
+HOSTFLAGS := -O2 -std=c++17 -fPIC -Wall -Wextra -pthread
+
+KERNEL_HDRS := $(wildcard $(CSRC)/*.cuh) include/vrt.h
+
+all: $(PKG)/libvrt.so $(PKG)/libvrt_host.so oracle
+
+$(CSRC)/vrt_kernels.o: $(CSRC)/vrt_kernels.cu $(KERNEL_HDRS)
+	$(NVCC) $(NVCCFLAGS) -c -o $@ $< 2> $(CSRC)/vrt_kernels.ptxas.log || (cat $(CSRC)/vrt_kernels.ptxas.log; false)
+
+$(CSRC)/vrt_shim.o: $(CSRC)/vrt_shim.cu $(KERNEL_HDRS)
+	$(NVCC) $(NVCCFLAGS) -c -o $@ $<
+
+$(PKG)/libvrt.so: $(CSRC)/vrt_kernels.o $(CSRC)/vrt_shim.o
+	$(NVCC) -gencode arch=compute_100a,code=sm_100a -shared -o $@ $^ -ldl
+
+$(PKG)/libvrt_host.so: $(wildcard $(CSRC)/host/*.cpp) $(wildcard $(CSRC)/host/*.h) include/vrt.h include/vrt_host.h $(PKG)/libvrt.so
+	$(CXX) $(HOSTFLAGS) -shared -o $@ $(wildcard $(CSRC)/host/*.cpp) -L$(PKG) -lvrt -Wl,-rpath,'$$ORIGIN'
+
+oracle:
+	$(MAKE) -C oracle
+
+clean:
+	rm -f $(CSRC)/*.o $(CSRC)/*.ptxas.log $(PKG)/*.so
+	$(MAKE) -C oracle clean
+
+.PHONY: all oracle clean

@@ -1,0 +1,570 @@
+// vrt_shim.cu — implementation of the C ABI in include/vrt.h on the CUDA runtime.
+//
+// One vrt_ctx == one ComputePipeline + its device buffer + its target image (reference:
+// src/modules/voxel_rt/ComputePipeline.zig, Pipeline.zig:103-126,272-316).  The Vulkan pieces map as:
+//   device-local buffer with UBO+6 SSBOs at offsets (ComputePipeline.zig:86-100)  -> seven cudaMalloc'd arrays
+//   StagingRamp.transferToBuffer + flush (render/StagingRamp.zig:318-495)          -> cudaMemcpyAsync on the ctx stream
+//   push constants + descriptor set (ComputePipeline.zig:488-545)                  -> one __grid_constant__ TraceParams
+//   vkQueueSubmit + complete_fence (ComputePipeline.zig:423-459)                   -> stream order + cudaStreamSynchronize
+// NCCL is loaded lazily with dlopen so that the library has no link-time dependency on it.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <dlfcn.h>
+#include <new>
+
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include "../../include/vrt.h"
+#include "vrt_kernels.cuh"
+
+using namespace vrt;
+
+namespace {
+
+char g_init_error[512] = "no error";
+
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi g_nccl;
+
+bool load_nccl(char* err, size_t err_len) {
+    if (g_nccl.handle) return true;
+    // RTLD_NOLOAD first: reuse the copy the host process already mapped (e.g. PyTorch's bundled libnccl.so.2)
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) {
+        snprintf(err, err_len, "dlopen(libnccl.so.2) failed: %s", dlerror());
+        return false;
+    }
+    g_nccl.GetUniqueId = reinterpret_cast<decltype(g_nccl.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
+    g_nccl.CommInitRank = reinterpret_cast<decltype(g_nccl.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
+    g_nccl.AllGather = reinterpret_cast<decltype(g_nccl.AllGather)>(dlsym(h, "ncclAllGather"));
+    g_nccl.CommDestroy = reinterpret_cast<decltype(g_nccl.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
+    g_nccl.GetErrorString = reinterpret_cast<decltype(g_nccl.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllGather || !g_nccl.CommDestroy || !g_nccl.GetErrorString) {
+        snprintf(err, err_len, "libnccl is missing a required symbol");
+        dlclose(h);
+        return false;
+    }
+    g_nccl.handle = h;
+    return true;
+}
+
+}  // namespace
+
+struct vrt_ctx {
+    vrt_config cfg;
+    uint32_t row_begin, row_end;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    bool timing_valid = false;
+
+    // the seven reference buffers (Pipeline.zig:273-283)
+    vrt_grid_state grid{};
+    bool have_grid = false;
+    vrt_material* d_materials = nullptr;
+    uint32_t* d_statuses = nullptr;
+    uint32_t* d_brick_indices = nullptr;
+    uint8_t* d_occupancy = nullptr;
+    uint32_t* d_start_indices = nullptr;
+    uint8_t* d_material_indices = nullptr;
+    size_t n_materials = 0, n_statuses = 0, n_brick_indices = 0, n_occupancy = 0, n_start_indices = 0, n_material_indices = 0;
+    vrt_material* h_materials = nullptr;  // host mirror, to answer "is there a type-3 material" (:427 shortcut)
+
+    // target image
+    uint32_t* d_fb_own = nullptr;
+    uint32_t* d_fb = nullptr;
+    size_t fb_bytes = 0;
+    uint8_t* h_pinned_fb = nullptr;  // bounce buffer for vrt_trace_to_host into pageable memory
+
+    // debug
+    vrt_aov* d_aov = nullptr;
+    unsigned long long* d_counters = nullptr;
+
+    // derived mask pyramid
+    unsigned long long* d_occ_dense = nullptr;
+    unsigned long long* d_status64 = nullptr;
+    uint32_t* d_coarse = nullptr;
+    size_t n_super = 0;
+    uint32_t sdim_x = 0, sdim_y = 0, sdim_z = 0, coarse_bytes = 0;
+    bool accel_dirty = true;
+
+    // persistent-kernel work counter
+    unsigned long long* d_tile_counter = nullptr;
+    unsigned long long tile_base = 0;
+
+    // multi-GPU
+    int rank = 0, world = 1;
+    ncclComm_t comm = nullptr;
+    uint32_t exchange_mode = VRT_EXCHANGE_ALLGATHER;
+    void* peer_fb[8] = {nullptr};
+    bool peers_open = false;
+
+    uint32_t last_launches = 0;
+    char err[512] = "no error";
+};
+
+namespace {
+
+int fail(vrt_ctx* ctx, int code, const char* fmt, ...) {
+    char* dst = ctx ? ctx->err : g_init_error;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(dst, 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define VRT_CUDA(ctx, call)                                                                                   \
+    do {                                                                                                      \
+        cudaError_t e__ = (call);                                                                             \
+        if (e__ != cudaSuccess) {                                                                             \
+            const int code__ = (e__ == cudaErrorMemoryAllocation) ? VRT_E_OOM : VRT_E_CUDA;                   \
+            return fail(ctx, code__, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+        }                                                                                                     \
+    } while (0)
+
+template <class T>
+int upload_range(vrt_ctx* ctx, T* dst, size_t capacity, size_t offset, const T* data, size_t count, const char* what) {
+    if (!ctx) return VRT_E_INVALID;
+    if (count == 0) return VRT_OK;
+    if (!data) return fail(ctx, VRT_E_INVALID, "%s: data is NULL", what);
+    if (offset > capacity || count > capacity - offset)
+        return fail(ctx, VRT_E_RANGE, "%s: [%zu, %zu) outside capacity %zu", what, offset, offset + count, capacity);
+    VRT_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    // Pageable source: the runtime stages it before returning, so the caller may reuse `data` immediately
+    // (stricter than the reference's deferred path, render/StagingRamp.zig:105-111).
+    VRT_CUDA(ctx, cudaMemcpyAsync(dst + offset, data, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    return VRT_OK;
+}
+
+void fill_params(const vrt_ctx* c, const vrt_camera* cam, const vrt_sun* sun, TraceParams& P) {
+    std::memset(&P, 0, sizeof(P));
+    P.cam = *cam;
+    P.sun = *sun;
+    P.grid = c->grid;
+    P.materials = c->d_materials;
+    P.statuses = c->d_statuses;
+    P.brick_indices = c->d_brick_indices;
+    P.occupancy = c->d_occupancy;
+    P.start_indices = c->d_start_indices;
+    P.material_indices = c->d_material_indices;
+    P.n_statuses = c->n_statuses, P.n_brick_indices = c->n_brick_indices, P.n_occupancy = c->n_occupancy;
+    P.n_start_indices = c->n_start_indices, P.n_material_indices = c->n_material_indices;
+    P.n_materials = (uint32_t)c->n_materials;
+    P.materials_have_none = 0;
+    for (size_t i = 0; i < c->n_materials; i++)
+        if (c->h_materials[i].type == VRT_MAT_NONE) P.materials_have_none = 1;
+    P.brick_dim = (int)c->cfg.brick_dim;
+    P.brick_bytes = c->cfg.brick_dim * c->cfg.brick_dim * c->cfg.brick_dim / 8;
+    P.brick_voxel_scale = 1.0f / (float)c->cfg.brick_dim;  // Pipeline.zig:313
+    P.row_begin = c->row_begin, P.row_end = c->row_end;
+    P.fb = c->d_fb;
+    P.aov = c->d_aov;
+    P.counters = c->d_counters;
+    P.occ_dense = c->d_occ_dense;
+    P.status64 = c->d_status64;
+    P.coarse = c->d_coarse;
+    P.sdim_x = c->sdim_x, P.sdim_y = c->sdim_y, P.sdim_z = c->sdim_z;
+    P.coarse_bytes = c->coarse_bytes;
+    P.status64_bytes = (uint32_t)(c->n_super * 8);
+    P.tile_counter = c->d_tile_counter;
+    P.tile_base = c->tile_base;
+    P.vec_store_ok = (cam->image_width % 4 == 0) && ((reinterpret_cast<uintptr_t>(c->d_fb) & 15u) == 0);
+    P.n_peers = 0;
+    if (c->world > 1 && c->exchange_mode == VRT_EXCHANGE_PEER_STORE && c->peers_open) {
+        for (int r = 0; r < c->world; r++)
+            if (r != c->rank) P.peer_fb[P.n_peers++] = static_cast<uint32_t*>(c->peer_fb[r]);
+    }
+}
+
+// (Re)allocate the pyramid for the grid dimensions in ctx->grid.
+int ensure_accel(vrt_ctx* ctx) {
+    const uint32_t sx = (ctx->grid.dim_x + 3) / 4, sy = (ctx->grid.dim_y + 3) / 4, sz = (ctx->grid.dim_z + 3) / 4;
+    if (ctx->d_status64 && sx == ctx->sdim_x && sy == ctx->sdim_y && sz == ctx->sdim_z) return VRT_OK;
+    if (ctx->d_status64) cudaFree(ctx->d_status64);
+    if (ctx->d_coarse) cudaFree(ctx->d_coarse);
+    ctx->d_status64 = nullptr, ctx->d_coarse = nullptr;
+    ctx->sdim_x = sx, ctx->sdim_y = sy, ctx->sdim_z = sz;
+    ctx->n_super = (size_t)sx * sy * sz;
+    const size_t coarse_words = (ctx->n_super + 31) / 32;
+    ctx->coarse_bytes = (uint32_t)((coarse_words * 4 + 15) & ~size_t(15));
+    VRT_CUDA(ctx, cudaMalloc(&ctx->d_status64, ctx->n_super * 8));
+    VRT_CUDA(ctx, cudaMalloc(&ctx->d_coarse, ctx->coarse_bytes));
+    VRT_CUDA(ctx, cudaMemsetAsync(ctx->d_coarse, 0, ctx->coarse_bytes, ctx->stream));
+    ctx->accel_dirty = true;
+    return VRT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* vrt_last_error(const vrt_ctx* ctx) { return ctx ? ctx->err : g_init_error; }
+
+int vrt_init(vrt_ctx** out_ctx, const vrt_config* cfg) {
+    if (!out_ctx) return fail(nullptr, VRT_E_INVALID, "vrt_init: out_ctx is NULL");
+    *out_ctx = nullptr;
+    if (!cfg) return fail(nullptr, VRT_E_INVALID, "vrt_init: cfg is NULL");
+    if (cfg->struct_size != sizeof(vrt_config) || cfg->abi_version != VRT_ABI_VERSION)
+        return fail(nullptr, VRT_E_INVALID, "vrt_init: ABI mismatch (struct_size %u vs %zu, version %u vs %u)", cfg->struct_size,
+                    sizeof(vrt_config), cfg->abi_version, VRT_ABI_VERSION);
+    if (cfg->width == 0 || cfg->height == 0 || cfg->width > 32768 || cfg->height > 32768)
+        return fail(nullptr, VRT_E_INVALID, "vrt_init: bad image size %ux%u", cfg->width, cfg->height);
+    if (cfg->brick_dim != 4 && cfg->brick_dim != 8 && cfg->brick_dim != 16)
+        return fail(nullptr, VRT_E_INVALID, "vrt_init: brick_dim must be 4, 8 or 16 (got %u)", cfg->brick_dim);
+    if (cfg->n_bricks == 0 || cfg->n_bricks > 0xffffffffull)
+        return fail(nullptr, VRT_E_INVALID, "vrt_init: n_bricks out of range");
+    if (cfg->row_begin > cfg->row_end || cfg->row_end > cfg->height)
+        return fail(nullptr, VRT_E_INVALID, "vrt_init: bad row slab [%u, %u) for height %u", cfg->row_begin, cfg->row_end, cfg->height);
+
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0)
+        return fail(nullptr, VRT_E_CUDA, "vrt_init: no CUDA device (%s) — this library has no CPU fallback", cudaGetErrorString(e));
+    if (cfg->device < 0 || cfg->device >= n_dev) return fail(nullptr, VRT_E_INVALID, "vrt_init: device %d of %d", cfg->device, n_dev);
+
+    vrt_ctx* ctx = new (std::nothrow) vrt_ctx();
+    if (!ctx) return fail(nullptr, VRT_E_OOM, "vrt_init: host allocation failed");
+    ctx->cfg = *cfg;
+    if (ctx->cfg.material_capacity == 0) ctx->cfg.material_capacity = 256;  // Pipeline.Config.material_buffer
+    if (ctx->cfg.n_brick_alloc == 0) ctx->cfg.n_brick_alloc = cfg->n_bricks;  // Grid.zig:51
+    ctx->row_begin = cfg->row_begin;
+    ctx->row_end = (cfg->row_begin == 0 && cfg->row_end == 0) ? cfg->height : cfg->row_end;
+
+    const uint32_t bits = cfg->brick_dim * cfg->brick_dim * cfg->brick_dim;
+    ctx->n_materials = ctx->cfg.material_capacity;
+    ctx->n_statuses = (cfg->n_bricks + 31) / 32;                      // Grid.zig:43
+    ctx->n_brick_indices = cfg->n_bricks;                             // Grid.zig:47
+    ctx->n_occupancy = ctx->cfg.n_brick_alloc * (bits / 8);           // Grid.zig:53
+    ctx->n_start_indices = ctx->cfg.n_brick_alloc;                    // Grid.zig:57
+    ctx->n_material_indices = ctx->cfg.n_brick_alloc * (size_t)bits;  // Grid.zig:61-62
+    ctx->fb_bytes = (size_t)cfg->width * cfg->height * 4;
+
+#define INIT_CUDA(call)                                                                                          \
+    do {                                                                                                         \
+        cudaError_t e__ = (call);                                                                                \
+        if (e__ != cudaSuccess) {                                                                                \
+            const int code__ = (e__ == cudaErrorMemoryAllocation) ? VRT_E_OOM : VRT_E_CUDA;                      \
+            fail(nullptr, code__, "vrt_init: %s failed: %s", #call, cudaGetErrorString(e__));                    \
+            vrt_deinit(ctx);                                                                                     \
+            return code__;                                                                                       \
+        }                                                                                                        \
+    } while (0)
+
+    INIT_CUDA(cudaSetDevice(cfg->device));
+    INIT_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    ctx->stream = ctx->own_stream;
+    INIT_CUDA(cudaEventCreate(&ctx->ev_begin));
+    INIT_CUDA(cudaEventCreate(&ctx->ev_end));
+    INIT_CUDA(cudaMalloc(&ctx->d_materials, ctx->n_materials * sizeof(vrt_material)));
+    INIT_CUDA(cudaMalloc(&ctx->d_statuses, ctx->n_statuses * 4));
+    INIT_CUDA(cudaMalloc(&ctx->d_brick_indices, ctx->n_brick_indices * 4));
+    INIT_CUDA(cudaMalloc(&ctx->d_occupancy, ctx->n_occupancy));
+    INIT_CUDA(cudaMalloc(&ctx->d_start_indices, ctx->n_start_indices * 4));
+    INIT_CUDA(cudaMalloc(&ctx->d_material_indices, ctx->n_material_indices));
+    INIT_CUDA(cudaMalloc(&ctx->d_fb_own, ctx->fb_bytes));
+    INIT_CUDA(cudaMalloc(&ctx->d_tile_counter, 8));
+    ctx->d_fb = ctx->d_fb_own;
+    ctx->h_materials = new (std::nothrow) vrt_material[ctx->n_materials]();
+    if (!ctx->h_materials) {
+        vrt_deinit(ctx);
+        return fail(nullptr, VRT_E_OOM, "vrt_init: host allocation failed");
+    }
+    // Same initial contents as Grid.init gives the host arrays (Grid.zig:45-64); the reference leaves
+    // the device buffer uninitialised until the first transfer.
+    INIT_CUDA(cudaMemsetAsync(ctx->d_materials, 0, ctx->n_materials * sizeof(vrt_material), ctx->stream));
+    INIT_CUDA(cudaMemsetAsync(ctx->d_statuses, 0, ctx->n_statuses * 4, ctx->stream));
+    INIT_CUDA(cudaMemsetAsync(ctx->d_brick_indices, 0, ctx->n_brick_indices * 4, ctx->stream));
+    INIT_CUDA(cudaMemsetAsync(ctx->d_occupancy, 0, ctx->n_occupancy, ctx->stream));
+    INIT_CUDA(cudaMemsetAsync(ctx->d_start_indices, 0xff, ctx->n_start_indices * 4, ctx->stream));
+    INIT_CUDA(cudaMemsetAsync(ctx->d_material_indices, 0, ctx->n_material_indices, ctx->stream));
+    INIT_CUDA(cudaMemsetAsync(ctx->d_fb_own, 0, ctx->fb_bytes, ctx->stream));
+    INIT_CUDA(cudaMemsetAsync(ctx->d_tile_counter, 0, 8, ctx->stream));
+    if (cfg->brick_dim == 4) INIT_CUDA(cudaMalloc(&ctx->d_occ_dense, cfg->n_bricks * 8));
+    if (cfg->flags & VRT_FLAG_AOV) {
+        INIT_CUDA(cudaMalloc(&ctx->d_aov, (size_t)cfg->width * cfg->height * sizeof(vrt_aov)));
+        INIT_CUDA(cudaMalloc(&ctx->d_counters, 8 * sizeof(unsigned long long)));
+        INIT_CUDA(cudaMemsetAsync(ctx->d_aov, 0, (size_t)cfg->width * cfg->height * sizeof(vrt_aov), ctx->stream));
+        INIT_CUDA(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
+    }
+    INIT_CUDA(cudaStreamSynchronize(ctx->stream));
+#undef INIT_CUDA
+    *out_ctx = ctx;
+    return VRT_OK;
+}
+
+void vrt_deinit(vrt_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->cfg.device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);  // ComputePipeline.deinit waits for the fence first (:386-393)
+    if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
+    if (ctx->peers_open) {
+        for (int r = 0; r < ctx->world; r++)
+            if (r != ctx->rank && ctx->peer_fb[r]) cudaIpcCloseMemHandle(ctx->peer_fb[r]);
+    }
+    cudaFree(ctx->d_materials), cudaFree(ctx->d_statuses), cudaFree(ctx->d_brick_indices), cudaFree(ctx->d_occupancy);
+    cudaFree(ctx->d_start_indices), cudaFree(ctx->d_material_indices), cudaFree(ctx->d_fb_own), cudaFree(ctx->d_aov);
+    cudaFree(ctx->d_counters), cudaFree(ctx->d_occ_dense), cudaFree(ctx->d_status64), cudaFree(ctx->d_coarse);
+    cudaFree(ctx->d_tile_counter);
+    if (ctx->h_pinned_fb) cudaFreeHost(ctx->h_pinned_fb);
+    if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
+    if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete[] ctx->h_materials;
+    delete ctx;
+}
+
+int vrt_upload_grid_state(vrt_ctx* ctx, const vrt_grid_state* state) {
+    if (!ctx) return VRT_E_INVALID;
+    if (!state) return fail(ctx, VRT_E_INVALID, "vrt_upload_grid_state: state is NULL");
+    const uint64_t bricks = (uint64_t)state->dim_x * state->dim_y * state->dim_z;
+    if (bricks == 0 || bricks > ctx->cfg.n_bricks)
+        return fail(ctx, VRT_E_RANGE, "vrt_upload_grid_state: %ux%ux%u bricks exceed the %llu sized at init", state->dim_x, state->dim_y,
+                    state->dim_z, (unsigned long long)ctx->cfg.n_bricks);
+    if (state->dim_x > 4096 || state->dim_y > 4096 || state->dim_z > 4096)
+        return fail(ctx, VRT_E_INVALID, "vrt_upload_grid_state: grid dimension above 4096 bricks");
+    VRT_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    ctx->grid = *state;
+    ctx->have_grid = true;
+    return ensure_accel(ctx);
+}
+
+int vrt_upload_materials(vrt_ctx* ctx, size_t offset, const vrt_material* data, size_t count) {
+    const int rc = upload_range(ctx, ctx ? ctx->d_materials : nullptr, ctx ? ctx->n_materials : 0, offset, data, count, "vrt_upload_materials");
+    if (rc == VRT_OK && count) std::memcpy(ctx->h_materials + offset, data, count * sizeof(vrt_material));
+    return rc;
+}
+int vrt_upload_brick_statuses(vrt_ctx* ctx, size_t offset, const uint32_t* data, size_t count) {
+    const int rc = upload_range(ctx, ctx ? ctx->d_statuses : nullptr, ctx ? ctx->n_statuses : 0, offset, data, count, "vrt_upload_brick_statuses");
+    if (rc == VRT_OK && count) ctx->accel_dirty = true;
+    return rc;
+}
+int vrt_upload_brick_indices(vrt_ctx* ctx, size_t offset, const uint32_t* data, size_t count) {
+    const int rc = upload_range(ctx, ctx ? ctx->d_brick_indices : nullptr, ctx ? ctx->n_brick_indices : 0, offset, data, count, "vrt_upload_brick_indices");
+    if (rc == VRT_OK && count) ctx->accel_dirty = true;
+    return rc;
+}
+int vrt_upload_brick_occupancy(vrt_ctx* ctx, size_t offset, const uint8_t* data, size_t count) {
+    const int rc = upload_range(ctx, ctx ? ctx->d_occupancy : nullptr, ctx ? ctx->n_occupancy : 0, offset, data, count, "vrt_upload_brick_occupancy");
+    if (rc == VRT_OK && count) ctx->accel_dirty = true;
+    return rc;
+}
+int vrt_upload_brick_start_indices(vrt_ctx* ctx, size_t offset, const uint32_t* data, size_t count) {
+    return upload_range(ctx, ctx ? ctx->d_start_indices : nullptr, ctx ? ctx->n_start_indices : 0, offset, data, count, "vrt_upload_brick_start_indices");
+}
+int vrt_upload_material_indices(vrt_ctx* ctx, size_t offset, const uint8_t* data, size_t count) {
+    return upload_range(ctx, ctx ? ctx->d_material_indices : nullptr, ctx ? ctx->n_material_indices : 0, offset, data, count, "vrt_upload_material_indices");
+}
+
+int vrt_trace(vrt_ctx* ctx, const vrt_camera* camera, const vrt_sun* sun) {
+    if (!ctx) return VRT_E_INVALID;
+    if (!camera || !sun) return fail(ctx, VRT_E_INVALID, "vrt_trace: camera or sun is NULL");
+    if (!ctx->have_grid) return fail(ctx, VRT_E_STATE, "vrt_trace: vrt_upload_grid_state has not been called");
+    if (camera->image_width != ctx->cfg.width || camera->image_height != ctx->cfg.height)
+        return fail(ctx, VRT_E_INVALID, "vrt_trace: camera image %ux%u != target image %ux%u", camera->image_width, camera->image_height,
+                    ctx->cfg.width, ctx->cfg.height);
+    if (camera->samples_per_pixel < 1) return fail(ctx, VRT_E_INVALID, "vrt_trace: samples_per_pixel < 1");
+    VRT_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+
+    TraceParams P;
+    fill_params(ctx, camera, sun, P);
+    LaunchInfo info = {0u, 0ull};
+    const bool aov = (ctx->cfg.flags & VRT_FLAG_AOV) != 0;
+    const TraceKernel which = (ctx->cfg.flags & VRT_FLAG_BASELINE) ? KERNEL_REF : KERNEL_TUNED;
+
+    VRT_CUDA(ctx, cudaEventRecord(ctx->ev_begin, ctx->stream));
+    if (which == KERNEL_TUNED && !aov && ctx->accel_dirty) {
+        // Uploads changed statuses / indices / occupancy: rebuild the pyramid before tracing.  Stream order
+        // gives upload -> build -> trace, where the reference has no barrier at all between its staging
+        // copy and the next dispatch (edits land one frame late, Pipeline.zig:540).
+        VRT_CUDA(ctx, launch_build_accel(P, ctx->d_occ_dense, ctx->d_status64, ctx->d_coarse, (size_t)ctx->grid.dim_x * ctx->grid.dim_y * ctx->grid.dim_z,
+                                         ctx->n_super, ctx->stream, &info));
+        ctx->accel_dirty = false;
+    }
+    if (aov) VRT_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
+    VRT_CUDA(ctx, launch_trace(P, which, aov, ctx->stream, &info));
+    ctx->tile_base += info.counter_advance;
+
+    if (ctx->world > 1 && ctx->exchange_mode == VRT_EXCHANGE_ALLGATHER) {
+        if (!ctx->comm) return fail(ctx, VRT_E_STATE, "vrt_trace: world > 1 but vrt_comm_init has not been called");
+        const size_t slab_bytes = (size_t)(ctx->row_end - ctx->row_begin) * ctx->cfg.width * 4;
+        const uint8_t* send = reinterpret_cast<const uint8_t*>(ctx->d_fb) + (size_t)ctx->row_begin * ctx->cfg.width * 4;
+        // in place: the kernel already wrote this rank's slab at its final offset in the full frame
+        const ncclResult_t r = g_nccl.AllGather(send, ctx->d_fb, slab_bytes, ncclUint8, ctx->comm, ctx->stream);
+        if (r != ncclSuccess) return fail(ctx, VRT_E_NCCL, "ncclAllGather failed: %s", g_nccl.GetErrorString(r));
+    }
+    VRT_CUDA(ctx, cudaEventRecord(ctx->ev_end, ctx->stream));
+    ctx->timing_valid = true;
+    ctx->last_launches = info.launches;
+    return VRT_OK;
+}
+
+int vrt_sync(vrt_ctx* ctx) {
+    if (!ctx) return VRT_E_INVALID;
+    VRT_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    VRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VRT_OK;
+}
+
+int vrt_read_framebuffer(vrt_ctx* ctx, uint8_t* rgba8_host, size_t bytes) {
+    if (!ctx) return VRT_E_INVALID;
+    if (!rgba8_host || bytes != ctx->fb_bytes) return fail(ctx, VRT_E_INVALID, "vrt_read_framebuffer: need a %zu-byte buffer", ctx->fb_bytes);
+    VRT_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    VRT_CUDA(ctx, cudaMemcpyAsync(rgba8_host, ctx->d_fb, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    VRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VRT_OK;
+}
+
+int vrt_trace_to_host(vrt_ctx* ctx, const vrt_camera* camera, const vrt_sun* sun, uint8_t* rgba8_host, size_t bytes) {
+    if (!ctx) return VRT_E_INVALID;
+    if (!rgba8_host || bytes != ctx->fb_bytes) return fail(ctx, VRT_E_INVALID, "vrt_trace_to_host: need a %zu-byte buffer", ctx->fb_bytes);
+    const int rc = vrt_trace(ctx, camera, sun);
+    if (rc != VRT_OK) return rc;
+    const size_t off = (size_t)ctx->row_begin * ctx->cfg.width * 4;
+    const size_t n = (ctx->world > 1) ? ctx->fb_bytes : (size_t)(ctx->row_end - ctx->row_begin) * ctx->cfg.width * 4;
+    const size_t from = (ctx->world > 1) ? 0 : off;
+    VRT_CUDA(ctx, cudaMemcpyAsync(rgba8_host + from, reinterpret_cast<const uint8_t*>(ctx->d_fb) + from, n, cudaMemcpyDeviceToHost, ctx->stream));
+    VRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VRT_OK;
+}
+
+int vrt_read_aov(vrt_ctx* ctx, vrt_aov* aov_host, size_t count) {
+    if (!ctx) return VRT_E_INVALID;
+    if (!ctx->d_aov) return fail(ctx, VRT_E_STATE, "vrt_read_aov: context was not created with VRT_FLAG_AOV");
+    if (!aov_host || count != (size_t)ctx->cfg.width * ctx->cfg.height) return fail(ctx, VRT_E_INVALID, "vrt_read_aov: need width*height records");
+    VRT_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    VRT_CUDA(ctx, cudaMemcpyAsync(aov_host, ctx->d_aov, count * sizeof(vrt_aov), cudaMemcpyDeviceToHost, ctx->stream));
+    VRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VRT_OK;
+}
+
+int vrt_get_counters(vrt_ctx* ctx, vrt_counters* out) {
+    if (!ctx) return VRT_E_INVALID;
+    if (!ctx->d_counters) return fail(ctx, VRT_E_STATE, "vrt_get_counters: context was not created with VRT_FLAG_AOV");
+    if (!out) return fail(ctx, VRT_E_INVALID, "vrt_get_counters: out is NULL");
+    unsigned long long h[8];
+    VRT_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    VRT_CUDA(ctx, cudaMemcpyAsync(h, ctx->d_counters, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    VRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    out->rays = h[0], out->primary_hits = h[1], out->shadow_rays = h[2], out->grid_steps = h[3];
+    out->voxel_steps = h[4], out->status_fetches = h[5], out->bricks_entered = h[6], out->hits = h[7];
+    return VRT_OK;
+}
+
+int vrt_last_trace_ms(vrt_ctx* ctx, float* out_ms) {
+    if (!ctx) return VRT_E_INVALID;
+    if (!out_ms) return fail(ctx, VRT_E_INVALID, "vrt_last_trace_ms: out is NULL");
+    if (!ctx->timing_valid) return fail(ctx, VRT_E_STATE, "vrt_last_trace_ms: no trace yet");
+    VRT_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    VRT_CUDA(ctx, cudaEventSynchronize(ctx->ev_end));
+    VRT_CUDA(ctx, cudaEventElapsedTime(out_ms, ctx->ev_begin, ctx->ev_end));
+    return VRT_OK;
+}
+
+int vrt_last_trace_launches(vrt_ctx* ctx, uint32_t* out) {
+    if (!ctx) return VRT_E_INVALID;
+    if (!out) return fail(ctx, VRT_E_INVALID, "vrt_last_trace_launches: out is NULL");
+    *out = ctx->last_launches;
+    return VRT_OK;
+}
+
+int vrt_set_stream(vrt_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return VRT_E_INVALID;
+    VRT_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    VRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    return VRT_OK;
+}
+
+int vrt_attach_framebuffer(vrt_ctx* ctx, void* device_ptr, size_t bytes) {
+    if (!ctx) return VRT_E_INVALID;
+    if (device_ptr && bytes != ctx->fb_bytes) return fail(ctx, VRT_E_INVALID, "vrt_attach_framebuffer: need %zu bytes", ctx->fb_bytes);
+    if (device_ptr && (reinterpret_cast<uintptr_t>(device_ptr) & 3u)) return fail(ctx, VRT_E_INVALID, "vrt_attach_framebuffer: pointer not 4-byte aligned");
+    ctx->d_fb = device_ptr ? static_cast<uint32_t*>(device_ptr) : ctx->d_fb_own;
+    return VRT_OK;
+}
+
+int vrt_framebuffer_device_ptr(vrt_ctx* ctx, void** out_device_ptr) {
+    if (!ctx) return VRT_E_INVALID;
+    if (!out_device_ptr) return fail(ctx, VRT_E_INVALID, "vrt_framebuffer_device_ptr: out is NULL");
+    *out_device_ptr = ctx->d_fb;
+    return VRT_OK;
+}
+
+int vrt_comm_get_unique_id(uint8_t id_out[VRT_NCCL_ID_BYTES]) {
+    static_assert(sizeof(ncclUniqueId) == VRT_NCCL_ID_BYTES, "ncclUniqueId size");
+    if (!id_out) return fail(nullptr, VRT_E_INVALID, "vrt_comm_get_unique_id: out is NULL");
+    if (!load_nccl(g_init_error, sizeof(g_init_error))) return VRT_E_NCCL;
+    ncclUniqueId id;
+    const ncclResult_t r = g_nccl.GetUniqueId(&id);
+    if (r != ncclSuccess) return fail(nullptr, VRT_E_NCCL, "ncclGetUniqueId failed: %s", g_nccl.GetErrorString(r));
+    std::memcpy(id_out, &id, sizeof(id));
+    return VRT_OK;
+}
+
+int vrt_comm_init(vrt_ctx* ctx, int rank, int world, const uint8_t id[VRT_NCCL_ID_BYTES]) {
+    if (!ctx) return VRT_E_INVALID;
+    if (world < 1 || world > 8 || rank < 0 || rank >= world || !id) return fail(ctx, VRT_E_INVALID, "vrt_comm_init: bad rank/world %d/%d", rank, world);
+    const uint32_t rows = ctx->row_end - ctx->row_begin;
+    if (world > 1 && (ctx->cfg.height % (uint32_t)world != 0 || rows != ctx->cfg.height / (uint32_t)world || ctx->row_begin != rows * (uint32_t)rank))
+        return fail(ctx, VRT_E_INVALID, "vrt_comm_init: rank %d of %d must own rows [%u, %u)", rank, world, ctx->cfg.height / world * rank,
+                    ctx->cfg.height / world * (rank + 1));
+    if (!load_nccl(ctx->err, sizeof(ctx->err))) return VRT_E_NCCL;
+    VRT_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    ncclUniqueId nid;
+    std::memcpy(&nid, id, sizeof(nid));
+    const ncclResult_t r = g_nccl.CommInitRank(&ctx->comm, world, nid, rank);
+    if (r != ncclSuccess) return fail(ctx, VRT_E_NCCL, "ncclCommInitRank failed: %s", g_nccl.GetErrorString(r));
+    ctx->rank = rank, ctx->world = world;
+    return VRT_OK;
+}
+
+int vrt_comm_get_ipc_handle(vrt_ctx* ctx, uint8_t handle_out[VRT_IPC_HANDLE_BYTES]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == VRT_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
+    if (!ctx) return VRT_E_INVALID;
+    if (!handle_out) return fail(ctx, VRT_E_INVALID, "vrt_comm_get_ipc_handle: out is NULL");
+    if (ctx->d_fb != ctx->d_fb_own) return fail(ctx, VRT_E_STATE, "vrt_comm_get_ipc_handle: only the context-owned framebuffer can be shared");
+    VRT_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    cudaIpcMemHandle_t h;
+    VRT_CUDA(ctx, cudaIpcGetMemHandle(&h, ctx->d_fb_own));
+    std::memcpy(handle_out, &h, sizeof(h));
+    return VRT_OK;
+}
+
+int vrt_comm_open_peers(vrt_ctx* ctx, int rank, int world, const uint8_t* handles) {
+    if (!ctx) return VRT_E_INVALID;
+    if (world < 1 || world > 8 || rank < 0 || rank >= world || !handles) return fail(ctx, VRT_E_INVALID, "vrt_comm_open_peers: bad arguments");
+    VRT_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    for (int r = 0; r < world; r++) {
+        if (r == rank) {
+            ctx->peer_fb[r] = ctx->d_fb_own;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, handles + (size_t)r * VRT_IPC_HANDLE_BYTES, sizeof(h));
+        VRT_CUDA(ctx, cudaIpcOpenMemHandle(&ctx->peer_fb[r], h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    ctx->rank = rank, ctx->world = world;
+    ctx->peers_open = true;
+    return VRT_OK;
+}
+
+int vrt_comm_set_exchange(vrt_ctx* ctx, uint32_t mode) {
+    if (!ctx) return VRT_E_INVALID;
+    if (mode != VRT_EXCHANGE_ALLGATHER && mode != VRT_EXCHANGE_PEER_STORE) return fail(ctx, VRT_E_INVALID, "vrt_comm_set_exchange: unknown mode %u", mode);
+    if (mode == VRT_EXCHANGE_PEER_STORE && !ctx->peers_open) return fail(ctx, VRT_E_STATE, "vrt_comm_set_exchange: call vrt_comm_open_peers first");
+    ctx->exchange_mode = mode;
+    return VRT_OK;
+}
+
+}  // extern "C"
