@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py — Mrays/s of the voxel ray-tracing hot path on B200 (contract: see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C3] [--impl ours|reference]
+
+A "step" is one frame of the workload: every pixel's primary ray marched through the brick grid plus, for C3/C5, one
+sun ray per primary hit (brick_raytracer.comp main()).  `value` counts rays actually cast (primary + sun) per second
+of device time with the grid resident in HBM; `e2e` is the same frame through vrt_trace_to_host() with the camera/sun
+blocks coming from host memory and the RGBA8 frame landing in pinned host memory inside the timed region.
+N > 1: one process per GPU (torchrun), the image rows are tiled across ranks and exchanged after the trace kernel;
+time is the max over ranks and rays are summed (strong scaling: the frame is fixed).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+POSE0 = dict(origin=(0.0, -10.0, 28.0), euler_deg=(25.0, 0.0, 0.0))
+L2_FLUSH_BYTES = 256 << 20  # > 126 MB L2
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--workload", default="C3", choices=["C1", "C2", "C3", "C4", "C5"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--exchange", default="allgather", choices=["allgather", "peer"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--baseline-kernel", action="store_true", help="time the reference-shape kernel instead of the tuned one")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """SM clock + throttle reasons sampled every few ms during the timed region (NVML)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for n, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def oracle_scene(wl):
+    """Grid arrays for the oracle.  The grid builder is libvrt_host (product); the oracle only traces."""
+    import zig_vulkan_b200 as zv
+    from zig_vulkan_b200 import scenes
+    from oracle import orc
+
+    grid = scenes.build_grid(wl.n_voxels, wl.brick_dim, brick_alloc=alloc_for(wl))
+    mats = zv.terrain_materials()
+    return grid, mats, orc.OracleScene.from_grid(grid, mats)
+
+
+def alloc_for(wl):
+    from zig_vulkan_b200 import scenes
+
+    if wl.n_voxels >= 1024:  # keep material_indices (brick_alloc * brick_dim^3 bytes) off the GiB scale
+        return scenes.count_bricks(wl.n_voxels, wl.brick_dim)
+    return 0
+
+
+def time_oracle(wl, steps, warmup, budget_s=None):
+    from zig_vulkan_b200 import scenes
+
+    grid, mats, sc = oracle_scene(wl)
+    cam = scenes.camera(wl.width, wl.height, **POSE0)
+    sun = scenes.sun(wl.sun)
+    cores = os.cpu_count() or 1
+    rays = None
+    for _ in range(warmup):
+        _, _, cnt = sc.render(cam, sun, threads=cores)
+        rays = cnt["rays"]
+    times = []
+    t_begin = time.perf_counter()
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        _, _, cnt = sc.render(cam, sun, threads=cores)
+        times.append(time.perf_counter() - t0)
+        rays = cnt["rays"]
+        if budget_s is not None and time.perf_counter() - t_begin > budget_s:
+            break
+    return rays, times, cores
+
+
+def run_reference(args):
+    """The reference's own algorithm on the host cores.  The reference ships this path only as a GLSL compute shader
+    and nothing of it builds here (no zig / glslc / Vulkan), so this is the oracle port, all host threads."""
+    from zig_vulkan_b200 import scenes
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = scenes.WORKLOADS[args.workload]
+    steps = min(args.steps, 60)
+    rays, times, cores = time_oracle(wl, steps, min(args.warmup, 3), budget_s=150.0)
+    total = sum(times)
+    value = rays * len(times) / total / 1e6
+    line = {
+        "impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": len(times), "warmup": min(args.warmup, 3),
+        "ms_per_step": total / len(times) * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": f"{wl.name}: {wl.description}", "pose": "pose0", "rays_per_step": rays},
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": "port",
+                         "sample": f"{len(times)} full {wl.width}x{wl.height} frames, all rows, oracle/liboracle.so with {cores} threads"},
+        "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun, one rank per GPU
+        port = 29500 + (os.getpid() % 2000)
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+               "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import zig_vulkan_b200 as zv
+    from zig_vulkan_b200 import ffi, scenes
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the trace path has no CPU fallback (use --impl reference for the host-core baseline)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    wl = scenes.WORKLOADS[args.workload]
+    W, H = wl.width, wl.height
+    if H % world != 0:
+        raise SystemExit(f"image height {H} is not divisible by {world} ranks")
+    rows = (rank * (H // world), (rank + 1) * (H // world))
+    n_pixels = W * H
+
+    grid = scenes.build_grid(wl.n_voxels, wl.brick_dim, brick_alloc=alloc_for(wl))
+    mats = zv.terrain_materials()
+    cam = scenes.camera(W, H, **POSE0)
+    sun = scenes.sun(wl.sun)
+    brick_bytes = wl.brick_dim ** 3 // 8
+
+    flags = ffi.VRT_FLAG_BASELINE if args.baseline_kernel else 0
+    ctx = ffi.Context(W, H, len(grid.brick_indices), brick_dim=wl.brick_dim, n_brick_alloc=grid.brick_alloc, device=local_rank, flags=flags,
+                      rows=rows if world > 1 else (0, 0))
+    stream = torch.cuda.Stream(dev)  # a non-default stream: handle 0 would mean "restore the ctx's own stream"
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)  # torch.cuda.Event only sees torch's current stream
+    ctx.upload_grid(grid, mats)
+
+    if world > 1:
+        if rank == 0:
+            uid = torch.frombuffer(bytearray(ffi.Context.comm_unique_id()), dtype=torch.uint8).to(dev)
+        else:
+            uid = torch.empty(ffi.VRT_NCCL_ID_BYTES, dtype=torch.uint8, device=dev)
+        dist.broadcast(uid, 0)
+        ctx.comm_init(rank, world, bytes(uid.cpu().numpy().tobytes()))
+        if args.exchange == "peer":
+            mine = torch.frombuffer(bytearray(ctx.comm_ipc_handle()), dtype=torch.uint8).to(dev)
+            allh = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(allh, mine)
+            ctx.comm_open_peers(rank, world, b"".join(bytes(h.cpu().numpy().tobytes()) for h in allh))
+            ctx.comm_set_exchange(ffi.VRT_EXCHANGE_PEER_STORE)
+
+    # ray / request-byte counters of this rank's rows from the reference-shape kernel (identical to the oracle's)
+    cctx = ffi.Context(W, H, len(grid.brick_indices), brick_dim=wl.brick_dim, n_brick_alloc=grid.brick_alloc, device=local_rank,
+                       flags=ffi.VRT_FLAG_AOV | ffi.VRT_FLAG_BASELINE, rows=rows if world > 1 else (0, 0))
+    cctx.upload_grid(grid, mats)
+    cctx.trace(cam, sun)
+    counters = cctx.counters()
+    cctx.close()
+    my_rays = counters["rays"]
+    my_alg_bytes = 4 * (rows[1] - rows[0]) * W + 4 * counters["status_fetches"] + (4 + brick_bytes) * counters["bricks_entered"] + 25 * counters["hits"]
+
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---------------------------------------------------------------- device-resident timing
+    for _ in range(max(args.warmup, 3)):
+        flush.fill_(1)
+        ctx.trace(cam, sun)
+    launches_per_step = ctx.last_trace_launches()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF)  # L2 flush between timed iterations (outside the per-step events)
+        starts[i].record(stream)
+        ctx.trace(cam, sun)
+        ends[i].record(stream)
+    barrier()
+    wall_ms = (time.perf_counter() - t_wall0) * 1e3
+    clocks = sampler.stop()
+    step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+    total_ms = float(sum(step_ms))
+
+    # ---------------------------------------------------------------- end-to-end through the C ABI with host buffers
+    host_frame = torch.empty(n_pixels * 4, dtype=torch.uint8).pin_memory()
+    e2e_s = 0.0
+    for i in range(3 + args.steps):
+        flush.fill_(i & 0xFF)
+        barrier()
+        t0 = time.perf_counter()
+        if rank == 0:
+            ctx.trace_to_host(cam, sun, out_ptr=host_frame.data_ptr())  # camera+sun: host structs; frame -> pinned host memory
+        else:
+            ctx.trace(cam, sun)
+            ctx.sync()
+        if world > 1:
+            dist.barrier()
+        if i >= 3:
+            e2e_s += time.perf_counter() - t0
+
+    t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev)
+    r = torch.tensor([float(my_rays), float(my_alg_bytes)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(r, op=dist.ReduceOp.SUM)
+    total_ms, e2e_s = float(t[0]), float(t[1])
+    rays, alg_bytes = float(r[0]), float(r[1])
+
+    if rank == 0:
+        peak, peak_kind = peaks()
+        ms_per_step = total_ms / args.steps
+        value = rays / (ms_per_step * 1e-3) / 1e6
+        # roofline of the dominant kernel = the trace kernel; at N=1 the step IS that one launch
+        achieved = (my_alg_bytes / (ms_per_step * 1e-3)) / 1e9
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                traffic = json.load(f).get(args.workload)
+        except Exception:
+            pass
+        line = {
+            "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {
+                "workload": f"{wl.name}: {wl.description}", "pose": "pose0 origin (0,-10,28) pitch 25deg", "rays_per_step": int(rays),
+                "grid_bricks": len(grid.brick_indices), "active_bricks": grid.active_bricks, "l2": f"flushed between steps ({L2_FLUSH_BYTES >> 20} MiB fill)",
+                "kernel": "baseline" if args.baseline_kernel else "tuned", "partition": f"{world} row slabs" if world > 1 else "whole frame",
+                "exchange": args.exchange if world > 1 else "none",
+            },
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "peak_kind": peak_kind, "algorithmic_bytes_per_launch": int(my_alg_bytes), "kernel_ms": ms_per_step,
+                         "note": "request-byte model of the reference algorithm (DESIGN.md); rank 0's launch"},
+            "e2e": {"value": rays * args.steps / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 128, "d2h_bytes_per_step": n_pixels * 4,
+                    "ms_per_step": e2e_s / args.steps * 1e3},
+            "gpu_launches": launches_per_step * args.steps, "wall_ms": wall_ms, "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            crays, ctimes, cores = time_oracle(wl, 12, 1, budget_s=20.0)
+            best = min(ctimes)
+            line["cpu_baseline"] = {"value": crays / best / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
+                                    "sample": f"best of {len(ctimes)} full {W}x{H} frames of the same workload, oracle/liboracle.so, {cores} threads"}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -669,6 +669,14 @@ int orc_grid_insert(orc_grid* g, uint32_t x, uint32_t y, uint32_t z, uint8_t mat
     return 0;
 }
 
+int orc_grid_insert_many(orc_grid* g, const uint32_t* xyzm, size_t n) {
+    for (size_t i = 0; i < n; i++) {
+        const int rc = orc_grid_insert(g, xyzm[4 * i], xyzm[4 * i + 1], xyzm[4 * i + 2], (uint8_t)xyzm[4 * i + 3]);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
 uint32_t orc_grid_active_bricks(const orc_grid* g) { return g->active_bricks; }
 void orc_grid_get_state(const orc_grid* g, vrt_grid_state* out) { *out = g->state; }
 const uint32_t* orc_grid_statuses(const orc_grid* g, uint64_t* n) { if (n) *n = g->statuses.size(); return g->statuses.data(); }

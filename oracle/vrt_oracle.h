@@ -30,6 +30,8 @@ orc_grid* orc_grid_create(uint32_t dim_x, uint32_t dim_y, uint32_t dim_z, uint32
 void orc_grid_destroy(orc_grid* g);
 /* Grid.insert (Grid.zig:129-194).  0 ok; -1 coordinate out of range; -2 out of brick / material capacity. */
 int orc_grid_insert(orc_grid* g, uint32_t x, uint32_t y, uint32_t z, uint8_t material);
+/* n packed {x,y,z,material} uint32 quadruples; stops at the first failure. */
+int orc_grid_insert_many(orc_grid* g, const uint32_t* xyzm, size_t n);
 uint32_t orc_grid_active_bricks(const orc_grid* g);
 void orc_grid_get_state(const orc_grid* g, vrt_grid_state* out);
 const uint32_t* orc_grid_statuses(const orc_grid* g, uint64_t* count);

@@ -1,0 +1,51 @@
+"""Regenerates tests/golden/*.npz from the CPU oracle.  Run from the repo root: python tests/golden/make_golden.py
+
+PARITY UNPINNED: the reference has no executable form of this path here (GLSL only; no zig/glslc/Vulkan), so these
+vectors freeze the ORACLE's output (itself checked by the hand-computed cases in tests/test_oracle_kat.py).  They guard
+against regressions of the oracle and give the GPU tests fixed targets that do not depend on the host CPU.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+import zig_vulkan_b200 as zv  # noqa: E402
+from zig_vulkan_b200 import scenes  # noqa: E402
+from oracle import orc  # noqa: E402
+
+POSE0 = dict(origin=(0.0, -10.0, 28.0), euler_deg=(25.0, 0.0, 0.0))
+
+# name -> (n_voxels, brick_dim, width, height, sun, sun_radius, spp, max_bounce, pose)
+CASES = {
+    "c1_64_256x256": (64, 4, 256, 256, False, 0.0, 1, 0, POSE0),
+    "c3_128_320x180_sun": (128, 4, 320, 180, True, 0.0, 1, 0, POSE0),
+    "look_64_160x90_spp2_bounce2": (64, 4, 160, 90, True, 5.0, 2, 2, POSE0),
+    "bd8_64_160x90_sun": (64, 8, 160, 90, True, 0.0, 1, 0, POSE0),
+    "bd16_128_160x90_sun": (128, 16, 160, 90, True, 0.0, 1, 0, POSE0),
+    "inside_64_160x90_sun": (64, 4, 160, 90, True, 0.0, 1, 0, dict(origin=(3.0, 4.0, 5.0), euler_deg=(-10.0, 140.0, 0.0))),
+}
+
+
+def render_case(case):
+    n, bd, w, h, sun_on, radius, spp, bounce, pose = case
+    grid = scenes.build_grid(n, brick_dim=bd)
+    sc = orc.OracleScene.from_grid(grid, zv.terrain_materials())
+    cam = scenes.camera(w, h, spp=spp, max_bounce=bounce, **pose)
+    sun = scenes.sun(sun_on, radius)
+    img, aov, cnt = sc.render(cam, sun, aov=True)
+    return grid, cam, sun, img, aov, cnt
+
+
+def main():
+    out_dir = os.path.dirname(os.path.abspath(__file__))
+    for name, case in CASES.items():
+        _, _, _, img, aov, cnt = render_case(case)
+        np.savez_compressed(os.path.join(out_dir, name + ".npz"), rgba=img, aov=aov, counters=np.array([cnt[k] for k in orc.COUNTER_NAMES], dtype=np.uint64))
+        print(name, cnt)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,93 @@
+"""The C ABI: struct layouts equal the reference's extern structs, and the built libraries export every symbol the
+headers declare.  No compute calls here (no GPU needed)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from zig_vulkan_b200 import ffi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_camera_device_layout():
+    # Camera.zig:183-193 — Zig @Vector(3,f32) is 16 bytes wide and 16-byte aligned; GLSL mirror brick_raytracer.comp:58-68
+    assert C.sizeof(ffi.CameraDevice) == 96
+    off = {n: getattr(ffi.CameraDevice, n).offset for n, *_ in ffi.CameraDevice._fields_}
+    assert off["image_width"] == 0 and off["image_height"] == 4
+    assert off["horizontal"] == 16 and off["vertical"] == 32 and off["lower_left_corner"] == 48 and off["origin"] == 64
+    assert off["samples_per_pixel"] == 80 and off["max_bounce"] == 84
+
+
+def test_sun_device_layout():
+    # Sun.zig:13-18, pushed at offset 96 (ComputePipeline.zig:259-263, 497-505)
+    assert C.sizeof(ffi.SunDevice) == 32
+    assert ffi.SunDevice.position.offset == 0 and ffi.SunDevice.enabled.offset == 12
+    assert ffi.SunDevice.color.offset == 16 and ffi.SunDevice.radius.offset == 28
+    assert C.sizeof(ffi.CameraDevice) + C.sizeof(ffi.SunDevice) == 128
+
+
+def test_grid_state_layout():
+    # State.zig:60-79 == BrickGridState UBO brick_raytracer.comp:79-95
+    assert C.sizeof(ffi.GridState) == 64
+    assert ffi.GridState.dim_x.offset == 12
+    assert ffi.GridState.min_point_base_t.offset == 32 and ffi.GridState.max_point_scale.offset == 48
+
+
+def test_material_layout():
+    # gpu_types.zig:16-32: 20 bytes, std430 stride 20
+    assert C.sizeof(ffi.Material) == 20
+    assert ffi.MATERIAL_DTYPE.itemsize == 20
+    assert ffi.Material.type_data.offset == 16
+
+
+def test_aov_and_config_layout():
+    assert C.sizeof(ffi.Aov) == 64 and ffi.AOV_DTYPE.itemsize == 64
+    assert C.sizeof(ffi.Counters) == 64
+    assert C.sizeof(ffi.Config) == 56
+
+
+def _declared(header):
+    text = open(os.path.join(ROOT, "include", header)).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(vrt_[a-z0-9_]+)\s*\(", text)) - {"vrt_emit_fn"})
+
+
+@pytest.mark.parametrize("header,libname,table", [("vrt.h", "libvrt.so", ffi.VRT_SYMBOLS), ("vrt_host.h", "libvrt_host.so", ffi.VRT_HOST_SYMBOLS)])
+def test_library_exports_every_declared_symbol(header, libname, table):
+    names = _declared(header)
+    assert len(names) >= 20
+    dll = C.CDLL(os.path.join(ROOT, "zig_vulkan_b200", libname), mode=C.RTLD_GLOBAL) if libname == "libvrt.so" else ffi.host_lib()
+    for n in names:
+        assert hasattr(dll, n), f"{libname} does not export {n} declared in include/{header}"
+    # the ctypes table binds exactly the declared set, so a header change cannot silently go unbound
+    assert sorted(table) == names
+
+
+def test_init_rejects_bad_config_without_touching_the_gpu():
+    l = ffi.lib()
+    h = C.c_void_p()
+    cfg = ffi.Config(C.sizeof(ffi.Config), ffi.VRT_ABI_VERSION, 0, 0, 4, 256, 64, 64, 0, 0, 0, 0)
+    assert l.vrt_init(C.byref(h), C.byref(cfg)) == -1  # VRT_E_INVALID: zero-sized image
+    assert b"image size" in l.vrt_last_error(None)
+    cfg = ffi.Config(C.sizeof(ffi.Config) - 4, ffi.VRT_ABI_VERSION, 16, 16, 4, 256, 64, 64, 0, 0, 0, 0)
+    assert l.vrt_init(C.byref(h), C.byref(cfg)) == -1
+    assert b"ABI mismatch" in l.vrt_last_error(None)
+    cfg = ffi.Config(C.sizeof(ffi.Config), ffi.VRT_ABI_VERSION, 16, 16, 5, 256, 64, 64, 0, 0, 0, 0)
+    assert l.vrt_init(C.byref(h), C.byref(cfg)) == -1
+    assert b"brick_dim" in l.vrt_last_error(None)
+    assert l.vrt_init(None, C.byref(cfg)) == -1
+    # NULL handles never crash
+    assert l.vrt_trace(None, None, None) == -1
+    assert l.vrt_sync(None) == -1
+    l.vrt_deinit(None)
+
+
+def test_no_silent_cpu_fallback(has_cuda):
+    """Without a CUDA device vrt_init must fail loudly (the product has no CPU path)."""
+    if has_cuda:
+        pytest.skip("a GPU is present")
+    with pytest.raises(ffi.VrtError) as e:
+        ffi.Context(16, 16, 64)
+    assert e.value.code == -4 and "no CPU fallback" in str(e.value)

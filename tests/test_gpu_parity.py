@@ -1,0 +1,279 @@
+"""-m gpu: the CUDA path through the C ABI against the oracle on the same seeded inputs, plus size-independent
+properties at BASELINE.json's full sizes.  Bar: hit records (flag, grid/voxel index, material, t, point, normal) and the
+RGBA8 image bit-exact (SURVEY.md §8c allows ±1 LSB on RGBA; the shared FP discipline makes it 0 in practice)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import zig_vulkan_b200 as zv
+from zig_vulkan_b200 import ffi, scenes
+from oracle import orc
+
+pytestmark = pytest.mark.gpu
+POSE0 = dict(origin=(0.0, -10.0, 28.0), euler_deg=(25.0, 0.0, 0.0))
+EXACT = ("flags", "grid_index", "voxel_index", "material", "shadow_grid_index", "shadow_voxel_index")
+
+
+def trace(grid, mats, cam, sun, flags=0, rows=(0, 0)):
+    ctx = ffi.Context(cam.image_width, cam.image_height, len(grid.brick_indices), brick_dim=grid.brick_dim, n_brick_alloc=grid.brick_alloc, flags=flags, rows=rows)
+    ctx.upload_grid(grid, mats)
+    ctx.trace(cam, sun)
+    img = ctx.read_framebuffer()
+    aov = ctx.read_aov() if flags & ffi.VRT_FLAG_AOV else None
+    cnt = ctx.counters() if flags & ffi.VRT_FLAG_AOV else None
+    ctx.close()
+    return img, aov, cnt
+
+
+def assert_same(img, aov, ref_img, ref_aov):
+    assert np.array_equal(img, ref_img), f"{(img != ref_img).any(axis=2).sum()} pixels differ"
+    if aov is not None:
+        for f in EXACT:
+            assert np.array_equal(aov[f], ref_aov[f]), f
+        for f in ("t", "point", "normal"):
+            assert np.array_equal(aov[f].view(np.uint32), ref_aov[f].view(np.uint32)), f
+
+
+@pytest.mark.parametrize("kernel", [0, ffi.VRT_FLAG_BASELINE], ids=["tuned", "baseline"])
+@pytest.mark.parametrize("seed", [420, 7])
+@pytest.mark.parametrize("pose", range(0, 11, 2))
+def test_differential_sweep(materials, kernel, seed, pose):
+    """Seeded scene x the reference's fly-through poses (Benchmark.zig:141-173), sun on."""
+    grid = scenes.build_grid(128, seed=seed)
+    origin, yaw = scenes.sweep_poses(11)[pose]
+    cam = scenes.camera_from_pose(200, 120, origin, yaw)
+    sun = scenes.sun(True)
+    ref_img, ref_aov, ref_cnt = orc.OracleScene.from_grid(grid, materials).render(cam, sun, aov=True)
+    img, aov, cnt = trace(grid, materials, cam, sun, kernel | ffi.VRT_FLAG_AOV)
+    assert_same(img, aov, ref_img, ref_aov)
+    assert cnt["rays"] == ref_cnt["rays"] and cnt["hits"] == ref_cnt["hits"] and cnt["grid_steps"] == ref_cnt["grid_steps"]
+    img2, _, _ = trace(grid, materials, cam, sun, kernel)
+    assert np.array_equal(img2, ref_img)
+
+
+@pytest.mark.parametrize("kernel", [0, ffi.VRT_FLAG_BASELINE], ids=["tuned", "baseline"])
+@pytest.mark.parametrize("w,h", [(1, 1), (2, 2), (7, 5), (33, 9), (130, 3), (8, 4), (257, 31)])
+def test_ragged_image_sizes(materials, kernel, w, h):
+    """Sizes that are not multiples of the 8x4 warp tile / 4-texel vector store, down to a single pixel (the 1x1 frame
+    divides by image_width-1 = 0 exactly as the shader does, :168)."""
+    grid = scenes.build_grid(64)
+    cam = scenes.camera(w, h, **POSE0)
+    sun = scenes.sun(True)
+    ref_img, ref_aov, _ = orc.OracleScene.from_grid(grid, materials).render(cam, sun, aov=True)
+    img, aov, _ = trace(grid, materials, cam, sun, kernel | ffi.VRT_FLAG_AOV)
+    if (w, h) == (1, 1):
+        assert img.shape == (1, 1, 4)  # u = 0/0 = NaN on both sides; only require that nothing crashes and alpha is set
+        assert img[0, 0, 3] == 255 and ref_img[0, 0, 3] == 255
+        return
+    assert_same(img, aov, ref_img, ref_aov)
+    img2, _, _ = trace(grid, materials, cam, sun, kernel)
+    assert np.array_equal(img2, ref_img)
+
+
+@pytest.mark.parametrize("kernel", [0, ffi.VRT_FLAG_BASELINE], ids=["tuned", "baseline"])
+def test_non_cubic_grid_and_reference_default_dims(materials, kernel):
+    """The reference's own grid shape: 128x64x128 bricks at scale 0.5, min (-32,-16,-32) (main.zig:77-81), scaled down 4x."""
+    g = ffi.Grid((32, 16, 32), min_point=(-32.0, -16.0, -32.0), scale=2.0)
+    rng = np.random.default_rng(3)
+    n = 30000
+    xyzm = np.stack([rng.integers(0, 128, n), rng.integers(0, 24, n), rng.integers(0, 128, n), rng.integers(0, 8, n)], axis=1).astype(np.uint32)
+    assert g.insert_many(xyzm) == 0
+    cam = scenes.camera(160, 90, origin=(0.0, -6.0, 20.0), euler_deg=(15.0, 20.0, 0.0))
+    sun = scenes.sun(True)
+    ref_img, ref_aov, _ = orc.OracleScene.from_grid(g, materials).render(cam, sun, aov=True)
+    img, aov, _ = trace(g, materials, cam, sun, kernel | ffi.VRT_FLAG_AOV)
+    assert_same(img, aov, ref_img, ref_aov)
+
+
+@pytest.mark.parametrize("kernel", [0, ffi.VRT_FLAG_BASELINE], ids=["tuned", "baseline"])
+def test_empty_and_full_grids(materials, kernel):
+    cam = scenes.camera(64, 40, origin=(0.0, 0.0, 40.0))
+    sun = scenes.sun(True)
+    empty = ffi.Grid((8, 8, 8), min_point=(-8.0, -8.0, -8.0), scale=2.0)
+    ref_img, ref_aov, cnt = orc.OracleScene.from_grid(empty, materials).render(cam, sun, aov=True)
+    assert cnt["hits"] == 0
+    img, aov, _ = trace(empty, materials, cam, sun, kernel | ffi.VRT_FLAG_AOV)
+    assert_same(img, aov, ref_img, ref_aov)
+    full = ffi.Grid((4, 4, 4), min_point=(-8.0, -8.0, -8.0), scale=4.0)
+    xs = np.arange(16, dtype=np.uint32)
+    xyz = np.stack(np.meshgrid(xs, xs, xs, indexing="ij"), axis=-1).reshape(-1, 3)
+    assert full.insert_many(np.concatenate([xyz, (xyz.sum(axis=1, keepdims=True) % 8).astype(np.uint32)], axis=1)) == 0
+    ref_img, ref_aov, cnt = orc.OracleScene.from_grid(full, materials).render(cam, sun, aov=True)
+    assert cnt["primary_hits"] > 0
+    img, aov, _ = trace(full, materials, cam, sun, kernel | ffi.VRT_FLAG_AOV)
+    assert_same(img, aov, ref_img, ref_aov)
+
+
+@pytest.mark.parametrize("kernel", [0, ffi.VRT_FLAG_BASELINE], ids=["tuned", "baseline"])
+def test_full_path_trace_modes(materials, kernel):
+    """The reference's default look (main.zig:125-131: spp 2, max_bounce 2, sun disc radius 5): bounces through water
+    (dielectric -> ignore type, :427,587), metal and lambert scatter, jittered samples.  Both sides evaluate the shader's
+    sin-hash with the same deterministic sine, so even this mode is bit-exact."""
+    grid = scenes.build_grid(128)
+    for spp, bounce, radius in [(2, 2, 5.0), (1, 3, 0.0), (3, 1, 2.0)]:
+        cam = scenes.camera(192, 108, spp=spp, max_bounce=bounce, **POSE0)
+        sun = scenes.sun(True, radius)
+        ref_img, ref_aov, ref_cnt = orc.OracleScene.from_grid(grid, materials).render(cam, sun, aov=True)
+        img, aov, cnt = trace(grid, materials, cam, sun, kernel | ffi.VRT_FLAG_AOV)
+        assert_same(img, aov, ref_img, ref_aov)
+        assert cnt["rays"] == ref_cnt["rays"] and cnt["shadow_rays"] == ref_cnt["shadow_rays"]
+    cam = scenes.camera(192, 108, spp=2, max_bounce=2, **POSE0)
+    ref_img, _, _ = orc.OracleScene.from_grid(grid, materials).render(cam, scenes.sun(False))
+    img, _, _ = trace(grid, materials, cam, scenes.sun(False), kernel)
+    assert np.array_equal(img, ref_img)
+
+
+def test_material_type_none_disables_the_ignore_shortcut(materials):
+    """A material of type 3 (MAT_NONE) with type_data 1.0 is ignored by every camera/sun ray (:427 with CreateRay's
+    ignore type 3 and ir 1.0); the tuned kernel must then evaluate the test it normally skips."""
+    mats = materials.copy()
+    mats[5]["type"], mats[5]["type_data"] = 3, 1.0
+    grid = scenes.build_grid(64)
+    cam = scenes.camera(160, 90, **POSE0)
+    sun = scenes.sun(True)
+    ref_img, ref_aov, _ = orc.OracleScene.from_grid(grid, mats).render(cam, sun, aov=True)
+    base_img, _, _ = orc.OracleScene.from_grid(grid, materials).render(cam, sun)
+    assert not np.array_equal(ref_img, base_img)
+    for kernel in (0, ffi.VRT_FLAG_BASELINE):
+        img, aov, _ = trace(grid, mats, cam, sun, kernel | ffi.VRT_FLAG_AOV)
+        assert_same(img, aov, ref_img, ref_aov)
+
+
+def test_row_slabs_tile_the_frame(materials):
+    """vrt_config.row_begin/row_end (the multi-GPU partition): the slabs of 1, 2, 4 and 8 'ranks' assemble the single-GPU frame."""
+    grid = scenes.build_grid(64)
+    cam = scenes.camera(128, 72, **POSE0)
+    sun = scenes.sun(True)
+    whole, _, _ = trace(grid, materials, cam, sun)
+    for world in (2, 4, 8):
+        out = np.zeros_like(whole)
+        for r in range(world):
+            r0, r1 = r * 72 // world, (r + 1) * 72 // world
+            part, _, _ = trace(grid, materials, cam, sun, rows=(r0, r1))
+            out[r0:r1] = part[r0:r1]
+            assert not part[:r0].any() and not part[r1:].any()  # a rank only writes its own rows
+        assert np.array_equal(out, whole)
+
+
+def test_partial_uploads_and_edit(materials):
+    """Edits shipped as dirty ranges (VoxelRT.updateGridDelta, VoxelRT.zig:107-172) through the Renderer facade."""
+    grid = scenes.build_grid(64)
+    r = ffi.Renderer(grid, width=160, height=90, samples_per_pixel=1, max_bounce=0, origin=POSE0["origin"], sun_enabled=True, sun_radius=0.0, sun_animate=False)
+    r.camera.set_euler_deg(*POSE0["euler_deg"])
+    r.push_materials(materials)
+    r.update_grid_delta()
+    img0 = r.draw_to_host()
+    ref0, _, _ = orc.OracleScene.from_grid(grid, materials).render(r.camera.device, r.sun.device)
+    assert np.array_equal(img0, ref0)
+    # drop a pillar of iron in front of the camera, upload only the dirty ranges, redraw
+    for y in range(20, 60):
+        for x in range(30, 34):
+            for z in range(50, 54):
+                assert grid.insert(x, y, z, 7) == 0
+    active, lo, hi = grid.delta(2)
+    assert active == 1 and hi - lo < len(grid.occupancy)
+    r.update_grid_delta()
+    assert grid.delta(2)[0] == 0
+    img1 = r.draw_to_host()
+    ref1, _, _ = orc.OracleScene.from_grid(grid, materials).render(r.camera.device, r.sun.device)
+    assert np.array_equal(img1, ref1) and not np.array_equal(img1, img0)
+    r.close()
+
+
+def test_error_paths(materials):
+    grid = scenes.build_grid(64)
+    ctx = ffi.Context(64, 36, len(grid.brick_indices))
+    cam = scenes.camera(64, 36, **POSE0)
+    with pytest.raises(ffi.VrtError) as e:  # trace before transferGridState
+        ctx.trace(cam, scenes.sun(False))
+    assert e.value.code == -6
+    ctx.upload_grid_state(grid.state)
+    with pytest.raises(ffi.VrtError) as e:  # past the end of the buffer sized at init
+        ctx.upload_brick_indices(len(grid.brick_indices) - 1, np.zeros(2, dtype=np.uint32))
+    assert e.value.code == -3
+    with pytest.raises(ffi.VrtError) as e:
+        ctx.trace(scenes.camera(32, 36, **POSE0), scenes.sun(False))  # camera image != target image
+    assert e.value.code == -1
+    with pytest.raises(ffi.VrtError) as e:
+        ctx.read_aov()
+    assert e.value.code == -6
+    big = ffi.GridState.from_buffer_copy(bytes(grid.state))
+    big.dim_x = 999
+    with pytest.raises(ffi.VrtError) as e:
+        ctx.upload_grid_state(big)
+    assert e.value.code == -3
+    ctx.upload_grid(grid, materials)
+    ctx.trace(cam, scenes.sun(False))
+    assert ctx.last_trace_ms() > 0 and ctx.last_trace_launches() >= 1
+    ctx.close()
+
+
+def test_attach_framebuffer_and_stream_interop(materials):
+    import torch
+
+    grid = scenes.build_grid(64)
+    cam = scenes.camera(128, 64, **POSE0)
+    sun = scenes.sun(True)
+    ref, _, _ = orc.OracleScene.from_grid(grid, materials).render(cam, sun)
+    ctx = ffi.Context(128, 64, len(grid.brick_indices))
+    ctx.upload_grid(grid, materials)
+    target = torch.zeros(64, 128, 4, dtype=torch.uint8, device="cuda")
+    s = torch.cuda.Stream()
+    ctx.set_stream(s.cuda_stream)
+    ctx.attach_framebuffer(target.data_ptr(), target.numel())
+    ctx.trace(cam, sun)
+    s.synchronize()
+    assert np.array_equal(target.cpu().numpy(), ref)
+    ctx.attach_framebuffer(None)
+    ctx.set_stream(None)
+    ctx.close()
+
+
+@pytest.mark.parametrize("name", ["C2", "C3"])
+def test_full_size_properties(materials, name):
+    """BASELINE sizes (1920x1080 over 256^3 / 512^3): the oracle is too slow to run per test at this size on every
+    pixel, so check size-independent properties: tuned == reference-shape kernel pixel for pixel and record for record;
+    traced rays = pixels + primary hits; every hit record is self-consistent with the uploaded grid (status bit set, occupancy
+    bit set, material index equal to material_indices[...]); a 1/16 sample of rows equals the oracle."""
+    wl = scenes.WORKLOADS[name]
+    grid = scenes.build_grid(wl.n_voxels, wl.brick_dim)
+    cam = scenes.camera(wl.width, wl.height, **POSE0)
+    sun = scenes.sun(wl.sun)
+    img_t, aov_t, cnt_t = trace(grid, materials, cam, sun, ffi.VRT_FLAG_AOV)
+    img_b, aov_b, cnt_b = trace(grid, materials, cam, sun, ffi.VRT_FLAG_AOV | ffi.VRT_FLAG_BASELINE)
+    assert_same(img_t, aov_t, img_b, aov_b)
+    img_plain, _, _ = trace(grid, materials, cam, sun, 0)
+    assert np.array_equal(img_plain, img_b)
+    n_px = wl.width * wl.height
+    assert cnt_b["rays"] == n_px + (cnt_b["primary_hits"] if wl.sun else 0) == cnt_t["rays"]
+    assert cnt_b["shadow_rays"] == (cnt_b["primary_hits"] if wl.sun else 0)
+    hit = (aov_b["flags"] & 1) != 0
+    assert hit.sum() == cnt_b["primary_hits"] and 0.2 < hit.mean() < 0.9
+    gi, vi = aov_b["grid_index"][hit].astype(np.int64), aov_b["voxel_index"][hit].astype(np.int64)
+    assert ((grid.statuses[gi // 32] >> (gi % 32).astype(np.uint32)) & 1).all()
+    bi = grid.brick_indices[gi].astype(np.int64)
+    assert ((grid.occupancy[bi * 8 + vi // 8] >> (vi % 8).astype(np.uint8)) & 1).all()
+    assert np.array_equal(grid.material_indices[(grid.start_indices[bi] & 0x7FFFFFFF).astype(np.int64) + vi], aov_b["material"][hit].astype(np.uint8))
+    assert (aov_b["material"][~hit] == 0xFFFFFFFF).all()
+    # oracle on a 1/16 sample of the rows (row blocks of 8 every 128 rows)
+    sc = orc.OracleScene.from_grid(grid, materials)
+    for r0 in range(0, wl.height, 128):
+        r1 = min(r0 + 8, wl.height)
+        ref_img, ref_aov, _ = sc.render(cam, sun, rows=(r0, r1), aov=True)
+        assert np.array_equal(ref_img[r0:r1], img_t[r0:r1])
+        for f in EXACT:
+            assert np.array_equal(ref_aov[f][r0:r1], aov_t[f][r0:r1]), f
+        assert np.array_equal(ref_aov["t"][r0:r1].view(np.uint32), aov_t["t"][r0:r1].view(np.uint32))
+
+
+def test_c4_brickmap_extension(materials):
+    """BASELINE config 4: 64^3 bricks of 16^3 voxels (an extension: the reference fixes brick_dimension = 4, State.zig:5,
+    and its uint8 mask index wraps above 8^3, :413).  Reduced here to 32^3 bricks of 16^3 at 480x270; oracle comparison on all pixels."""
+    n, bd = 512, 16
+    grid = scenes.build_grid(n, bd, brick_alloc=scenes.count_bricks(n, bd))
+    cam = scenes.camera(480, 270, **POSE0)
+    sun = scenes.sun(False)
+    ref_img, ref_aov, _ = orc.OracleScene.from_grid(grid, materials).render(cam, sun, aov=True)
+    img, aov, _ = trace(grid, materials, cam, sun, ffi.VRT_FLAG_AOV)
+    assert_same(img, aov, ref_img, ref_aov)

@@ -67,6 +67,7 @@ VRT_DI void wait_pyramid() {
         : "memory");
 }
 
+template <bool AOV>
 __global__ void __launch_bounds__(kTunedThreads, 2)
     trace_tuned_kernel(const __grid_constant__ TraceParams P, const uint32_t tiles_x, const uint32_t tiles_total, const uint32_t stage_status) {
     SmemHeader* h = reinterpret_cast<SmemHeader*>(vrt_smem);
@@ -93,7 +94,7 @@ __global__ void __launch_bounds__(kTunedThreads, 2)
         const uint32_t py = P.row_begin + (tile / tiles_x) * kTileH + ly;
         const bool inside = px < width && py < P.row_end;  // :156-159
         uint32_t texel = 0u;
-        if (inside) texel = shade_pixel<TunedTrav, false>(P, px, py, pc);
+        if (inside) texel = shade_pixel<TunedTrav, AOV>(P, px, py, pc);
 
         // 128-bit framebuffer stores: lanes with lx in {0,4} gather the 4 texels to their right
         const uint32_t t1 = __shfl_down_sync(0xffffffffu, texel, 1);
@@ -111,15 +112,17 @@ __global__ void __launch_bounds__(kTunedThreads, 2)
             for (uint32_t p = 0; p < P.n_peers; p++) P.peer_fb[p][(size_t)py * width + px] = texel;
         }
     }
+    if (AOV) flush_counters(P, pc);
 }
 
-cudaError_t launch_trace_tuned(const TraceParams& P, cudaStream_t stream, LaunchInfo* info) {
+cudaError_t launch_trace_tuned(const TraceParams& P, bool aov, cudaStream_t stream, LaunchInfo* info) {
     if (P.brick_dim != 4) {
         // 8^3 / 16^3 bricks (the C4 extension) have no u64-per-brick mask; they run the transliteration.
         const uint32_t rows = P.row_end - P.row_begin;
         const dim3 block(32, 8);
         const dim3 grid((P.cam.image_width + 31) / 32, (rows + 7) / 8);
-        trace_ref_kernel<false><<<grid, block, 0, stream>>>(P);
+        if (aov) trace_ref_kernel<true><<<grid, block, 0, stream>>>(P);
+        else trace_ref_kernel<false><<<grid, block, 0, stream>>>(P);
         if (info) info->launches++;
         return cudaGetLastError();
     }
@@ -133,11 +136,12 @@ cudaError_t launch_trace_tuned(const TraceParams& P, cudaStream_t stream, Launch
     if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
     if (sm_count[dev] == 0) {
         if ((e = cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(trace_tuned_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(trace_tuned_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(trace_tuned_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess) return e;
     }
     const int num_sms = sm_count[dev];
     int blocks_per_sm = 0;
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, trace_tuned_kernel, kTunedThreads, smem)) != cudaSuccess) return e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, aov ? trace_tuned_kernel<true> : trace_tuned_kernel<false>, kTunedThreads, smem)) != cudaSuccess) return e;
     if (blocks_per_sm < 1) return cudaErrorLaunchOutOfResources;
     const uint32_t rows = P.row_end - P.row_begin;
     const uint32_t tiles_x = (P.cam.image_width + kTileW - 1) / kTileW;
@@ -147,7 +151,8 @@ cudaError_t launch_trace_tuned(const TraceParams& P, cudaStream_t stream, Launch
     uint32_t grid = (uint32_t)(num_sms * blocks_per_sm);
     const uint32_t needed = (tiles_total + warps_per_block - 1) / warps_per_block;
     if (grid > needed) grid = needed;
-    trace_tuned_kernel<<<grid, kTunedThreads, smem, stream>>>(P, tiles_x, tiles_total, stage_status ? 1u : 0u);
+    if (aov) trace_tuned_kernel<true><<<grid, kTunedThreads, smem, stream>>>(P, tiles_x, tiles_total, stage_status ? 1u : 0u);
+    else trace_tuned_kernel<false><<<grid, kTunedThreads, smem, stream>>>(P, tiles_x, tiles_total, stage_status ? 1u : 0u);
     if (info) {
         info->launches++;
         info->counter_advance = (unsigned long long)tiles_total + (unsigned long long)grid * warps_per_block;  // every warp overshoots once
@@ -219,7 +224,7 @@ cudaError_t launch_build_accel(const TraceParams& P, unsigned long long* occ_den
 cudaError_t launch_trace(const TraceParams& P, TraceKernel which, bool aov, cudaStream_t stream, LaunchInfo* info) {
     const uint32_t rows = P.row_end - P.row_begin;
     if (rows == 0 || P.cam.image_width == 0) return cudaSuccess;
-    if (which == KERNEL_REF || aov) {
+    if (which == KERNEL_REF) {
         const dim3 block(32, 8);
         const dim3 grid((P.cam.image_width + 31) / 32, (rows + 7) / 8);
         if (aov) trace_ref_kernel<true><<<grid, block, 0, stream>>>(P);
@@ -227,7 +232,7 @@ cudaError_t launch_trace(const TraceParams& P, TraceKernel which, bool aov, cuda
         if (info) info->launches++;
         return cudaGetLastError();
     }
-    return launch_trace_tuned(P, stream, info);
+    return launch_trace_tuned(P, aov, stream, info);
 }
 
 }  // namespace vrt

@@ -383,7 +383,7 @@ int vrt_trace(vrt_ctx* ctx, const vrt_camera* camera, const vrt_sun* sun) {
     const TraceKernel which = (ctx->cfg.flags & VRT_FLAG_BASELINE) ? KERNEL_REF : KERNEL_TUNED;
 
     VRT_CUDA(ctx, cudaEventRecord(ctx->ev_begin, ctx->stream));
-    if (which == KERNEL_TUNED && !aov && ctx->accel_dirty) {
+    if (which == KERNEL_TUNED && ctx->accel_dirty) {
         // Uploads changed statuses / indices / occupancy: rebuild the pyramid before tracing.  Stream order
         // gives upload -> build -> trace, where the reference has no barrier at all between its staging
         // copy and the next dispatch (edits land one frame late, Pipeline.zig:540).

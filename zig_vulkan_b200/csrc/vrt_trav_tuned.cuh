@@ -101,9 +101,10 @@ VRT_DI int brick_hit_u64(const TraceParams& P, const Ray& r, float grid_t_max, V
 // brick_raytracer.comp:271-376 with t_min = 0.00001, t_max = +inf, for brick_dim == 4.
 // NEED_MATERIAL: produce hit.index (primary / bounce rays); sun rays only need the boolean.
 // IGNORE_TEST:   the ray can actually ignore voxels (:427) — see TunedTrav.
-template <bool NEED_MATERIAL, bool IGNORE_TEST>
+// COUNT:         record the hit cell / voxel and the number of cells marched in `ti` (AOV parity path).
+template <bool NEED_MATERIAL, bool IGNORE_TEST, bool COUNT>
 VRT_DI bool grid_hit_tuned(const TraceParams& P, const uint32_t* __restrict__ s_coarse, const unsigned long long* __restrict__ s_status64,
-                           const Ray& r, HitRecord& hit) {
+                           const Ray& r, HitRecord& hit, TraceInfo& ti) {
     const V3 g_min = v3(P.grid.min_point_base_t[0], P.grid.min_point_base_t[1], P.grid.min_point_base_t[2]);
     const V3 g_max = v3(P.grid.max_point_scale[0], P.grid.max_point_scale[1], P.grid.max_point_scale[2]);
     const float g_scale = P.grid.max_point_scale[3];
@@ -131,6 +132,7 @@ VRT_DI bool grid_hit_tuned(const TraceParams& P, const uint32_t* __restrict__ s_
 
     // :313-317 (the `global_t_value <= t_max` term is `finite <= +inf`)
     while ((uint32_t)pos.x < (uint32_t)dim_x && (uint32_t)pos.y < (uint32_t)dim_y && (uint32_t)pos.z < (uint32_t)dim_z) {
+        if (COUNT) ti.grid_steps++;
         const uint32_t super = (uint32_t)(pos.x >> 2) + P.sdim_x * ((uint32_t)(pos.z >> 2) + P.sdim_z * (uint32_t)(pos.y >> 2));
         if (super != cached_super) {
             cached_super = super;
@@ -148,6 +150,7 @@ VRT_DI bool grid_hit_tuned(const TraceParams& P, const uint32_t* __restrict__ s_
                     brick_hit_u64<IGNORE_TEST>(P, r, grid_t_max, ray_delta, ray_step, g_scale, brick_min, occ, grid_index, hit, n);
                 if (voxel_index >= 0) {
                     if (NEED_MATERIAL && !IGNORE_TEST) hit.index = material_index_at(P, grid_index, voxel_index);
+                    if (COUNT) ti.grid_index = grid_index, ti.voxel_index = (uint32_t)voxel_index;
                     return true;
                 }
             }
@@ -165,19 +168,17 @@ VRT_DI bool grid_hit_tuned(const TraceParams& P, const uint32_t* __restrict__ s_
 struct TunedTrav {
     template <bool COUNT>
     static VRT_DI bool grid_hit(const TraceParams& P, const Ray& r, HitRecord& hit, TraceInfo& ti) {
-        (void)ti;
         if (r.ignore_type_material != VRT_MAT_NONE || P.materials_have_none)
-            return grid_hit_tuned<true, true>(P, smem_coarse(), smem_status64(), r, hit);
-        return grid_hit_tuned<true, false>(P, smem_coarse(), smem_status64(), r, hit);
+            return grid_hit_tuned<true, true, COUNT>(P, smem_coarse(), smem_status64(), r, hit, ti);
+        return grid_hit_tuned<true, false, COUNT>(P, smem_coarse(), smem_status64(), r, hit, ti);
     }
     template <bool COUNT>
     static VRT_DI bool shadow_hit(const TraceParams& P, const Ray& r, HitRecord& hit, TraceInfo& ti) {
-        (void)ti;
-        if (P.materials_have_none) return grid_hit_tuned<false, true>(P, smem_coarse(), smem_status64(), r, hit);
-        return grid_hit_tuned<false, false>(P, smem_coarse(), smem_status64(), r, hit);
+        if (P.materials_have_none) return grid_hit_tuned<false, true, COUNT>(P, smem_coarse(), smem_status64(), r, hit, ti);
+        return grid_hit_tuned<false, false, COUNT>(P, smem_coarse(), smem_status64(), r, hit, ti);
     }
 };
 
-cudaError_t launch_trace_tuned(const TraceParams& P, cudaStream_t stream, LaunchInfo* info);
+cudaError_t launch_trace_tuned(const TraceParams& P, bool aov, cudaStream_t stream, LaunchInfo* info);
 
 }  // namespace vrt
