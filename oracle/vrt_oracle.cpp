@@ -21,7 +21,9 @@
  *   - sin(x) = orc_sinf(x) below: Cody-Waite reduction + minimax polynomials written with explicit fmaf, so
  *     it is bit-identical on x86 and on the GPU (libm sinf and CUDA sinf are not).  GLSL only promises
  *     2^-11 absolute error for sin, so any faithful-ish sine is a conforming implementation of the shader.
- *   - Rgba8 imageStore: clamp to [0,1] then (uint8_t)(c*255.0f + 0.5f).
+ *   - Rgba8 imageStore: clamp to [0,1] then (uint8_t)(c*255.0f + 0.5f); NaN stores 0.
+ *   - float -> int conversion of floor(fposition) saturates and maps NaN to 0 (the CUDA cvt.rzi behaviour), so the
+ *     two sides agree even where the C++ cast would be undefined.
  */
 #include "vrt_oracle.h"
 
@@ -60,6 +62,13 @@ inline V3 operator*(float s, V3 a) { return V3{s * a.x, s * a.y, s * a.z}; }
 inline V3 neg(V3 a) { return V3{-a.x, -a.y, -a.z}; }
 inline V3 fma3(V3 a, V3 b, V3 c) { return V3{fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y), fmaf(a.z, b.z, c.z)}; }
 inline V3 tofloat(I3 i) { return V3{(float)i.x, (float)i.y, (float)i.z}; }
+// ivec3(floor(f)) with the saturating / NaN -> 0 semantics of the GPU's float->int conversion
+inline int f2i(float f) {
+    if (f != f) return 0;
+    if (f >= 2147483648.0f) return 2147483647;
+    if (f <= -2147483648.0f) return -2147483647 - 1;
+    return (int)f;
+}
 inline float gmin(float a, float b) { return b < a ? b : a; }
 inline float gmax(float a, float b) { return a < b ? b : a; }
 inline float gsign(float x) { return x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : 0.0f); }
@@ -253,7 +262,7 @@ bool BrickHit(const Ctx& c, const Ray& r, float /*t_min*/, float t_max, V3 ray_d
 
     const V3 normal_axis = v3(ray_step.x < 0 ? 1.f : -1.f, ray_step.y < 0 ? 1.f : -1.f, ray_step.z < 0 ? 1.f : -1.f);
 
-    I3 pos = I3{(int)floorf(fposition.x), (int)floorf(fposition.y), (int)floorf(fposition.z)};  // :403
+    I3 pos = I3{f2i(floorf(fposition.x)), f2i(floorf(fposition.y)), f2i(floorf(fposition.z))};  // :403
     const float local_t_max = t_max - hit.t;                                                   // :405
     float t_value = 0;
     const int bd = c.bd;
@@ -299,6 +308,11 @@ bool GridHit(const Ctx& c, const Ray& r, float t_min, float t_max, V3& hit_min, 
     const float g_scale = c.g_scale;
     const I3 brick_dim = c.brick_dim;
 
+    // Deviation (DESIGN.md "Deviations"): a ray whose direction is not finite (normalize of a zero or NaN vector, e.g. the
+    // 0/0 of a 1-pixel-wide image at :168) has ray_step = 0 on every axis; the shader's loop would then never advance
+    // (undefined behaviour in GLSL, a hang in practice).  Such a ray is a miss here and in the CUDA kernels.
+    if (std::isnan((r.direction.x + r.direction.y) + r.direction.z)) return false;
+
     const V3 inv_ray_dir = v3(safeInverse(r.direction.x), safeInverse(r.direction.y), safeInverse(r.direction.z));  // :278
 
     float grid_t_min = t_min;
@@ -323,7 +337,7 @@ bool GridHit(const Ctx& c, const Ray& r, float t_min, float t_max, V3& hit_min, 
     const V3 normal_axis = v3(ray_step.x < 0 ? 1.f : -1.f, ray_step.y < 0 ? 1.f : -1.f, ray_step.z < 0 ? 1.f : -1.f);
 
     float t_value = 0;
-    I3 pos = I3{(int)floorf(fposition.x), (int)floorf(fposition.y), (int)floorf(fposition.z)};  // :311
+    I3 pos = I3{f2i(floorf(fposition.x)), f2i(floorf(fposition.y)), f2i(floorf(fposition.z))};  // :311
 
     while (pos.x >= 0 && pos.y >= 0 && pos.z >= 0 && pos.x < brick_dim.x && pos.y < brick_dim.y && pos.z < brick_dim.z &&
            global_t_value <= t_max) {  // :313-317 (the PARAMETER t_max = +inf, not grid_t_max)

@@ -241,3 +241,13 @@ def test_max_bounce_one_means_no_rng_in_image(materials):
     a, aov_a, _ = sc.render(cam, scenes.sun(True), aov=True)
     b, aov_b, _ = sc.render(cam, scenes.sun(True), aov=True, threads=1)
     assert np.array_equal(a, b) and np.array_equal(aov_a, aov_b)
+
+
+def test_degenerate_direction_is_a_miss(one_voxel):
+    """Deviation from the shader (DESIGN.md "Deviations"): normalize((0,0,0)) is NaN, ray_step is 0 on all axes and the
+    shader's DDA would never advance; oracle and CUDA kernels define such rays as misses."""
+    _, sc = one_voxel
+    hit, a = sc.grid_hit((2.125, 2.125, 2.125), (0.0, 0.0, 0.0))
+    assert not hit and a["grid_steps"] == 0
+    img, _, cnt = sc.render(scenes.camera(1, 1), scenes.sun(True))  # u = 0/0 (:168)
+    assert cnt["hits"] == 0 and tuple(img[0, 0]) == (0, 0, 0, 255)

@@ -57,6 +57,9 @@ struct RefTraversal {
         const float g_scale = P.grid.max_point_scale[3];
         const I3 brick_dim = I3{(int)P.grid.dim_x, (int)P.grid.dim_y, (int)P.grid.dim_z};
 
+        // A non-finite direction has ray_step 0 on every axis and would never leave the loop: treated as a miss
+        // (DESIGN.md "Deviations"; the oracle does the same).
+        if (isnan((r.direction.x + r.direction.y) + r.direction.z)) return false;
         const V3 inv_ray_dir = v3(safeInverse(r.direction.x), safeInverse(r.direction.y), safeInverse(r.direction.z));  // :278
         float grid_t_min = 0.00001f;
         float grid_t_max = __int_as_float(0x7f800000);

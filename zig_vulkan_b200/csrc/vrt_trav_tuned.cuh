@@ -110,6 +110,7 @@ VRT_DI bool grid_hit_tuned(const TraceParams& P, const uint32_t* __restrict__ s_
     const float g_scale = P.grid.max_point_scale[3];
     const int dim_x = (int)P.grid.dim_x, dim_y = (int)P.grid.dim_y, dim_z = (int)P.grid.dim_z;
 
+    if (isnan((r.direction.x + r.direction.y) + r.direction.z)) return false;  // see RefTraversal::grid_hit
     const V3 inv_ray_dir = v3(safeInverse(r.direction.x), safeInverse(r.direction.y), safeInverse(r.direction.z));  // :278
     float grid_t_min = 0.00001f;
     float grid_t_max = __int_as_float(0x7f800000);
