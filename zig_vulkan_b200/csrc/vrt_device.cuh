@@ -253,13 +253,12 @@ struct TraceParams {
     uint32_t* fb;                 // RGBA8 image, binding 0 (row-major, width*height words)
     vrt_aov* aov;                 // nullable
     unsigned long long* counters; // nullable, 8 x u64 in vrt_counters order
-    // derived acceleration structures (built on device from the buffers above, see vrt_accel.cu)
+    // derived acceleration structures (built on the device from the buffers above, vrt_kernels.cu "build_*")
     const unsigned long long* occ_dense;  // [n_bricks] 4^3 voxel mask per GRID cell (brick_dim == 4 only)
-    const unsigned long long* status64;   // [ceil(dim/4)^3] 4^3 brick mask per super cell
-    const uint32_t* coarse;               // 1 bit per super cell
-    uint32_t sdim_x, sdim_y, sdim_z;      // super-cell grid dims
-    uint32_t coarse_bytes;                // size of `coarse`, padded to 16 B
-    uint32_t status64_bytes;              // size of `status64` (n_super * 8)
+    const uint8_t* dist;                  // padded Chebyshev distance grid, see vrt_trav_warp.cuh
+    uint32_t dist_log_px, dist_log_pz;    // row / plane strides of `dist` are powers of two: x + (z << log_px) + (y << (log_px+log_pz))
+    uint32_t scale_pow2, voxel_scale_pow2;  // brick / voxel scale is a power of two -> divide by multiplying with the exact inverse
+    float inv_scale, inv_voxel_scale;
     unsigned long long* tile_counter;     // persistent-kernel work counter (monotonic across frames)
     unsigned long long tile_base;         // value of *tile_counter when this launch starts
     uint32_t vec_store_ok;                // framebuffer rows are 16-B aligned -> 128-bit stores

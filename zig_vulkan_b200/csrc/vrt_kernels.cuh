@@ -7,7 +7,7 @@ namespace vrt {
 
 enum TraceKernel : int {
     KERNEL_REF = 0,    // transliteration, one thread per pixel (VRT_FLAG_BASELINE and the AOV path)
-    KERNEL_TUNED = 1,  // warp-tile traversal over the derived mask pyramid
+    KERNEL_TUNED = 1,  // warp-cooperative traversal over the derived distance grid (vrt_trav_warp.cuh)
 };
 
 struct LaunchInfo {
@@ -18,8 +18,9 @@ struct LaunchInfo {
 // Enqueue the kernels that trace rows [P.row_begin, P.row_end) into P.fb.
 cudaError_t launch_trace(const TraceParams& P, TraceKernel which, bool aov, cudaStream_t stream, LaunchInfo* info);
 
-// Rebuild the derived mask pyramid (occ_dense / status64 / coarse) from the reference-format buffers.
-cudaError_t launch_build_accel(const TraceParams& P, unsigned long long* occ_dense, unsigned long long* status64,
-                               uint32_t* coarse, size_t n_bricks, size_t n_super, cudaStream_t stream, LaunchInfo* info);
+// Rebuild the derived structures (occ_dense, dist) from the reference-format buffers.  tmp_a / tmp_b: n_bricks bytes each.
+cudaError_t launch_build_accel(const TraceParams& P, unsigned long long* occ_dense, uint8_t* dist, size_t dist_bytes, uint8_t* tmp_a, uint8_t* tmp_b,
+                               size_t n_bricks, cudaStream_t stream, LaunchInfo* info);
+cudaError_t launch_trace_tuned(const TraceParams& P, bool aov, cudaStream_t stream, LaunchInfo* info);
 
 }  // namespace vrt

@@ -25,6 +25,14 @@ namespace {
 
 char g_init_error[512] = "no error";
 
+// finite, normal, exactly a power of two: x / s == x * (1/s) bit for bit
+bool is_pow2(float s) {
+    uint32_t u;
+    std::memcpy(&u, &s, 4);
+    const uint32_t e = (u >> 23) & 0xffu;
+    return (u & 0x807fffffu) == 0u && e > 1u && e < 253u;
+}
+
 struct NcclApi {
     void* handle = nullptr;
     ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
@@ -90,12 +98,13 @@ struct vrt_ctx {
     vrt_aov* d_aov = nullptr;
     unsigned long long* d_counters = nullptr;
 
-    // derived mask pyramid
+    // derived acceleration structures (vrt_trav_warp.cuh)
     unsigned long long* d_occ_dense = nullptr;
-    unsigned long long* d_status64 = nullptr;
-    uint32_t* d_coarse = nullptr;
-    size_t n_super = 0;
-    uint32_t sdim_x = 0, sdim_y = 0, sdim_z = 0, coarse_bytes = 0;
+    uint8_t* d_dist = nullptr;
+    uint8_t* d_dist_tmp = nullptr;  // 2 x n_bricks bytes of scratch for the separable distance transform
+    size_t dist_bytes = 0;
+    uint32_t dist_log_px = 0, dist_log_pz = 0;
+    uint32_t accel_dim[3] = {0, 0, 0};
     bool accel_dirty = true;
 
     // persistent-kernel work counter
@@ -172,11 +181,14 @@ void fill_params(const vrt_ctx* c, const vrt_camera* cam, const vrt_sun* sun, Tr
     P.aov = c->d_aov;
     P.counters = c->d_counters;
     P.occ_dense = c->d_occ_dense;
-    P.status64 = c->d_status64;
-    P.coarse = c->d_coarse;
-    P.sdim_x = c->sdim_x, P.sdim_y = c->sdim_y, P.sdim_z = c->sdim_z;
-    P.coarse_bytes = c->coarse_bytes;
-    P.status64_bytes = (uint32_t)(c->n_super * 8);
+    P.dist = c->d_dist;
+    P.dist_log_px = c->dist_log_px, P.dist_log_pz = c->dist_log_pz;
+    const float scale = c->grid.max_point_scale[3];
+    const float voxel_scale = scale * P.brick_voxel_scale;  // :389, same f32 product the kernels form
+    P.scale_pow2 = is_pow2(scale) ? 1u : 0u;
+    P.voxel_scale_pow2 = is_pow2(voxel_scale) ? 1u : 0u;
+    P.inv_scale = P.scale_pow2 ? 1.0f / scale : 0.0f;
+    P.inv_voxel_scale = P.voxel_scale_pow2 ? 1.0f / voxel_scale : 0.0f;
     P.tile_counter = c->d_tile_counter;
     P.tile_base = c->tile_base;
     P.vec_store_ok = (cam->image_width % 4 == 0) && ((reinterpret_cast<uintptr_t>(c->d_fb) & 15u) == 0);
@@ -187,20 +199,22 @@ void fill_params(const vrt_ctx* c, const vrt_camera* cam, const vrt_sun* sun, Tr
     }
 }
 
-// (Re)allocate the pyramid for the grid dimensions in ctx->grid.
+// (Re)allocate the distance grid for the grid dimensions in ctx->grid.
 int ensure_accel(vrt_ctx* ctx) {
-    const uint32_t sx = (ctx->grid.dim_x + 3) / 4, sy = (ctx->grid.dim_y + 3) / 4, sz = (ctx->grid.dim_z + 3) / 4;
-    if (ctx->d_status64 && sx == ctx->sdim_x && sy == ctx->sdim_y && sz == ctx->sdim_z) return VRT_OK;
-    if (ctx->d_status64) cudaFree(ctx->d_status64);
-    if (ctx->d_coarse) cudaFree(ctx->d_coarse);
-    ctx->d_status64 = nullptr, ctx->d_coarse = nullptr;
-    ctx->sdim_x = sx, ctx->sdim_y = sy, ctx->sdim_z = sz;
-    ctx->n_super = (size_t)sx * sy * sz;
-    const size_t coarse_words = (ctx->n_super + 31) / 32;
-    ctx->coarse_bytes = (uint32_t)((coarse_words * 4 + 15) & ~size_t(15));
-    VRT_CUDA(ctx, cudaMalloc(&ctx->d_status64, ctx->n_super * 8));
-    VRT_CUDA(ctx, cudaMalloc(&ctx->d_coarse, ctx->coarse_bytes));
-    VRT_CUDA(ctx, cudaMemsetAsync(ctx->d_coarse, 0, ctx->coarse_bytes, ctx->stream));
+    const uint32_t dx = ctx->grid.dim_x, dy = ctx->grid.dim_y, dz = ctx->grid.dim_z;
+    if (ctx->d_dist && dx == ctx->accel_dim[0] && dy == ctx->accel_dim[1] && dz == ctx->accel_dim[2]) return VRT_OK;
+    if (ctx->d_dist) cudaFree(ctx->d_dist);
+    if (ctx->d_dist_tmp) cudaFree(ctx->d_dist_tmp);
+    ctx->d_dist = nullptr, ctx->d_dist_tmp = nullptr;
+    uint32_t lx = 1, lz = 1;
+    while ((1u << lx) < dx + 2) lx++;  // one border cell on each side; power-of-two strides make the index decodable with shifts
+    while ((1u << lz) < dz + 2) lz++;
+    ctx->dist_log_px = lx, ctx->dist_log_pz = lz;
+    ctx->dist_bytes = ((size_t)(dy + 2)) << (lx + lz);
+    if (ctx->dist_bytes > 0x7fffffffull) return fail(ctx, VRT_E_INVALID, "grid %ux%ux%u is too large for the 31-bit cell index of the march", dx, dy, dz);
+    VRT_CUDA(ctx, cudaMalloc(&ctx->d_dist, ctx->dist_bytes));
+    VRT_CUDA(ctx, cudaMalloc(&ctx->d_dist_tmp, 2 * (size_t)dx * dy * dz));
+    ctx->accel_dim[0] = dx, ctx->accel_dim[1] = dy, ctx->accel_dim[2] = dz;
     ctx->accel_dirty = true;
     return VRT_OK;
 }
@@ -314,7 +328,7 @@ void vrt_deinit(vrt_ctx* ctx) {
     }
     cudaFree(ctx->d_materials), cudaFree(ctx->d_statuses), cudaFree(ctx->d_brick_indices), cudaFree(ctx->d_occupancy);
     cudaFree(ctx->d_start_indices), cudaFree(ctx->d_material_indices), cudaFree(ctx->d_fb_own), cudaFree(ctx->d_aov);
-    cudaFree(ctx->d_counters), cudaFree(ctx->d_occ_dense), cudaFree(ctx->d_status64), cudaFree(ctx->d_coarse);
+    cudaFree(ctx->d_counters), cudaFree(ctx->d_occ_dense), cudaFree(ctx->d_dist), cudaFree(ctx->d_dist_tmp);
     cudaFree(ctx->d_tile_counter);
     if (ctx->h_pinned_fb) cudaFreeHost(ctx->h_pinned_fb);
     if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
@@ -384,11 +398,12 @@ int vrt_trace(vrt_ctx* ctx, const vrt_camera* camera, const vrt_sun* sun) {
 
     VRT_CUDA(ctx, cudaEventRecord(ctx->ev_begin, ctx->stream));
     if (which == KERNEL_TUNED && ctx->accel_dirty) {
-        // Uploads changed statuses / indices / occupancy: rebuild the pyramid before tracing.  Stream order
+        // Uploads changed statuses / indices / occupancy: rebuild the derived structures before tracing.  Stream order
         // gives upload -> build -> trace, where the reference has no barrier at all between its staging
         // copy and the next dispatch (edits land one frame late, Pipeline.zig:540).
-        VRT_CUDA(ctx, launch_build_accel(P, ctx->d_occ_dense, ctx->d_status64, ctx->d_coarse, (size_t)ctx->grid.dim_x * ctx->grid.dim_y * ctx->grid.dim_z,
-                                         ctx->n_super, ctx->stream, &info));
+        const size_t n_cells = (size_t)ctx->grid.dim_x * ctx->grid.dim_y * ctx->grid.dim_z;
+        VRT_CUDA(ctx, launch_build_accel(P, ctx->d_occ_dense, ctx->d_dist, ctx->dist_bytes, ctx->d_dist_tmp, ctx->d_dist_tmp + n_cells, n_cells, ctx->stream,
+                                         &info));
         ctx->accel_dirty = false;
     }
     if (aov) VRT_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));

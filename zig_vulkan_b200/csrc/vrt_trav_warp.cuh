@@ -1,0 +1,245 @@
+// vrt_trav_warp.cuh — the B200 traversal: a warp-cooperative GridHit.
+//
+// Results are bit-identical to the shader (assets/shaders/brick_raytracer.comp:271-471): every ray still visits the
+// same cells in the same order and advances side_dist by the same sequence of FP32 additions — skipping k cells with
+// one multiply would round differently and can flip which voxel is hit.  What changes is everything
+// AROUND that arithmetic:
+//
+//   * Safe-step counts instead of per-cell occupancy tests.  A derived byte grid `dist` holds, per brick cell, the
+//     Chebyshev distance D (in cells) to the nearest loaded brick or grid face (0 = loaded brick, 255 = the one-cell
+//     border around the grid).  From a cell with distance D the next D-1 DDA steps cannot land on a loaded brick or
+//     leave the grid (each step moves one cell along one axis), so they run with no memory access and no bounds test:
+//     three compares, one min, one predicated FADD, one predicated IADD.  Only the D-th step is followed by a lookup.
+//     The border makes "left the grid" a byte value, so the march carries ONE linear index, not three coordinates.
+//   * Warp supersteps (ballot/shfl free: the SIMT reconvergence stack does it).  Phase A: all 32 rays march until each
+//     is parked on a loaded brick or has left the grid.  Phase B: the parked rays run the voxel-level DDA together.
+//     The expensive brick entry (three divides, a 64-bit mask fetch) is therefore executed coherently instead of once
+//     per ray at 32 different times.
+//   * The 4^3 voxel mask of a brick is one 64-bit load from a grid-indexed copy (`occ_dense`) and the voxel DDA runs in
+//     registers (the shader does a dependent brick_indices load plus one byte load per voxel step, :337,:415).
+//   * Divisions by the brick/voxel scale become exact multiplications when the scale is a power of two (the result of
+//     x / 2^k and x * 2^-k is the same correctly-rounded number).
+//   * The material chain (brick_indices -> start index -> material index -> material) is walked once per hit, and not at
+//     all for sun rays, unless the ray can ignore voxels (:427), in which case it is evaluated where the shader does.
+#pragma once
+
+#include "vrt_kernels.cuh"
+#include "vrt_shade.cuh"
+
+namespace vrt {
+
+constexpr unsigned kFullMask = 0xffffffffu;
+constexpr uint32_t kDistBorder = 255u;
+
+// hit.normal as (axis, sign): every normal this path produces has one non-zero component (:350-370, :530-531)
+struct AxisNormal {
+    int axis;
+    float sign;
+};
+VRT_DI V3 to_v3(AxisNormal n) { return v3(n.axis == 0 ? n.sign : 0.0f, n.axis == 1 ? n.sign : 0.0f, n.axis == 2 ? n.sign : 0.0f); }
+VRT_DI AxisNormal step_normal(int axis, I3 ray_step) {
+    const int s = axis == 0 ? ray_step.x : (axis == 1 ? ray_step.y : ray_step.z);
+    return AxisNormal{axis, s < 0 ? 1.0f : -1.0f};  // normal_axis (:304-308)
+}
+
+// brick_indices -> start index -> material_indices (:337, :422-425)
+VRT_DI uint32_t material_index_at(const TraceParams& P, uint32_t grid_index, int voxel_index) {
+    const uint32_t brick_index = grid_index < P.n_brick_indices ? __ldg(P.brick_indices + grid_index) : 0u;
+    const uint32_t sw = brick_index < P.n_start_indices ? __ldg(P.start_indices + brick_index) : 0u;
+    const unsigned long long mi = (unsigned long long)(sw & 0x7fffffffu) + (uint32_t)voxel_index;
+    return mi < P.n_material_indices ? (uint32_t)__ldg(P.material_indices + mi) : 0u;
+}
+
+// x / s, as a multiplication when s is a power of two (bit-identical, see header)
+VRT_DI V3 div_scale(V3 v, float s, float inv_s, bool exact) { return exact ? v * inv_s : v / v3s(s); }
+
+// The DDA advance (:440-467) without branches: same ladder, same additions; returns the axis stepped.
+VRT_DI int dda_step_sel(V3& side, V3 delta, I3& pos, I3 step, float scale, float& t_value) {
+    const bool pxy = side.x < side.y, pxz = side.x < side.z, pyz = side.y < side.z;
+    const bool take_x = pxy && pxz, take_y = !pxy && pyz;
+    const bool take_z = !take_x && !take_y;
+    t_value = fminf(fminf(side.x, side.y), side.z) * scale;  // the picked side value is the minimum (see march_step)
+    side.x = take_x ? side.x + delta.x : side.x;
+    side.y = take_y ? side.y + delta.y : side.y;
+    side.z = take_z ? side.z + delta.z : side.z;
+    pos.x += take_x ? step.x : 0;
+    pos.y += take_y ? step.y : 0;
+    pos.z += take_z ? step.z : 0;
+    return take_x ? 0 : (take_y ? 1 : 2);
+}
+
+// Voxel-level DDA inside one brick (brick_raytracer.comp:378-471).  Returns the voxel index hit or -1.
+// BD == 4: the brick's 64-bit mask is in `occ`.  Otherwise mask bytes are read from the occupancy buffer (:415).
+template <int BD, bool COUNT>
+VRT_DI int brick_hit_warp(const TraceParams& P, const Ray& r, bool ignore_test, float grid_t_max, V3 ray_delta, I3 ray_step, float g_scale,
+                          V3 brick_position, unsigned long long occ, uint32_t grid_index, HitRecord& hit, AxisNormal& n, TraceInfo& ti) {
+    const int bd = BD == 4 ? 4 : P.brick_dim;
+    const float voxel_scale = g_scale * P.brick_voxel_scale;                                                  // :389
+    const V3 fposition = div_scale(RayAt(r, hit.t) - brick_position, voxel_scale, P.inv_voxel_scale, P.voxel_scale_pow2 != 0u);  // :393
+    V3 side_dist = init_side_dist(fposition, ray_step, ray_delta);                                            // :394-395
+    I3 pos = I3{(int)floorf(fposition.x), (int)floorf(fposition.y), (int)floorf(fposition.z)};                // :403
+    const float local_t_max = grid_t_max - hit.t;                                                            // :405
+    float t_value = 0.0f;
+    unsigned long long mask_base = 0ull;
+    if (BD != 4) {
+        const uint32_t brick_index = grid_index < P.n_brick_indices ? __ldg(P.brick_indices + grid_index) : 0u;  // :337
+        mask_base = (unsigned long long)brick_index * P.brick_bytes;                                            // :390
+    }
+    while ((uint32_t)pos.x < (uint32_t)bd && (uint32_t)pos.y < (uint32_t)bd && (uint32_t)pos.z < (uint32_t)bd && t_value <= local_t_max) {
+        if (COUNT) ti.voxel_steps++;
+        const int voxel_index = pos.x + bd * (pos.z + bd * pos.y);  // :412
+        bool solid;
+        if (BD == 4) {
+            solid = ((voxel_index & 32 ? (uint32_t)(occ >> 32) : (uint32_t)occ) >> (voxel_index & 31)) & 1u;  // :415-417
+        } else {
+            const uint32_t mask_index = (bd <= 8) ? (uint32_t)(uint8_t)(voxel_index / 8) : (uint32_t)(voxel_index / 8);  // :413
+            const unsigned long long at = mask_base + mask_index;
+            const uint32_t entry = at < P.n_occupancy ? (uint32_t)__ldg(P.occupancy + at) : 0u;
+            solid = (entry >> (voxel_index % 8)) & 1u;
+        }
+        if (solid) {
+            bool ignore_brick = false;
+            if (ignore_test) {
+                hit.index = material_index_at(P, grid_index, voxel_index);  // :425
+                const vrt_material m = load_material(P, hit.index);
+                ignore_brick = (m.type == r.ignore_type_material) && (r.internal_reflection == m.type_data);  // :427
+            }
+            if (!ignore_brick) {
+                const float t_offset = voxel_scale * 0.05f;           // :431
+                hit.t += t_value - t_offset;                          // :432
+                hit.normal = to_v3(n);
+                hit.point = RayAt(r, hit.t) + hit.normal * t_offset;  // :433
+                return voxel_index;
+            }
+        }
+        n = step_normal(dda_step_sel(side_dist, ray_delta, pos, ray_step, voxel_scale, t_value), ray_step);  // :440-467
+    }
+    return -1;
+}
+
+// Reference grid index (:318) of the padded linear cell index used by the march.
+VRT_DI uint32_t cell_grid_index(const TraceParams& P, int idx, int log_px, int log_pzx) {
+    const int x = (idx & ((1 << log_px) - 1)) - 1, z = ((idx >> log_px) & ((1 << (log_pzx - log_px)) - 1)) - 1, y = (idx >> log_pzx) - 1;
+    return (uint32_t)(x + (int)P.grid.dim_x * (z + (int)P.grid.dim_z * y));
+}
+
+// One brick-level DDA step (:345-372) on the linear cell index: strict '<', tie order x -> z / y -> z.  The side value
+// of the axis the ladder picks is always the minimum of the three (ties pick between equal values), so
+// t_side = min(sx, sy, sz) is side_dist.<axis> read before its increment (:347,353,361,367).  Adding the deltas under
+// a select keeps each axis' additions exactly the shader's sequence.
+VRT_DI void march_step(float& sx, float& sy, float& sz, float dx, float dy, float dz, int stx, int sty, int stz, int& idx, int& last_stride,
+                       float& t_side) {
+    const bool pxy = sx < sy, pxz = sx < sz, pyz = sy < sz;
+    const bool take_x = pxy && pxz, take_y = !pxy && pyz;
+    const bool take_z = !take_x && !take_y;
+    t_side = fminf(fminf(sx, sy), sz);
+    sx = take_x ? sx + dx : sx;
+    sy = take_y ? sy + dy : sy;
+    sz = take_z ? sz + dz : sz;
+    last_stride = take_x ? stx : (take_y ? sty : stz);
+    idx += last_stride;
+}
+
+// GridHit(r, 0.00001, infinity, ...) (:271-376) for the 32 rays of a warp.  Every lane of the warp must call this;
+// `active` says whether the lane has a ray.  need_material: produce hit.index (camera / bounce rays; sun rays only
+// need the boolean).  ignore_test: the ray can ignore voxels (:427).
+template <int BD, bool COUNT>
+VRT_DI bool grid_hit_warp(const TraceParams& P, const Ray& r, bool active, bool need_material, bool ignore_test, HitRecord& hit, TraceInfo& ti) {
+    const V3 g_min = v3(P.grid.min_point_base_t[0], P.grid.min_point_base_t[1], P.grid.min_point_base_t[2]);
+    const float g_scale = P.grid.max_point_scale[3];
+    const int log_px = (int)P.dist_log_px, log_pzx = (int)(P.dist_log_px + P.dist_log_pz);
+
+    float grid_t_min = 0.00001f, grid_t_max = __int_as_float(0x7f800000);
+    V3 ray_delta = v3s(0.0f);
+    I3 ray_step = I3{0, 0, 0};
+    AxisNormal n = AxisNormal{0, 0.0f};
+    float sx = 0.0f, sy = 0.0f, sz = 0.0f, t_side = 0.0f;
+    int idx = 0, stx = 0, sty = 0, stz = 0, safe = 0;
+    bool marching = false;
+
+    if (active && !isnan((r.direction.x + r.direction.y) + r.direction.z)) {  // non-finite direction: a miss (DESIGN.md "Deviations")
+        const V3 g_max = v3(P.grid.max_point_scale[0], P.grid.max_point_scale[1], P.grid.max_point_scale[2]);
+        const V3 inv_ray_dir = v3(safeInverse(r.direction.x), safeInverse(r.direction.y), safeInverse(r.direction.z));  // :278
+        V3 slab_normal;
+        if (AdvNormIntersect(g_min, g_max, r, inv_ray_dir, slab_normal, grid_t_min, grid_t_max)) {  // :282
+            n.axis = slab_normal.x != 0.0f ? 0 : (slab_normal.y != 0.0f ? 1 : 2);
+            n.sign = n.axis == 0 ? slab_normal.x : (n.axis == 1 ? slab_normal.y : slab_normal.z);
+            const float global_t_value = grid_t_min + 0.0001f * g_scale;  // :287
+            ray_delta = v3(fabsf(inv_ray_dir.x), fabsf(inv_ray_dir.y), fabsf(inv_ray_dir.z));  // :290
+            ray_step = I3{(int)gsign(r.direction.x), (int)gsign(r.direction.y), (int)gsign(r.direction.z)};  // :291
+            const V3 fposition = div_scale(RayAt(r, global_t_value) - g_min, g_scale, P.inv_scale, P.scale_pow2 != 0u);  // :293-296
+            const V3 side_dist = init_side_dist(fposition, ray_step, ray_delta);  // :297-298
+            sx = side_dist.x, sy = side_dist.y, sz = side_dist.z;
+            const int px = (int)floorf(fposition.x), py = (int)floorf(fposition.y), pz = (int)floorf(fposition.z);  // :311
+            // :313-315 for the start cell; afterwards the border bytes of `dist` stand in for the bounds test
+            if ((uint32_t)px < P.grid.dim_x && (uint32_t)py < P.grid.dim_y && (uint32_t)pz < P.grid.dim_z) {
+                idx = (px + 1) + ((pz + 1) << log_px) + ((py + 1) << log_pzx);
+                stx = ray_step.x, stz = ray_step.z << log_px, sty = ray_step.y << log_pzx;
+                marching = true;
+            }
+        }
+    }
+    const float dx = ray_delta.x, dy = ray_delta.y, dz = ray_delta.z;
+    const uint8_t* __restrict__ dist = P.dist;
+    int last_stride = 0;  // stride of the most recent step (0: none yet -> slab normal)
+    bool parked = false, result = false;
+    uint32_t cnt_word = ~0u;  // COUNT: the reference's one-word status cache (:301,:321-326)
+
+    while (__any_sync(kFullMask, marching)) {
+        // ---- phase A: march until parked on a loaded brick or out of the grid (:313-373 without the per-cell tests)
+        while (marching && !parked) {
+            uint32_t d = 1u;
+            if (safe == 0) {
+                d = __ldg(dist + idx);
+                if (d == kDistBorder) {
+                    marching = false;  // left the grid (:313-315)
+                    break;
+                }
+            }
+            if (COUNT) {  // this cell is one iteration of the shader's loop: emulate its one-word status cache (:321-326)
+                ti.grid_steps++;
+                const uint32_t gi = cell_grid_index(P, idx, log_px, log_pzx);
+                if ((gi >> 5) != cnt_word) cnt_word = gi >> 5, ti.status_fetches++;
+            }
+            if (safe == 0) {
+                if (d == 0u) {
+                    parked = true;  // status bit set (:328)
+                    break;
+                }
+                safe = (int)d;
+            }
+            march_step(sx, sy, sz, dx, dy, dz, stx, sty, stz, idx, last_stride, t_side);
+            safe--;
+        }
+        __syncwarp();
+        // ---- phase B: the parked rays test their bricks together (:329-342)
+        if (parked) {
+            parked = false;
+            if (last_stride != 0) {
+                const int a = last_stride < 0 ? -last_stride : last_stride;
+                n = step_normal(a == 1 ? 0 : (a == (1 << log_px) ? 2 : 1), ray_step);
+            }
+            const int x = (idx & ((1 << log_px) - 1)) - 1, z = ((idx >> log_px) & ((1 << (log_pzx - log_px)) - 1)) - 1, y = (idx >> log_pzx) - 1;
+            const uint32_t grid_index = (uint32_t)(x + (int)P.grid.dim_x * (z + (int)P.grid.dim_z * y));  // :318
+            unsigned long long occ = 0ull;
+            if (BD == 4) occ = __ldg(P.occ_dense + grid_index);
+            const V3 brick_min = fma3(v3((float)x, (float)y, (float)z), v3s(g_scale), g_min);  // :331
+            const float t_value = t_side * g_scale;                                            // :347,353,361,367
+            hit.t = (t_value + grid_t_min) + 0.01f * g_scale;                                  // :332-334
+            if (COUNT) ti.bricks_entered++;
+            const int voxel_index = brick_hit_warp<BD, COUNT>(P, r, ignore_test, grid_t_max, ray_delta, ray_step, g_scale, brick_min, occ, grid_index, hit, n, ti);
+            if (voxel_index >= 0) {
+                if (need_material && !ignore_test) hit.index = material_index_at(P, grid_index, voxel_index);
+                if (COUNT) ti.grid_index = grid_index, ti.voxel_index = (uint32_t)voxel_index;
+                result = true;
+                marching = false;
+            } else {
+                march_step(sx, sy, sz, dx, dy, dz, stx, sty, stz, idx, last_stride, t_side);  // :345-372, then look the next cell up
+                safe = 0;
+            }
+        }
+    }
+    return result;
+}
+
+}  // namespace vrt
