@@ -9,10 +9,13 @@
 //     Chebyshev distance D (in cells) to the nearest loaded brick or grid face (0 = loaded brick, 255 = the one-cell
 //     border around the grid).  From a cell with distance D the next D-1 DDA steps cannot land on a loaded brick or
 //     leave the grid (each step moves one cell along one axis), so they run with no memory access and no bounds test:
-//     three compares, one min, one predicated FADD, one predicated IADD.  Only the D-th step is followed by a lookup.
+//     four compares, predicated FADDs and IADDs.  Only the D-th step is followed by a lookup.
 //     The border makes "left the grid" a byte value, so the march carries ONE linear index, not three coordinates.
-//   * Warp supersteps (ballot/shfl free: the SIMT reconvergence stack does it).  Phase A: all 32 rays march until each
-//     is parked on a loaded brick or has left the grid.  Phase B: the parked rays run the voxel-level DDA together.
+//   * Warp rounds.  The 32 rays of a tile look their cells up TOGETHER, reduce the distances found to the warp minimum
+//     k (redux.sync) and all take k steps: the step loop is warp-uniform (no per-lane counters, no divergence) and the
+//     lookup latency is paid once per round instead of once per ray.
+//   * Warp supersteps.  Phase A: the rays march in rounds until each is parked on a loaded brick or has left
+//     the grid.  Phase B: the parked rays run the voxel-level DDA together.
 //     The expensive brick entry (three divides, a 64-bit mask fetch) is therefore executed coherently instead of once
 //     per ray at 32 different times.
 //   * The 4^3 voxel mask of a brick is one 64-bit load from a grid-indexed copy (`occ_dense`) and the voxel DDA runs in
@@ -123,21 +126,27 @@ VRT_DI uint32_t cell_grid_index(const TraceParams& P, int idx, int log_px, int l
     return (uint32_t)(x + (int)P.grid.dim_x * (z + (int)P.grid.dim_z * y));
 }
 
-// One brick-level DDA step (:345-372) on the linear cell index: strict '<', tie order x -> z / y -> z.  The side value
-// of the axis the ladder picks is always the minimum of the three (ties pick between equal values), so
-// t_side = min(sx, sy, sz) is side_dist.<axis> read before its increment (:347,353,361,367).  Adding the deltas under
-// a select keeps each axis' additions exactly the shader's sequence.
-VRT_DI void march_step(float& sx, float& sy, float& sz, float dx, float dy, float dz, int stx, int sty, int stz, int& idx, int& last_stride,
-                       float& t_side) {
-    const bool pxy = sx < sy, pxz = sx < sz, pyz = sy < sz;
-    const bool take_x = pxy && pxz, take_y = !pxy && pyz;
-    const bool take_z = !take_x && !take_y;
-    t_side = fminf(fminf(sx, sy), sz);
-    sx = take_x ? sx + dx : sx;
-    sy = take_y ? sy + dy : sy;
-    sz = take_z ? sz + dz : sz;
-    last_stride = take_x ? stx : (take_y ? sty : stz);
-    idx += last_stride;
+// One brick-level DDA step (:345-372) on the linear cell index: strict '<', tie order x -> z / y -> z, the picked
+// axis' side value gets its delta added (the shader's own sequence of FP32 additions per axis) and the cell index moves
+// by that axis' stride.  Written in PTX so that the step is exactly 4 setp + 1 predicate op + 3 predicated add.f32 +
+// 3 predicated add.s32: take_x = (sx<sy)&(sx<sz); take_y = !(sx<sy)&(sy<sz); take_z = neither.
+VRT_DI void march_step(float& sx, float& sy, float& sz, float dx, float dy, float dz, int stx, int sty, int stz, int& idx) {
+    asm("{\n\t"
+        ".reg .pred pxz, pyz, px, py, pxy;\n\t"
+        "setp.lt.f32 pxz, %0, %2;\n\t"
+        "setp.lt.f32 pyz, %1, %2;\n\t"
+        "setp.lt.and.f32 px, %0, %1, pxz;\n\t"
+        "setp.geu.and.f32 py, %0, %1, pyz;\n\t"
+        "or.pred pxy, px, py;\n\t"
+        "@px add.rn.f32 %0, %0, %4;\n\t"
+        "@py add.rn.f32 %1, %1, %5;\n\t"
+        "@!pxy add.rn.f32 %2, %2, %6;\n\t"
+        "@px add.s32 %3, %3, %7;\n\t"
+        "@py add.s32 %3, %3, %8;\n\t"
+        "@!pxy add.s32 %3, %3, %9;\n\t"
+        "}"
+        : "+f"(sx), "+f"(sy), "+f"(sz), "+r"(idx)
+        : "f"(dx), "f"(dy), "f"(dz), "r"(stx), "r"(sty), "r"(stz));
 }
 
 // GridHit(r, 0.00001, infinity, ...) (:271-376) for the 32 rays of a warp.  Every lane of the warp must call this;
@@ -154,7 +163,7 @@ VRT_DI bool grid_hit_warp(const TraceParams& P, const Ray& r, bool active, bool 
     I3 ray_step = I3{0, 0, 0};
     AxisNormal n = AxisNormal{0, 0.0f};
     float sx = 0.0f, sy = 0.0f, sz = 0.0f, t_side = 0.0f;
-    int idx = 0, stx = 0, sty = 0, stz = 0, safe = 0;
+    int idx = 0, stx = 0, sty = 0, stz = 0;
     bool marching = false;
 
     if (active && !isnan((r.direction.x + r.direction.y) + r.direction.z)) {  // non-finite direction: a miss (DESIGN.md "Deviations")
@@ -184,34 +193,51 @@ VRT_DI bool grid_hit_warp(const TraceParams& P, const Ray& r, bool active, bool 
     int last_stride = 0;  // stride of the most recent step (0: none yet -> slab normal)
     bool parked = false, result = false;
     uint32_t cnt_word = ~0u;  // COUNT: the reference's one-word status cache (:301,:321-326)
+    constexpr uint32_t kIdle = 0xffffu;
 
     while (__any_sync(kFullMask, marching)) {
-        // ---- phase A: march until parked on a loaded brick or out of the grid (:313-373 without the per-cell tests)
-        while (marching && !parked) {
-            uint32_t d = 1u;
-            if (safe == 0) {
+        // ---- phase A (:313-373 without the per-cell tests): rounds of { every marching ray looks its cell up; all of
+        // them take k = min over the warp of the distances found steps }.  k is warp-uniform, so the step loop has no
+        // per-lane counter and no divergence; rays that are parked / finished ride along with zero deltas and strides
+        // (x + 0.0f == x), which keeps the parked rays' DDA state intact for the step after a brick miss.
+        for (;;) {
+            uint32_t d = kIdle;
+            if (marching && !parked) {
                 d = __ldg(dist + idx);
                 if (d == kDistBorder) {
                     marching = false;  // left the grid (:313-315)
-                    break;
+                    d = kIdle;
+                } else {
+                    if (COUNT) {  // an in-grid cell = one iteration of the shader's loop; emulate its one-word status cache (:321-326)
+                        ti.grid_steps++;
+                        const uint32_t gi = cell_grid_index(P, idx, log_px, log_pzx);
+                        if ((gi >> 5) != cnt_word) cnt_word = gi >> 5, ti.status_fetches++;
+                    }
+                    if (d == 0u) {
+                        parked = true;  // status bit set (:328)
+                        d = kIdle;
+                    }
                 }
             }
-            if (COUNT) {  // this cell is one iteration of the shader's loop: emulate its one-word status cache (:321-326)
-                ti.grid_steps++;
-                const uint32_t gi = cell_grid_index(P, idx, log_px, log_pzx);
-                if ((gi >> 5) != cnt_word) cnt_word = gi >> 5, ti.status_fetches++;
-            }
-            if (safe == 0) {
-                if (d == 0u) {
-                    parked = true;  // status bit set (:328)
-                    break;
+            const uint32_t k = __reduce_min_sync(kFullMask, d);
+            if (k == kIdle) break;
+            const bool on = d != kIdle;
+            const float fdx = on ? dx : 0.0f, fdy = on ? dy : 0.0f, fdz = on ? dz : 0.0f;
+            const int fsx = on ? stx : 0, fsy = on ? sty : 0, fsz = on ? stz : 0;
+            for (uint32_t i = 1; i < k; i++) {  // k-1 steps onto cells known to be empty and inside
+                march_step(sx, sy, sz, fdx, fdy, fdz, fsx, fsy, fsz, idx);
+                if (COUNT && on) {
+                    ti.grid_steps++;
+                    const uint32_t gi = cell_grid_index(P, idx, log_px, log_pzx);
+                    if ((gi >> 5) != cnt_word) cnt_word = gi >> 5, ti.status_fetches++;
                 }
-                safe = (int)d;
             }
-            march_step(sx, sy, sz, dx, dy, dz, stx, sty, stz, idx, last_stride, t_side);
-            safe--;
+            // the k-th step lands on a cell that is looked up next round; remember its side value and axis
+            if (on) t_side = fminf(fminf(sx, sy), sz);  // = side_dist.<axis> before the increment (the picked side is the minimum)
+            const int before = idx;
+            march_step(sx, sy, sz, fdx, fdy, fdz, fsx, fsy, fsz, idx);
+            if (on) last_stride = idx - before;
         }
-        __syncwarp();
         // ---- phase B: the parked rays test their bricks together (:329-342)
         if (parked) {
             parked = false;
@@ -233,9 +259,11 @@ VRT_DI bool grid_hit_warp(const TraceParams& P, const Ray& r, bool active, bool 
                 if (COUNT) ti.grid_index = grid_index, ti.voxel_index = (uint32_t)voxel_index;
                 result = true;
                 marching = false;
-            } else {
-                march_step(sx, sy, sz, dx, dy, dz, stx, sty, stz, idx, last_stride, t_side);  // :345-372, then look the next cell up
-                safe = 0;
+            } else {  // :345-372, then the next cell is looked up
+                t_side = fminf(fminf(sx, sy), sz);
+                const int before = idx;
+                march_step(sx, sy, sz, dx, dy, dz, stx, sty, stz, idx);
+                last_stride = idx - before;
             }
         }
     }
