@@ -265,21 +265,42 @@ def main():
     total_ms = float(sum(step_ms))
 
     # ---------------------------------------------------------------- end-to-end through the C ABI with host buffers
-    host_frame = torch.empty(n_pixels * 4, dtype=torch.uint8).pin_memory()
-    e2e_s = 0.0
-    for i in range(3 + args.steps):
+    # (a) frame latency: vrt_trace_to_host per frame, blocking (camera+sun from host structs -> frame in pinned host memory)
+    host_frames = [torch.empty(n_pixels * 4, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    lat_s = 0.0
+    n_lat = min(args.steps, 50)
+    for i in range(3 + n_lat):
         flush.fill_(i & 0xFF)
         barrier()
         t0 = time.perf_counter()
         if rank == 0:
-            ctx.trace_to_host(cam, sun, out_ptr=host_frame.data_ptr())  # camera+sun: host structs; frame -> pinned host memory
+            ctx.trace_to_host(cam, sun, out_ptr=host_frames[0].data_ptr())
         else:
             ctx.trace(cam, sun)
             ctx.sync()
         if world > 1:
             dist.barrier()
         if i >= 3:
-            e2e_s += time.perf_counter() - t0
+            lat_s += time.perf_counter() - t0
+    # (b) frame throughput: the same call pipelined (vrt_trace_to_host_async, 2 frames in flight: the copy of frame k
+    # overlaps the trace of frame k+1).  The L2 flush is enqueued between frames INSIDE the timed region.
+    use_async = not (world > 1 and args.exchange == "peer")
+    for i in range(3):
+        ctx.trace_to_host_async(cam, sun, host_frames[i & 1].data_ptr()) if (rank == 0 and use_async) else ctx.trace(cam, sun)
+    ctx.sync()
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF)
+        if rank == 0 and use_async:
+            ctx.trace_to_host_async(cam, sun, host_frames[i & 1].data_ptr())
+        elif rank == 0:
+            ctx.trace_to_host(cam, sun, out_ptr=host_frames[i & 1].data_ptr())
+        else:
+            ctx.trace(cam, sun)
+    ctx.sync()
+    barrier()
+    e2e_s = time.perf_counter() - t0
 
     t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev)
     r = torch.tensor([float(my_rays), float(my_alg_bytes)], dtype=torch.float64, device=dev)
@@ -314,7 +335,9 @@ def main():
                          "peak_kind": peak_kind, "algorithmic_bytes_per_launch": int(my_alg_bytes), "kernel_ms": ms_per_step,
                          "note": "request-byte model of the reference algorithm (DESIGN.md); rank 0's launch"},
             "e2e": {"value": rays * args.steps / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 128, "d2h_bytes_per_step": n_pixels * 4,
-                    "ms_per_step": e2e_s / args.steps * 1e3},
+                    "ms_per_step": e2e_s / args.steps * 1e3, "frame_latency_ms": lat_s / n_lat * 1e3,
+                    "how": "vrt_trace_to_host_async per frame (camera+sun host structs in, RGBA8 frame into pinned host memory, 2 frames in flight), "
+                           "L2 flush enqueued between frames inside the timed region; frame_latency_ms = blocking vrt_trace_to_host"},
             "gpu_launches": launches_per_step * args.steps, "wall_ms": wall_ms, "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -191,6 +191,15 @@ int vrt_read_framebuffer(vrt_ctx* ctx, uint8_t* rgba8_host, size_t bytes);
  * written).  Blocks until the pixels are in host memory. */
 int vrt_trace_to_host(vrt_ctx* ctx, const vrt_camera* camera, const vrt_sun* sun, uint8_t* rgba8_host, size_t bytes);
 
+/* The same frame for a STREAM of frames: enqueue the trace and the device->host copy of this context's rows and return
+ * without waiting.  Two frames may be in flight (the context double-buffers its framebuffer and copies on a second
+ * stream), so the copy of frame k overlaps the trace of frame k+1 — the CUDA counterpart of the reference keeping one
+ * compute frame in flight while the previous one is presented (ComputePipeline.zig:423-434, Pipeline.zig:494-517).
+ * `rgba8_host` must stay valid until vrt_sync() (or until two further async calls have been made) and should be pinned
+ * host memory, otherwise the copy is staged and does not overlap.  Not available while a caller-owned framebuffer is
+ * attached or in VRT_EXCHANGE_PEER_STORE mode (VRT_E_STATE). */
+int vrt_trace_to_host_async(vrt_ctx* ctx, const vrt_camera* camera, const vrt_sun* sun, uint8_t* rgba8_host, size_t bytes);
+
 /* Debug / parity (requires VRT_FLAG_AOV). */
 int vrt_read_aov(vrt_ctx* ctx, vrt_aov* aov_host, size_t count);
 int vrt_get_counters(vrt_ctx* ctx, vrt_counters* out);

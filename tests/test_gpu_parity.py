@@ -275,3 +275,25 @@ def test_c4_brickmap_extension(materials):
     ref_img, ref_aov, _ = orc.OracleScene.from_grid(grid, materials).render(cam, sun, aov=True)
     img, aov, _ = trace(grid, materials, cam, sun, ffi.VRT_FLAG_AOV)
     assert_same(img, aov, ref_img, ref_aov)
+
+
+def test_pipelined_frames_match_blocking_frames(materials):
+    """vrt_trace_to_host_async: 6 frames of the fly-through with two in flight, each into its own pinned buffer; every
+    frame must equal the blocking call's frame (and the oracle's) — no frame may be overwritten before it reached the host."""
+    import torch
+
+    grid = scenes.build_grid(64)
+    sun = scenes.sun(True)
+    cams = [scenes.camera_from_pose(160, 96, o, q) for o, q in scenes.sweep_poses(6)]
+    ctx = ffi.Context(160, 96, len(grid.brick_indices))
+    ctx.upload_grid(grid, materials)
+    bufs = [torch.zeros(96, 160, 4, dtype=torch.uint8).pin_memory() for _ in cams]
+    for cam, buf in zip(cams, bufs):
+        ctx.trace_to_host_async(cam, sun, buf.data_ptr())
+    ctx.sync()
+    sc = orc.OracleScene.from_grid(grid, materials)
+    for cam, buf in zip(cams, bufs):
+        ref, _, _ = sc.render(cam, sun)
+        assert np.array_equal(buf.numpy(), ref)
+        assert np.array_equal(ctx.trace_to_host(cam, sun), ref)
+    ctx.close()

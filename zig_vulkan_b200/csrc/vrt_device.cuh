@@ -255,7 +255,8 @@ struct TraceParams {
     unsigned long long* counters; // nullable, 8 x u64 in vrt_counters order
     // derived acceleration structures (built on the device from the buffers above, vrt_kernels.cu "build_*")
     const unsigned long long* occ_dense;  // [n_bricks] 4^3 voxel mask per GRID cell (brick_dim == 4 only)
-    const uint8_t* dist;                  // padded Chebyshev distance grid, see vrt_trav_warp.cuh
+    const uint8_t* dist;                  // 8 padded directional Chebyshev distance grids (one per octant), see vrt_trav_warp.cuh
+    unsigned long long dist_plane;        // bytes per octant
     uint32_t dist_log_px, dist_log_pz;    // row / plane strides of `dist` are powers of two: x + (z << log_px) + (y << (log_px+log_pz))
     uint32_t scale_pow2, voxel_scale_pow2;  // brick / voxel scale is a power of two -> divide by multiplying with the exact inverse
     float inv_scale, inv_voxel_scale;

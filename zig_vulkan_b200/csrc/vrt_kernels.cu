@@ -3,6 +3,8 @@
 // Compile with:  nvcc -gencode arch=compute_100a,code=sm_100a --fmad=false -lineinfo  (see Makefile).
 // --fmad=false is part of the contract: parity with the oracle is bit-exact only if no mul+add pair is
 // contracted beyond the explicit fmaf() calls (DESIGN.md "FP discipline").
+#include <cstdlib>
+
 #include "vrt_kernels.cuh"
 #include "vrt_shade.cuh"
 #include "vrt_shade_warp.cuh"
@@ -36,8 +38,8 @@ __global__ void __launch_bounds__(256) trace_ref_kernel(const __grid_constant__ 
 constexpr int kTunedThreads = 256;
 constexpr uint32_t kTileW = 8, kTileH = 4;
 
-template <int BD, bool AOV>
-__global__ void __launch_bounds__(kTunedThreads, 2) trace_warp_kernel(const __grid_constant__ TraceParams P, const uint32_t tiles_x, const uint32_t tiles_total) {
+template <int BD, bool AOV, int MINB = 3>
+__global__ void __launch_bounds__(kTunedThreads, MINB) trace_warp_kernel(const __grid_constant__ TraceParams P, const uint32_t tiles_x, const uint32_t tiles_total) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t lx = lane & (kTileW - 1u), ly = lane >> 3;
     const uint32_t width = P.cam.image_width;
@@ -73,10 +75,10 @@ __global__ void __launch_bounds__(kTunedThreads, 2) trace_warp_kernel(const __gr
     if (AOV) flush_counters(P, pc);
 }
 
-template <int BD, bool AOV>
+template <int BD, bool AOV, int MINB = 3>
 cudaError_t launch_warp_kernel(const TraceParams& P, int num_sms, cudaStream_t stream, LaunchInfo* info) {
     int blocks_per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, trace_warp_kernel<BD, AOV>, kTunedThreads, 0);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, trace_warp_kernel<BD, AOV, MINB>, kTunedThreads, 0);
     if (e != cudaSuccess) return e;
     if (blocks_per_sm < 1) return cudaErrorLaunchOutOfResources;
     const uint32_t rows = P.row_end - P.row_begin;
@@ -87,7 +89,7 @@ cudaError_t launch_warp_kernel(const TraceParams& P, int num_sms, cudaStream_t s
     uint32_t grid = (uint32_t)(num_sms * blocks_per_sm);  // one resident wave: a multiple of the SM count
     const uint32_t needed = (tiles_total + warps_per_block - 1) / warps_per_block;
     if (grid > needed) grid = needed;
-    trace_warp_kernel<BD, AOV><<<grid, kTunedThreads, 0, stream>>>(P, tiles_x, tiles_total);
+    trace_warp_kernel<BD, AOV, MINB><<<grid, kTunedThreads, 0, stream>>>(P, tiles_x, tiles_total);
     if (info) {
         info->launches++;
         info->counter_advance = (unsigned long long)tiles_total + (unsigned long long)grid * warps_per_block;  // every warp overshoots once
@@ -103,6 +105,11 @@ cudaError_t launch_trace_tuned(const TraceParams& P, bool aov, cudaStream_t stre
     if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
     if (sm_count[dev] == 0 && (e = cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
     const int n = sm_count[dev];
+    if (P.brick_dim == 4 && !aov) {  // EXPERIMENT: occupancy variants
+        const char* v = getenv("VRT_TUNE_BLOCKS");
+        if (v && v[0] == '2') return launch_warp_kernel<4, false, 2>(P, n, stream, info);
+        if (v && v[0] == '4') return launch_warp_kernel<4, false, 4>(P, n, stream, info);
+    }
     if (P.brick_dim == 4) return aov ? launch_warp_kernel<4, true>(P, n, stream, info) : launch_warp_kernel<4, false>(P, n, stream, info);
     return aov ? launch_warp_kernel<0, true>(P, n, stream, info) : launch_warp_kernel<0, false>(P, n, stream, info);
 }
@@ -125,66 +132,75 @@ __global__ void __launch_bounds__(256) build_occ_dense_kernel(const __grid_const
     occ_dense[g] = occ;
 }
 
-// Chebyshev distance transform, separable: three 1-D passes (x, z, y).  After pass k a cell holds
-// min over blockers q sharing the not-yet-processed coordinates of max |p_a - q_a| over the processed axes a;
-// blockers are loaded bricks (status bit set) and everything outside the grid.  Values are capped at 254.
+// Directional Chebyshev distance transform.  For each of the 8 direction octants o (bit0: x decreasing, bit1: y
+// decreasing, bit2: z decreasing) dist[o][p] = min over blockers q in the closed octant of p (every coordinate of
+// q - p has the octant's sign or is 0) of max_a |q_a - p_a|; blockers are loaded bricks (status bit set) and every cell
+// outside the grid.  A DDA only ever moves along its own octant, so a ray at p can take dist-1 steps blind.
+// Separable: three one-sided 1-D passes (x, z, y), each a bounded scan with early exit; values are capped at 254.
 constexpr int kDistCap = 254;
 
+// pass x: blockIdx.y = 0 scans towards +x, 1 towards -x; out[v][g]
 __global__ void __launch_bounds__(256) dist_pass_x_kernel(const __grid_constant__ TraceParams P, uint8_t* __restrict__ out, size_t n_bricks) {
     const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n_bricks) return;
+    const int neg = (int)blockIdx.y;
     const int dim_x = (int)P.grid.dim_x;
     const int x = (int)(g % dim_x);
     const size_t row = g - x;
-    int best = min(min(x + 1, dim_x - x), kDistCap);
+    int best = min(neg ? x + 1 : dim_x - x, kDistCap);  // distance to the first cell outside the grid
     for (int k = 0; k < best; k++) {
-        if ((x - k >= 0 && status_bit(P, row + x - k)) || (x + k < dim_x && status_bit(P, row + x + k))) best = k;
+        if (status_bit(P, row + (neg ? x - k : x + k))) best = k;
     }
-    out[g] = (uint8_t)best;
+    out[(size_t)neg * n_bricks + g] = (uint8_t)best;
 }
 
-// generic 1-D pass along an axis with element stride `stride` and extent `dim`; `coord` = this cell's coordinate on it
-VRT_DI int dist_scan(const uint8_t* __restrict__ in, size_t g, int coord, int dim, size_t stride) {
-    int best = min(min(coord + 1, dim - coord), kDistCap);
+// one-sided 1-D pass along an axis with element stride `stride` and extent `dim`; `coord` = this cell's coordinate on it
+VRT_DI int dist_scan(const uint8_t* __restrict__ in, size_t g, int coord, int dim, size_t stride, int neg) {
+    int best = min(neg ? coord + 1 : dim - coord, kDistCap);
     for (int k = 0; k < best; k++) {
-        if (coord - k >= 0) best = min(best, max(k, (int)in[g - (size_t)k * stride]));
-        if (coord + k < dim) best = min(best, max(k, (int)in[g + (size_t)k * stride]));
+        const int v = (int)in[neg ? g - (size_t)k * stride : g + (size_t)k * stride];
+        best = min(best, max(k, v));
     }
     return best;
 }
 
+// pass z: blockIdx.y = xneg | zneg << 1; in[xneg][g] -> out[xneg | zneg<<1][g]
 __global__ void __launch_bounds__(256) dist_pass_z_kernel(const __grid_constant__ TraceParams P, const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
                                                           size_t n_bricks) {
     const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n_bricks) return;
+    const int v = (int)blockIdx.y, xneg = v & 1, zneg = v >> 1;
     const int z = (int)((g / P.grid.dim_x) % P.grid.dim_z);
-    out[g] = (uint8_t)dist_scan(in, g, z, (int)P.grid.dim_z, P.grid.dim_x);
+    out[(size_t)v * n_bricks + g] = (uint8_t)dist_scan(in + (size_t)xneg * n_bricks, g, z, (int)P.grid.dim_z, P.grid.dim_x, zneg);
 }
 
-// last pass (y) writes the padded layout the march indexes: (x+1) + ((z+1) << log_px) + ((y+1) << (log_px+log_pz))
+// pass y: blockIdx.y = octant = xneg | yneg << 1 | zneg << 2; writes the padded layout the march indexes:
+// dist[octant * plane + (x+1) + ((z+1) << log_px) + ((y+1) << (log_px+log_pz))]
 __global__ void __launch_bounds__(256) dist_pass_y_kernel(const __grid_constant__ TraceParams P, const uint8_t* __restrict__ in, uint8_t* __restrict__ dist,
                                                           size_t n_bricks) {
     const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n_bricks) return;
+    const int oct = (int)blockIdx.y, xneg = oct & 1, yneg = (oct >> 1) & 1, zneg = oct >> 2;
     const uint32_t x = (uint32_t)(g % P.grid.dim_x);
     const uint32_t z = (uint32_t)((g / P.grid.dim_x) % P.grid.dim_z);
     const uint32_t y = (uint32_t)(g / ((size_t)P.grid.dim_x * P.grid.dim_z));
-    const int d = dist_scan(in, g, (int)y, (int)P.grid.dim_y, (size_t)P.grid.dim_x * P.grid.dim_z);
-    dist[(size_t)(x + 1) + ((size_t)(z + 1) << P.dist_log_px) + ((size_t)(y + 1) << (P.dist_log_px + P.dist_log_pz))] = (uint8_t)d;
+    const int d = dist_scan(in + (size_t)(xneg | (zneg << 1)) * n_bricks, g, (int)y, (int)P.grid.dim_y, (size_t)P.grid.dim_x * P.grid.dim_z, yneg);
+    dist[(size_t)oct * P.dist_plane + (size_t)(x + 1) + ((size_t)(z + 1) << P.dist_log_px) + ((size_t)(y + 1) << (P.dist_log_px + P.dist_log_pz))] = (uint8_t)d;
 }
 
-cudaError_t launch_build_accel(const TraceParams& P, unsigned long long* occ_dense, uint8_t* dist, size_t dist_bytes, uint8_t* tmp_a, uint8_t* tmp_b,
-                               size_t n_bricks, cudaStream_t stream, LaunchInfo* info) {
+// tmp: 6 * n_bricks bytes of scratch.  The border bytes of `dist` (255) are written once when it is allocated.
+cudaError_t launch_build_accel(const TraceParams& P, unsigned long long* occ_dense, uint8_t* dist, uint8_t* tmp, size_t n_bricks, cudaStream_t stream,
+                               LaunchInfo* info) {
     const unsigned blocks = (unsigned)((n_bricks + 255) / 256);
     if (occ_dense) {
         build_occ_dense_kernel<<<blocks, 256, 0, stream>>>(P, occ_dense, n_bricks);
         if (info) info->launches++;
     }
-    cudaError_t e = cudaMemsetAsync(dist, (int)kDistBorder, dist_bytes, stream);
-    if (e != cudaSuccess) return e;
-    dist_pass_x_kernel<<<blocks, 256, 0, stream>>>(P, tmp_a, n_bricks);
-    dist_pass_z_kernel<<<blocks, 256, 0, stream>>>(P, tmp_a, tmp_b, n_bricks);
-    dist_pass_y_kernel<<<blocks, 256, 0, stream>>>(P, tmp_b, dist, n_bricks);
+    uint8_t* tmp_x = tmp;                 // [2][n]
+    uint8_t* tmp_z = tmp + 2 * n_bricks;  // [4][n]
+    dist_pass_x_kernel<<<dim3(blocks, 2), 256, 0, stream>>>(P, tmp_x, n_bricks);
+    dist_pass_z_kernel<<<dim3(blocks, 4), 256, 0, stream>>>(P, tmp_x, tmp_z, n_bricks);
+    dist_pass_y_kernel<<<dim3(blocks, 8), 256, 0, stream>>>(P, tmp_z, dist, n_bricks);
     if (info) info->launches += 3;
     return cudaGetLastError();
 }

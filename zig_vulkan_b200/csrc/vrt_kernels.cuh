@@ -18,9 +18,9 @@ struct LaunchInfo {
 // Enqueue the kernels that trace rows [P.row_begin, P.row_end) into P.fb.
 cudaError_t launch_trace(const TraceParams& P, TraceKernel which, bool aov, cudaStream_t stream, LaunchInfo* info);
 
-// Rebuild the derived structures (occ_dense, dist) from the reference-format buffers.  tmp_a / tmp_b: n_bricks bytes each.
-cudaError_t launch_build_accel(const TraceParams& P, unsigned long long* occ_dense, uint8_t* dist, size_t dist_bytes, uint8_t* tmp_a, uint8_t* tmp_b,
-                               size_t n_bricks, cudaStream_t stream, LaunchInfo* info);
+// Rebuild the derived structures (occ_dense, dist) from the reference-format buffers.  tmp: 6 * n_bricks bytes.
+cudaError_t launch_build_accel(const TraceParams& P, unsigned long long* occ_dense, uint8_t* dist, uint8_t* tmp, size_t n_bricks, cudaStream_t stream,
+                               LaunchInfo* info);
 cudaError_t launch_trace_tuned(const TraceParams& P, bool aov, cudaStream_t stream, LaunchInfo* info);
 
 }  // namespace vrt

@@ -92,7 +92,12 @@ struct vrt_ctx {
     uint32_t* d_fb_own = nullptr;
     uint32_t* d_fb = nullptr;
     size_t fb_bytes = 0;
-    uint8_t* h_pinned_fb = nullptr;  // bounce buffer for vrt_trace_to_host into pageable memory
+    // vrt_trace_to_host_async: second framebuffer + copy stream + per-slot events
+    uint32_t* d_fb_ring1 = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_traced[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+    bool slot_used[2] = {false, false};
+    uint64_t async_frames = 0;
 
     // debug
     vrt_aov* d_aov = nullptr;
@@ -101,8 +106,8 @@ struct vrt_ctx {
     // derived acceleration structures (vrt_trav_warp.cuh)
     unsigned long long* d_occ_dense = nullptr;
     uint8_t* d_dist = nullptr;
-    uint8_t* d_dist_tmp = nullptr;  // 2 x n_bricks bytes of scratch for the separable distance transform
-    size_t dist_bytes = 0;
+    uint8_t* d_dist_tmp = nullptr;  // 6 x n_bricks bytes of scratch for the separable distance transform
+    size_t dist_plane = 0;          // bytes per octant
     uint32_t dist_log_px = 0, dist_log_pz = 0;
     uint32_t accel_dim[3] = {0, 0, 0};
     bool accel_dirty = true;
@@ -182,6 +187,7 @@ void fill_params(const vrt_ctx* c, const vrt_camera* cam, const vrt_sun* sun, Tr
     P.counters = c->d_counters;
     P.occ_dense = c->d_occ_dense;
     P.dist = c->d_dist;
+    P.dist_plane = c->dist_plane;
     P.dist_log_px = c->dist_log_px, P.dist_log_pz = c->dist_log_pz;
     const float scale = c->grid.max_point_scale[3];
     const float voxel_scale = scale * P.brick_voxel_scale;  // :389, same f32 product the kernels form
@@ -210,10 +216,12 @@ int ensure_accel(vrt_ctx* ctx) {
     while ((1u << lx) < dx + 2) lx++;  // one border cell on each side; power-of-two strides make the index decodable with shifts
     while ((1u << lz) < dz + 2) lz++;
     ctx->dist_log_px = lx, ctx->dist_log_pz = lz;
-    ctx->dist_bytes = ((size_t)(dy + 2)) << (lx + lz);
-    if (ctx->dist_bytes > 0x7fffffffull) return fail(ctx, VRT_E_INVALID, "grid %ux%ux%u is too large for the 31-bit cell index of the march", dx, dy, dz);
-    VRT_CUDA(ctx, cudaMalloc(&ctx->d_dist, ctx->dist_bytes));
-    VRT_CUDA(ctx, cudaMalloc(&ctx->d_dist_tmp, 2 * (size_t)dx * dy * dz));
+    ctx->dist_plane = ((size_t)(dy + 2)) << (lx + lz);
+    if (8 * ctx->dist_plane > 0x7fffffffull)
+        return fail(ctx, VRT_E_INVALID, "grid %ux%ux%u is too large for the 31-bit cell index of the march (8 padded distance planes)", dx, dy, dz);
+    VRT_CUDA(ctx, cudaMalloc(&ctx->d_dist, 8 * ctx->dist_plane));
+    VRT_CUDA(ctx, cudaMalloc(&ctx->d_dist_tmp, 6 * (size_t)dx * dy * dz));
+    VRT_CUDA(ctx, cudaMemsetAsync(ctx->d_dist, 255, 8 * ctx->dist_plane, ctx->stream));  // the border; interiors are rewritten by every build
     ctx->accel_dim[0] = dx, ctx->accel_dim[1] = dy, ctx->accel_dim[2] = dz;
     ctx->accel_dirty = true;
     return VRT_OK;
@@ -330,7 +338,13 @@ void vrt_deinit(vrt_ctx* ctx) {
     cudaFree(ctx->d_start_indices), cudaFree(ctx->d_material_indices), cudaFree(ctx->d_fb_own), cudaFree(ctx->d_aov);
     cudaFree(ctx->d_counters), cudaFree(ctx->d_occ_dense), cudaFree(ctx->d_dist), cudaFree(ctx->d_dist_tmp);
     cudaFree(ctx->d_tile_counter);
-    if (ctx->h_pinned_fb) cudaFreeHost(ctx->h_pinned_fb);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    cudaFree(ctx->d_fb_ring1);
+    for (int i = 0; i < 2; i++) {
+        if (ctx->ev_traced[i]) cudaEventDestroy(ctx->ev_traced[i]);
+        if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
+    }
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
     if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -402,8 +416,7 @@ int vrt_trace(vrt_ctx* ctx, const vrt_camera* camera, const vrt_sun* sun) {
         // gives upload -> build -> trace, where the reference has no barrier at all between its staging
         // copy and the next dispatch (edits land one frame late, Pipeline.zig:540).
         const size_t n_cells = (size_t)ctx->grid.dim_x * ctx->grid.dim_y * ctx->grid.dim_z;
-        VRT_CUDA(ctx, launch_build_accel(P, ctx->d_occ_dense, ctx->d_dist, ctx->dist_bytes, ctx->d_dist_tmp, ctx->d_dist_tmp + n_cells, n_cells, ctx->stream,
-                                         &info));
+        VRT_CUDA(ctx, launch_build_accel(P, ctx->d_occ_dense, ctx->d_dist, ctx->d_dist_tmp, n_cells, ctx->stream, &info));
         ctx->accel_dirty = false;
     }
     if (aov) VRT_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
@@ -428,6 +441,45 @@ int vrt_sync(vrt_ctx* ctx) {
     if (!ctx) return VRT_E_INVALID;
     VRT_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
     VRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->copy_stream) VRT_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    return VRT_OK;
+}
+
+int vrt_trace_to_host_async(vrt_ctx* ctx, const vrt_camera* camera, const vrt_sun* sun, uint8_t* rgba8_host, size_t bytes) {
+    if (!ctx) return VRT_E_INVALID;
+    if (!rgba8_host || bytes != ctx->fb_bytes) return fail(ctx, VRT_E_INVALID, "vrt_trace_to_host_async: need a %zu-byte buffer", ctx->fb_bytes);
+    if (ctx->d_fb != ctx->d_fb_own && ctx->d_fb != ctx->d_fb_ring1)
+        return fail(ctx, VRT_E_STATE, "vrt_trace_to_host_async: not available while a caller-owned framebuffer is attached");
+    if (ctx->world > 1 && ctx->exchange_mode == VRT_EXCHANGE_PEER_STORE)
+        return fail(ctx, VRT_E_STATE, "vrt_trace_to_host_async: not available in VRT_EXCHANGE_PEER_STORE mode");
+    VRT_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    if (!ctx->copy_stream) {  // first use: second framebuffer, copy stream, events
+        VRT_CUDA(ctx, cudaMalloc(&ctx->d_fb_ring1, ctx->fb_bytes));
+        VRT_CUDA(ctx, cudaMemsetAsync(ctx->d_fb_ring1, 0, ctx->fb_bytes, ctx->stream));
+        VRT_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            VRT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_traced[i], cudaEventDisableTiming));
+            VRT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
+        }
+    }
+    const int slot = (int)(ctx->async_frames & 1u);
+    uint32_t* const fb = slot ? ctx->d_fb_ring1 : ctx->d_fb_own;
+    // the trace may not overwrite this slot before its previous contents (frame k-2) have reached the host
+    if (ctx->slot_used[slot]) VRT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[slot], 0));
+    uint32_t* const saved = ctx->d_fb;
+    ctx->d_fb = fb;
+    const int rc = vrt_trace(ctx, camera, sun);
+    ctx->d_fb = saved;
+    if (rc != VRT_OK) return rc;
+    VRT_CUDA(ctx, cudaEventRecord(ctx->ev_traced[slot], ctx->stream));
+    VRT_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_traced[slot], 0));
+    const size_t off = (size_t)ctx->row_begin * ctx->cfg.width * 4;
+    const size_t n = (ctx->world > 1) ? ctx->fb_bytes : (size_t)(ctx->row_end - ctx->row_begin) * ctx->cfg.width * 4;
+    const size_t from = (ctx->world > 1) ? 0 : off;
+    VRT_CUDA(ctx, cudaMemcpyAsync(rgba8_host + from, reinterpret_cast<const uint8_t*>(fb) + from, n, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    VRT_CUDA(ctx, cudaEventRecord(ctx->ev_copied[slot], ctx->copy_stream));
+    ctx->slot_used[slot] = true;
+    ctx->async_frames++;
     return VRT_OK;
 }
 

@@ -5,10 +5,11 @@
 // one multiply would round differently and can flip which voxel is hit.  What changes is everything
 // AROUND that arithmetic:
 //
-//   * Safe-step counts instead of per-cell occupancy tests.  A derived byte grid `dist` holds, per brick cell, the
-//     Chebyshev distance D (in cells) to the nearest loaded brick or grid face (0 = loaded brick, 255 = the one-cell
-//     border around the grid).  From a cell with distance D the next D-1 DDA steps cannot land on a loaded brick or
-//     leave the grid (each step moves one cell along one axis), so they run with no memory access and no bounds test:
+//   * Safe-step counts instead of per-cell occupancy tests.  A derived byte grid `dist` holds, per brick cell and per
+//     direction octant, the Chebyshev distance D (in cells) to the nearest loaded brick or grid face lying in that octant
+//     (0 = loaded brick, 255 = the one-cell border around the grid).  A DDA only moves along its own octant, one cell
+//     along one axis per step, so from a cell with distance D the next D-1 steps cannot land on a loaded brick or
+//     leave the grid and run with no memory access and no bounds test:
 //     four compares, predicated FADDs and IADDs.  Only the D-th step is followed by a lookup.
 //     The border makes "left the grid" a byte value, so the march carries ONE linear index, not three coordinates.
 //   * Warp rounds.  The 32 rays of a tile look their cells up TOGETHER, reduce the distances found to the warp minimum
@@ -189,11 +190,18 @@ VRT_DI bool grid_hit_warp(const TraceParams& P, const Ray& r, bool active, bool 
         }
     }
     const float dx = ray_delta.x, dy = ray_delta.y, dz = ray_delta.z;
+    // `idx` addresses the distance grid of this ray's direction octant (a zero step never moves, either sign's grid is
+    // valid for it): the octant's plane offset is folded into the index and removed again when a cell is decoded
+    const int obase = (int)(((ray_step.x < 0 ? 1u : 0u) | (ray_step.y < 0 ? 2u : 0u) | (ray_step.z < 0 ? 4u : 0u)) * (uint32_t)P.dist_plane);
+    idx += obase;
     const uint8_t* __restrict__ dist = P.dist;
     int last_stride = 0;  // stride of the most recent step (0: none yet -> slab normal)
     bool parked = false, result = false;
     uint32_t cnt_word = ~0u;  // COUNT: the reference's one-word status cache (:301,:321-326)
     constexpr uint32_t kIdle = 0xffffu;
+    // deltas / strides actually applied in the step loop: zero while this lane is parked or finished
+    float fdx = marching ? dx : 0.0f, fdy = marching ? dy : 0.0f, fdz = marching ? dz : 0.0f;
+    int fsx = stx, fsy = sty, fsz = stz;  // (stx.. are 0 when not marching)
 
     while (__any_sync(kFullMask, marching)) {
         // ---- phase A (:313-373 without the per-cell tests): rounds of { every marching ray looks its cell up; all of
@@ -210,7 +218,7 @@ VRT_DI bool grid_hit_warp(const TraceParams& P, const Ray& r, bool active, bool 
                 } else {
                     if (COUNT) {  // an in-grid cell = one iteration of the shader's loop; emulate its one-word status cache (:321-326)
                         ti.grid_steps++;
-                        const uint32_t gi = cell_grid_index(P, idx, log_px, log_pzx);
+                        const uint32_t gi = cell_grid_index(P, idx - obase, log_px, log_pzx);
                         if ((gi >> 5) != cnt_word) cnt_word = gi >> 5, ti.status_fetches++;
                     }
                     if (d == 0u) {
@@ -222,13 +230,12 @@ VRT_DI bool grid_hit_warp(const TraceParams& P, const Ray& r, bool active, bool 
             const uint32_t k = __reduce_min_sync(kFullMask, d);
             if (k == kIdle) break;
             const bool on = d != kIdle;
-            const float fdx = on ? dx : 0.0f, fdy = on ? dy : 0.0f, fdz = on ? dz : 0.0f;
-            const int fsx = on ? stx : 0, fsy = on ? sty : 0, fsz = on ? stz : 0;
+            if (!on) fdx = fdy = fdz = 0.0f, fsx = fsy = fsz = 0;
             for (uint32_t i = 1; i < k; i++) {  // k-1 steps onto cells known to be empty and inside
                 march_step(sx, sy, sz, fdx, fdy, fdz, fsx, fsy, fsz, idx);
                 if (COUNT && on) {
                     ti.grid_steps++;
-                    const uint32_t gi = cell_grid_index(P, idx, log_px, log_pzx);
+                    const uint32_t gi = cell_grid_index(P, idx - obase, log_px, log_pzx);
                     if ((gi >> 5) != cnt_word) cnt_word = gi >> 5, ti.status_fetches++;
                 }
             }
@@ -245,7 +252,8 @@ VRT_DI bool grid_hit_warp(const TraceParams& P, const Ray& r, bool active, bool 
                 const int a = last_stride < 0 ? -last_stride : last_stride;
                 n = step_normal(a == 1 ? 0 : (a == (1 << log_px) ? 2 : 1), ray_step);
             }
-            const int x = (idx & ((1 << log_px) - 1)) - 1, z = ((idx >> log_px) & ((1 << (log_pzx - log_px)) - 1)) - 1, y = (idx >> log_pzx) - 1;
+            const int cell = idx - obase;
+            const int x = (cell & ((1 << log_px) - 1)) - 1, z = ((cell >> log_px) & ((1 << (log_pzx - log_px)) - 1)) - 1, y = (cell >> log_pzx) - 1;
             const uint32_t grid_index = (uint32_t)(x + (int)P.grid.dim_x * (z + (int)P.grid.dim_z * y));  // :318
             unsigned long long occ = 0ull;
             if (BD == 4) occ = __ldg(P.occ_dense + grid_index);
@@ -264,6 +272,7 @@ VRT_DI bool grid_hit_warp(const TraceParams& P, const Ray& r, bool active, bool 
                 const int before = idx;
                 march_step(sx, sy, sz, dx, dy, dz, stx, sty, stz, idx);
                 last_stride = idx - before;
+                fdx = dx, fdy = dy, fdz = dz, fsx = stx, fsy = sty, fsz = stz;  // marching again
             }
         }
     }

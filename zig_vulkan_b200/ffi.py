@@ -135,6 +135,7 @@ VRT_SYMBOLS = {
     "vrt_sync": (C.c_int, [_P]),
     "vrt_read_framebuffer": (C.c_int, [_P, _P, _SZ]),
     "vrt_trace_to_host": (C.c_int, [_P, C.POINTER(CameraDevice), C.POINTER(SunDevice), _P, _SZ]),
+    "vrt_trace_to_host_async": (C.c_int, [_P, C.POINTER(CameraDevice), C.POINTER(SunDevice), _P, _SZ]),
     "vrt_read_aov": (C.c_int, [_P, _P, _SZ]),
     "vrt_get_counters": (C.c_int, [_P, C.POINTER(Counters)]),
     "vrt_last_trace_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
@@ -522,6 +523,10 @@ class Context:
             out = np.empty((self.height, self.width, 4), dtype=np.uint8)
         self._check(self._l.vrt_trace_to_host(self.handle, C.byref(camera), C.byref(sun), _ptr(out), nbytes))
         return out
+
+    def trace_to_host_async(self, camera: CameraDevice, sun: SunDevice, out_ptr: int):
+        """Pipelined frame: returns after enqueueing; `out_ptr` (pinned host memory, width*height*4 bytes) is valid after sync()."""
+        self._check(self._l.vrt_trace_to_host_async(self.handle, C.byref(camera), C.byref(sun), C.c_void_p(out_ptr), self.width * self.height * 4))
 
     def read_aov(self) -> np.ndarray:
         out = np.empty(self.height * self.width, dtype=AOV_DTYPE)
