@@ -137,7 +137,36 @@ __global__ void __launch_bounds__(256) build_occ_dense_kernel(const __grid_const
 // q - p has the octant's sign or is 0) of max_a |q_a - p_a|; blockers are loaded bricks (status bit set) and every cell
 // outside the grid.  A DDA only ever moves along its own octant, so a ray at p can take dist-1 steps blind.
 // Separable: three one-sided 1-D passes (x, z, y), each a bounded scan with early exit; values are capped at 254.
-constexpr int kDistCap = 254;
+constexpr int kDistCap = 126;  // 7 bits; bit 7 of a dist byte = "no loaded brick anywhere in this octant" (kDistFree)
+
+// "Is there any loaded brick in the closed octant of this cell": three OR-scans along x, z, y.  One thread per line and
+// output variant; a line is walked once from its far end, so the cost is O(cells) whatever the scene.
+//   axis 0 (x): in = status bits,            variants v = xneg                       -> out[v]
+//   axis 1 (z): in = out of axis 0 [xneg],   variants v = xneg | zneg << 1           -> out[v]
+//   axis 2 (y): in = out of axis 1 [x|z<<1], variants v = xneg | yneg << 1 | zneg << 2 -> out[v]
+__global__ void __launch_bounds__(128) any_scan_kernel(const __grid_constant__ TraceParams P, const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
+                                                       size_t n_bricks, int axis) {
+    const size_t dim_x = P.grid.dim_x, dim_y = P.grid.dim_y, dim_z = P.grid.dim_z;
+    const size_t lines = axis == 0 ? dim_z * dim_y : (axis == 1 ? dim_x * dim_y : dim_x * dim_z);
+    const size_t line = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (line >= lines) return;
+    const int v = (int)blockIdx.y;
+    size_t base, stride;
+    int len, neg, vin;
+    if (axis == 0) {
+        base = line * dim_x, stride = 1, len = (int)dim_x, neg = v & 1, vin = 0;
+    } else if (axis == 1) {
+        base = (line % dim_x) + dim_x * dim_z * (line / dim_x), stride = dim_x, len = (int)dim_z, neg = v >> 1, vin = v & 1;
+    } else {
+        base = line, stride = dim_x * dim_z, len = (int)dim_y, neg = (v >> 1) & 1, vin = (v & 1) | ((v >> 2) << 1);
+    }
+    uint8_t acc = 0;
+    for (int i = 0; i < len; i++) {
+        const size_t g = base + (size_t)(neg ? i : len - 1 - i) * stride;  // walk from the end the octant looks towards
+        acc |= axis == 0 ? (uint8_t)status_bit(P, g) : in[(size_t)vin * n_bricks + g];
+        out[(size_t)v * n_bricks + g] = acc;
+    }
+}
 
 // pass x: blockIdx.y = 0 scans towards +x, 1 towards -x; out[v][g]
 __global__ void __launch_bounds__(256) dist_pass_x_kernel(const __grid_constant__ TraceParams P, uint8_t* __restrict__ out, size_t n_bricks) {
@@ -176,8 +205,8 @@ __global__ void __launch_bounds__(256) dist_pass_z_kernel(const __grid_constant_
 
 // pass y: blockIdx.y = octant = xneg | yneg << 1 | zneg << 2; writes the padded layout the march indexes:
 // dist[octant * plane + (x+1) + ((z+1) << log_px) + ((y+1) << (log_px+log_pz))]
-__global__ void __launch_bounds__(256) dist_pass_y_kernel(const __grid_constant__ TraceParams P, const uint8_t* __restrict__ in, uint8_t* __restrict__ dist,
-                                                          size_t n_bricks) {
+__global__ void __launch_bounds__(256) dist_pass_y_kernel(const __grid_constant__ TraceParams P, const uint8_t* __restrict__ in,
+                                                          const uint8_t* __restrict__ any_oct, uint8_t* __restrict__ dist, size_t n_bricks) {
     const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n_bricks) return;
     const int oct = (int)blockIdx.y, xneg = oct & 1, yneg = (oct >> 1) & 1, zneg = oct >> 2;
@@ -185,10 +214,12 @@ __global__ void __launch_bounds__(256) dist_pass_y_kernel(const __grid_constant_
     const uint32_t z = (uint32_t)((g / P.grid.dim_x) % P.grid.dim_z);
     const uint32_t y = (uint32_t)(g / ((size_t)P.grid.dim_x * P.grid.dim_z));
     const int d = dist_scan(in + (size_t)(xneg | (zneg << 1)) * n_bricks, g, (int)y, (int)P.grid.dim_y, (size_t)P.grid.dim_x * P.grid.dim_z, yneg);
-    dist[(size_t)oct * P.dist_plane + (size_t)(x + 1) + ((size_t)(z + 1) << P.dist_log_px) + ((size_t)(y + 1) << (P.dist_log_px + P.dist_log_pz))] = (uint8_t)d;
+    const uint32_t free_flag = any_oct[(size_t)oct * n_bricks + g] ? 0u : kDistFree;
+    dist[(size_t)oct * P.dist_plane + (size_t)(x + 1) + ((size_t)(z + 1) << P.dist_log_px) + ((size_t)(y + 1) << (P.dist_log_px + P.dist_log_pz))] =
+        (uint8_t)((uint32_t)d | free_flag);
 }
 
-// tmp: 6 * n_bricks bytes of scratch.  The border bytes of `dist` (255) are written once when it is allocated.
+// tmp: 20 * n_bricks bytes of scratch.  The border bytes of `dist` (255) are written once when it is allocated.
 cudaError_t launch_build_accel(const TraceParams& P, unsigned long long* occ_dense, uint8_t* dist, uint8_t* tmp, size_t n_bricks, cudaStream_t stream,
                                LaunchInfo* info) {
     const unsigned blocks = (unsigned)((n_bricks + 255) / 256);
@@ -196,12 +227,19 @@ cudaError_t launch_build_accel(const TraceParams& P, unsigned long long* occ_den
         build_occ_dense_kernel<<<blocks, 256, 0, stream>>>(P, occ_dense, n_bricks);
         if (info) info->launches++;
     }
-    uint8_t* tmp_x = tmp;                 // [2][n]
-    uint8_t* tmp_z = tmp + 2 * n_bricks;  // [4][n]
+    uint8_t* tmp_x = tmp;                  // [2][n]  distance pass x
+    uint8_t* tmp_z = tmp + 2 * n_bricks;   // [4][n]  distance pass z
+    uint8_t* any_x = tmp + 6 * n_bricks;   // [2][n]  OR-scan x
+    uint8_t* any_z = tmp + 8 * n_bricks;   // [4][n]  OR-scan z
+    uint8_t* any_y = tmp + 12 * n_bricks;  // [8][n]  OR-scan y = "a loaded brick exists in the octant"
+    const size_t dx = P.grid.dim_x, dy = P.grid.dim_y, dz = P.grid.dim_z;
+    any_scan_kernel<<<dim3((unsigned)((dz * dy + 127) / 128), 2), 128, 0, stream>>>(P, nullptr, any_x, n_bricks, 0);
+    any_scan_kernel<<<dim3((unsigned)((dx * dy + 127) / 128), 4), 128, 0, stream>>>(P, any_x, any_z, n_bricks, 1);
+    any_scan_kernel<<<dim3((unsigned)((dx * dz + 127) / 128), 8), 128, 0, stream>>>(P, any_z, any_y, n_bricks, 2);
     dist_pass_x_kernel<<<dim3(blocks, 2), 256, 0, stream>>>(P, tmp_x, n_bricks);
     dist_pass_z_kernel<<<dim3(blocks, 4), 256, 0, stream>>>(P, tmp_x, tmp_z, n_bricks);
-    dist_pass_y_kernel<<<dim3(blocks, 8), 256, 0, stream>>>(P, tmp_z, dist, n_bricks);
-    if (info) info->launches += 3;
+    dist_pass_y_kernel<<<dim3(blocks, 8), 256, 0, stream>>>(P, tmp_z, any_y, dist, n_bricks);
+    if (info) info->launches += 6;
     return cudaGetLastError();
 }
 

@@ -10,6 +10,9 @@ enum TraceKernel : int {
     KERNEL_TUNED = 1,  // warp-cooperative traversal over the derived distance grid (vrt_trav_warp.cuh)
 };
 
+constexpr uint32_t kDistBorder = 255u;  // dist byte of the one-cell border around the grid
+constexpr uint32_t kDistFree = 0x80u;   // dist bit: no loaded brick anywhere in this cell's octant (low 7 bits: distance, <= 126)
+
 struct LaunchInfo {
     uint32_t launches;                 // kernels enqueued
     unsigned long long counter_advance;  // how far the launch moves *tile_counter (tuned kernel)
@@ -18,7 +21,7 @@ struct LaunchInfo {
 // Enqueue the kernels that trace rows [P.row_begin, P.row_end) into P.fb.
 cudaError_t launch_trace(const TraceParams& P, TraceKernel which, bool aov, cudaStream_t stream, LaunchInfo* info);
 
-// Rebuild the derived structures (occ_dense, dist) from the reference-format buffers.  tmp: 6 * n_bricks bytes.
+// Rebuild the derived structures (occ_dense, dist) from the reference-format buffers.  tmp: 20 * n_bricks bytes.
 cudaError_t launch_build_accel(const TraceParams& P, unsigned long long* occ_dense, uint8_t* dist, uint8_t* tmp, size_t n_bricks, cudaStream_t stream,
                                LaunchInfo* info);
 cudaError_t launch_trace_tuned(const TraceParams& P, bool aov, cudaStream_t stream, LaunchInfo* info);

@@ -106,7 +106,7 @@ struct vrt_ctx {
     // derived acceleration structures (vrt_trav_warp.cuh)
     unsigned long long* d_occ_dense = nullptr;
     uint8_t* d_dist = nullptr;
-    uint8_t* d_dist_tmp = nullptr;  // 6 x n_bricks bytes of scratch for the separable distance transform
+    uint8_t* d_dist_tmp = nullptr;  // 20 x n_bricks bytes of scratch for the separable distance transform + octant OR-scans
     size_t dist_plane = 0;          // bytes per octant
     uint32_t dist_log_px = 0, dist_log_pz = 0;
     uint32_t accel_dim[3] = {0, 0, 0};
@@ -220,7 +220,7 @@ int ensure_accel(vrt_ctx* ctx) {
     if (8 * ctx->dist_plane > 0x7fffffffull)
         return fail(ctx, VRT_E_INVALID, "grid %ux%ux%u is too large for the 31-bit cell index of the march (8 padded distance planes)", dx, dy, dz);
     VRT_CUDA(ctx, cudaMalloc(&ctx->d_dist, 8 * ctx->dist_plane));
-    VRT_CUDA(ctx, cudaMalloc(&ctx->d_dist_tmp, 6 * (size_t)dx * dy * dz));
+    VRT_CUDA(ctx, cudaMalloc(&ctx->d_dist_tmp, 20 * (size_t)dx * dy * dz));
     VRT_CUDA(ctx, cudaMemsetAsync(ctx->d_dist, 255, 8 * ctx->dist_plane, ctx->stream));  // the border; interiors are rewritten by every build
     ctx->accel_dim[0] = dx, ctx->accel_dim[1] = dy, ctx->accel_dim[2] = dz;
     ctx->accel_dirty = true;

@@ -33,7 +33,6 @@
 namespace vrt {
 
 constexpr unsigned kFullMask = 0xffffffffu;
-constexpr uint32_t kDistBorder = 255u;
 
 // hit.normal as (axis, sign): every normal this path produces has one non-zero component (:350-370, :530-531)
 struct AxisNormal {
@@ -212,10 +211,14 @@ VRT_DI bool grid_hit_warp(const TraceParams& P, const Ray& r, bool active, bool 
             uint32_t d = kIdle;
             if (marching && !parked) {
                 d = __ldg(dist + idx);
-                if (d == kDistBorder) {
-                    marching = false;  // left the grid (:313-315)
+                // left the grid (:313-315), or — exact shortcut — no loaded brick exists anywhere in the octant this
+                // DDA can reach: the shader's loop would only step through empty cells until it leaves the grid.
+                // (COUNT keeps marching so that the step counters equal the shader's.)
+                if (d == kDistBorder || (!COUNT && (d & kDistFree))) {
+                    marching = false;
                     d = kIdle;
                 } else {
+                    d &= 0x7fu;
                     if (COUNT) {  // an in-grid cell = one iteration of the shader's loop; emulate its one-word status cache (:321-326)
                         ti.grid_steps++;
                         const uint32_t gi = cell_grid_index(P, idx - obase, log_px, log_pzx);
