@@ -33,6 +33,7 @@ def parse_args():
     ap.add_argument("--workload", default="C3", choices=["C1", "C2", "C3", "C4", "C5"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--exchange", default="allgather", choices=["allgather", "peer"])
+    ap.add_argument("--partition", default="interleave", choices=["interleave", "slab"], help="N > 1: 4-row strips round-robin, or one row slab per rank")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--baseline-kernel", action="store_true", help="time the reference-shape kernel instead of the tuned one")
     return ap.parse_args()
@@ -192,9 +193,11 @@ def main():
 
     wl = scenes.WORKLOADS[args.workload]
     W, H = wl.width, wl.height
-    if H % world != 0:
+    interleave = world > 1 and args.partition == "interleave" and not args.baseline_kernel
+    if not interleave and H % world != 0:
         raise SystemExit(f"image height {H} is not divisible by {world} ranks")
-    rows = (rank * (H // world), (rank + 1) * (H // world))
+    rows = (rank * (H // world), (rank + 1) * (H // world)) if (world > 1 and not interleave) else (0, 0)
+    part = (rank, world) if interleave else None
     n_pixels = W * H
 
     grid = scenes.build_grid(wl.n_voxels, wl.brick_dim, brick_alloc=alloc_for(wl))
@@ -205,7 +208,7 @@ def main():
 
     flags = ffi.VRT_FLAG_BASELINE if args.baseline_kernel else 0
     ctx = ffi.Context(W, H, len(grid.brick_indices), brick_dim=wl.brick_dim, n_brick_alloc=grid.brick_alloc, device=local_rank, flags=flags,
-                      rows=rows if world > 1 else (0, 0))
+                      rows=rows, part=part)
     stream = torch.cuda.Stream(dev)  # a non-default stream: handle 0 would mean "restore the ctx's own stream"
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)  # torch.cuda.Event only sees torch's current stream
@@ -225,15 +228,17 @@ def main():
             ctx.comm_open_peers(rank, world, b"".join(bytes(h.cpu().numpy().tobytes()) for h in allh))
             ctx.comm_set_exchange(ffi.VRT_EXCHANGE_PEER_STORE)
 
-    # ray / request-byte counters of this rank's rows from the reference-shape kernel (identical to the oracle's)
+    # ray / request-byte counters of this rank's rows (identical to the oracle's, tests/test_golden.py): the reference-shape
+    # kernel for slabs, the tuned kernel's counting variant for interleaved strips
     cctx = ffi.Context(W, H, len(grid.brick_indices), brick_dim=wl.brick_dim, n_brick_alloc=grid.brick_alloc, device=local_rank,
-                       flags=ffi.VRT_FLAG_AOV | ffi.VRT_FLAG_BASELINE, rows=rows if world > 1 else (0, 0))
+                       flags=ffi.VRT_FLAG_AOV | (0 if interleave else ffi.VRT_FLAG_BASELINE), rows=rows, part=part)
     cctx.upload_grid(grid, mats)
     cctx.trace(cam, sun)
     counters = cctx.counters()
     cctx.close()
     my_rays = counters["rays"]
-    my_alg_bytes = 4 * (rows[1] - rows[0]) * W + 4 * counters["status_fetches"] + (4 + brick_bytes) * counters["bricks_entered"] + 25 * counters["hits"]
+    my_rows = (sum(min(4, H - t * 4) for t in range(rank, (H + 3) // 4, world)) if interleave else (rows[1] - rows[0] if world > 1 else H))
+    my_alg_bytes = 4 * my_rows * W + 4 * counters["status_fetches"] + (4 + brick_bytes) * counters["bricks_entered"] + 25 * counters["hits"]
 
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
 
@@ -328,7 +333,7 @@ def main():
             "config": {
                 "workload": f"{wl.name}: {wl.description}", "pose": "pose0 origin (0,-10,28) pitch 25deg", "rays_per_step": int(rays),
                 "grid_bricks": len(grid.brick_indices), "active_bricks": grid.active_bricks, "l2": f"flushed between steps ({L2_FLUSH_BYTES >> 20} MiB fill)",
-                "kernel": "baseline" if args.baseline_kernel else "tuned", "partition": f"{world} row slabs" if world > 1 else "whole frame",
+                "kernel": "baseline" if args.baseline_kernel else "tuned", "partition": (f"4-row strips round-robin over {world} ranks" if interleave else f"{world} row slabs") if world > 1 else "whole frame",
                 "exchange": args.exchange if world > 1 else "none",
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,

@@ -137,6 +137,8 @@ typedef struct vrt_ctx vrt_ctx;
 
 #define VRT_FLAG_AOV 1u        /* allocate + fill the AOV buffer and counters on every trace (debug)   */
 #define VRT_FLAG_BASELINE 2u   /* use the one-thread-per-pixel transliteration kernel, not the tuned one */
+#define VRT_FLAG_INTERLEAVE 4u /* partition by interleaved strips of 4 image rows (part_rank / part_world) instead of a row slab:
+                                  strip t belongs to rank t % part_world.  Balances sky against terrain across GPUs. */
 
 /* What ComputePipeline.init receives as ImageInfo + StateConfigs + specialization constants
  * (ComputePipeline.zig:67-73, Pipeline.zig:272-316), flattened. */
@@ -152,6 +154,8 @@ typedef struct vrt_config {
     uint32_t flags;              /* VRT_FLAG_*                                                           */
     uint32_t row_begin, row_end; /* image rows [begin,end) this context traces; 0,0 = all rows.
                                     Multi-GPU runs give each rank one slab of the same full image.       */
+    uint32_t part_rank, part_world; /* VRT_FLAG_INTERLEAVE: this context traces the 4-row strips t with
+                                    t % part_world == part_rank (row_begin/row_end must be 0).            */
 } vrt_config;
 
 int vrt_init(vrt_ctx** out_ctx, const vrt_config* cfg);
@@ -224,9 +228,11 @@ int vrt_framebuffer_device_ptr(vrt_ctx* ctx, void** out_device_ptr);
 /* ---------------------------------------------------------------------------------------------------
  * Multi-GPU: one process (and one ctx) per GPU, each tracing a row slab of the same image; the slabs are
  * exchanged right after the trace kernel on the same stream so that every rank ends with the full frame.
- *   exchange mode 0: one in-place ncclAllGather over NVLink (needs equal slabs)
+ *   exchange mode 0: one in-place ncclAllGather over NVLink.  Row slabs must be equal; interleaved strips are traced
+ *                    into a rank-major gather buffer and re-ordered into the frame by a copy kernel after the gather.
  *   exchange mode 1: fused — the trace kernel itself stores its pixels into every peer's framebuffer
- *                    through NVLink peer mappings (vrt_comm_open_peers), no separate collective.
+ *                    through NVLink peer mappings (vrt_comm_open_peers); the only collective left is a 4-byte
+ *                    all-reduce that orders frame k+1's stores after every rank has consumed frame k.
  * ------------------------------------------------------------------------------------------------- */
 #define VRT_NCCL_ID_BYTES 128
 #define VRT_IPC_HANDLE_BYTES 64

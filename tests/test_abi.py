@@ -45,7 +45,7 @@ def test_material_layout():
 def test_aov_and_config_layout():
     assert C.sizeof(ffi.Aov) == 64 and ffi.AOV_DTYPE.itemsize == 64
     assert C.sizeof(ffi.Counters) == 64
-    assert C.sizeof(ffi.Config) == 56
+    assert C.sizeof(ffi.Config) == 64
 
 
 def _declared(header):
@@ -68,13 +68,13 @@ def test_library_exports_every_declared_symbol(header, libname, table):
 def test_init_rejects_bad_config_without_touching_the_gpu():
     l = ffi.lib()
     h = C.c_void_p()
-    cfg = ffi.Config(C.sizeof(ffi.Config), ffi.VRT_ABI_VERSION, 0, 0, 4, 256, 64, 64, 0, 0, 0, 0)
+    cfg = ffi.Config(C.sizeof(ffi.Config), ffi.VRT_ABI_VERSION, 0, 0, 4, 256, 64, 64, 0, 0, 0, 0, 0, 0)
     assert l.vrt_init(C.byref(h), C.byref(cfg)) == -1  # VRT_E_INVALID: zero-sized image
     assert b"image size" in l.vrt_last_error(None)
-    cfg = ffi.Config(C.sizeof(ffi.Config) - 4, ffi.VRT_ABI_VERSION, 16, 16, 4, 256, 64, 64, 0, 0, 0, 0)
+    cfg = ffi.Config(C.sizeof(ffi.Config) - 4, ffi.VRT_ABI_VERSION, 16, 16, 4, 256, 64, 64, 0, 0, 0, 0, 0, 0)
     assert l.vrt_init(C.byref(h), C.byref(cfg)) == -1
     assert b"ABI mismatch" in l.vrt_last_error(None)
-    cfg = ffi.Config(C.sizeof(ffi.Config), ffi.VRT_ABI_VERSION, 16, 16, 5, 256, 64, 64, 0, 0, 0, 0)
+    cfg = ffi.Config(C.sizeof(ffi.Config), ffi.VRT_ABI_VERSION, 16, 16, 5, 256, 64, 64, 0, 0, 0, 0, 0, 0)
     assert l.vrt_init(C.byref(h), C.byref(cfg)) == -1
     assert b"brick_dim" in l.vrt_last_error(None)
     assert l.vrt_init(None, C.byref(cfg)) == -1

@@ -154,6 +154,37 @@ def test_row_slabs_tile_the_frame(materials):
         assert np.array_equal(out, whole)
 
 
+def test_interleaved_strips_tile_the_frame(materials):
+    """VRT_FLAG_INTERLEAVE: rank r traces the 4-row strips t with t % world == r (load-balanced multi-GPU partition).
+    The ranks' frames are disjoint, assemble the single-GPU frame, and their ray counters add up — also when the
+    strip count does not divide evenly (70 rows = 17.5 strips)."""
+    grid = scenes.build_grid(64)
+    cam = scenes.camera(128, 70, **POSE0)
+    sun = scenes.sun(True)
+    whole, _, whole_cnt = trace(grid, materials, cam, sun, ffi.VRT_FLAG_AOV)
+    for world in (1, 2, 3, 8):
+        out = np.zeros_like(whole)
+        rays = 0
+        for r in range(world):
+            ctx = ffi.Context(128, 70, len(grid.brick_indices), flags=ffi.VRT_FLAG_AOV, part=(r, world))
+            ctx.upload_grid(grid, materials)
+            ctx.trace(cam, sun)
+            part = ctx.read_framebuffer()
+            rays += ctx.counters()["rays"]
+            ctx.close()
+            mine = np.zeros(70, dtype=bool)
+            for t in range(r, 18, world):
+                mine[t * 4:(t + 1) * 4] = True
+            assert not part[~mine].any()
+            out[mine] = part[mine]
+        assert np.array_equal(out, whole)
+        assert rays == whole_cnt["rays"]
+    with pytest.raises(ffi.VrtError):
+        ffi.Context(128, 70, len(grid.brick_indices), part=(2, 2))
+    with pytest.raises(ffi.VrtError):
+        ffi.Context(128, 70, len(grid.brick_indices), flags=ffi.VRT_FLAG_BASELINE, part=(0, 2))
+
+
 def test_partial_uploads_and_edit(materials):
     """Edits shipped as dirty ranges (VoxelRT.updateGridDelta, VoxelRT.zig:107-172) through the Renderer facade."""
     grid = scenes.build_grid(64)

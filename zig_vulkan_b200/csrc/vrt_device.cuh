@@ -250,6 +250,9 @@ struct TraceParams {
     uint32_t brick_bytes;     // spec const 3
     float brick_voxel_scale;  // spec const 5 (host-computed 1.0f/brick_dim, Pipeline.zig:313)
     uint32_t row_begin, row_end;
+    // interleaved partition (il_world > 0): this launch traces the 4-row strips t with t % il_world == il_rank.
+    // il_gather: store strip k of this rank at rows (il_rank * il_strips_max + k) * 4 of `fb` (rank-major all-gather layout)
+    uint32_t il_world, il_rank, il_gather, il_strips_max;
     uint32_t* fb;                 // RGBA8 image, binding 0 (row-major, width*height words)
     vrt_aov* aov;                 // nullable
     unsigned long long* counters; // nullable, 8 x u64 in vrt_counters order

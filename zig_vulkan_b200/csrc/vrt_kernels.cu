@@ -52,9 +52,11 @@ __global__ void __launch_bounds__(kTunedThreads, MINB) trace_warp_kernel(const _
         if (t >= (unsigned long long)tiles_total) break;
         const uint32_t tile = (uint32_t)t;
         const uint32_t px = (tile % tiles_x) * kTileW + lx;
-        const uint32_t py = P.row_begin + (tile / tiles_x) * kTileH + ly;
+        const uint32_t strip = tile / tiles_x;  // this launch's k-th strip of kTileH rows
+        const uint32_t py = P.il_world ? (strip * P.il_world + P.il_rank) * kTileH + ly : P.row_begin + strip * kTileH + ly;
         const bool inside = px < width && py < P.row_end;  // :156-159
         const uint32_t texel = shade_pixel_warp<BD, AOV>(P, px, py, inside, pc);
+        const uint32_t out_row = P.il_gather ? (P.il_rank * P.il_strips_max + strip) * kTileH + ly : py;
 
         // 128-bit framebuffer stores: lanes with lx in {0,4} gather the 4 texels to their right
         const uint32_t t1 = __shfl_down_sync(kFullMask, texel, 1);
@@ -64,12 +66,12 @@ __global__ void __launch_bounds__(kTunedThreads, MINB) trace_warp_kernel(const _
         if (vec) {
             if ((lx & 3u) == 0u && py < P.row_end) {
                 const uint4 v = make_uint4(texel, t1, t2, t3);
-                *reinterpret_cast<uint4*>(P.fb + (size_t)py * width + px) = v;
-                for (uint32_t p = 0; p < P.n_peers; p++) *reinterpret_cast<uint4*>(P.peer_fb[p] + (size_t)py * width + px) = v;
+                *reinterpret_cast<uint4*>(P.fb + (size_t)out_row * width + px) = v;
+                for (uint32_t p = 0; p < P.n_peers; p++) *reinterpret_cast<uint4*>(P.peer_fb[p] + (size_t)out_row * width + px) = v;
             }
         } else if (inside) {
-            P.fb[(size_t)py * width + px] = texel;
-            for (uint32_t p = 0; p < P.n_peers; p++) P.peer_fb[p][(size_t)py * width + px] = texel;
+            P.fb[(size_t)out_row * width + px] = texel;
+            for (uint32_t p = 0; p < P.n_peers; p++) P.peer_fb[p][(size_t)out_row * width + px] = texel;
         }
     }
     if (AOV) flush_counters(P, pc);
@@ -83,8 +85,10 @@ cudaError_t launch_warp_kernel(const TraceParams& P, int num_sms, cudaStream_t s
     if (blocks_per_sm < 1) return cudaErrorLaunchOutOfResources;
     const uint32_t rows = P.row_end - P.row_begin;
     const uint32_t tiles_x = (P.cam.image_width + kTileW - 1) / kTileW;
-    const uint32_t tiles_y = (rows + kTileH - 1) / kTileH;
+    uint32_t tiles_y = (rows + kTileH - 1) / kTileH;
+    if (P.il_world) tiles_y = (tiles_y + P.il_world - 1 - P.il_rank) / P.il_world;  // strips t = k * world + rank < tiles_y
     const uint32_t tiles_total = tiles_x * tiles_y;
+    if (tiles_total == 0) return cudaSuccess;
     const uint32_t warps_per_block = kTunedThreads / 32;
     uint32_t grid = (uint32_t)(num_sms * blocks_per_sm);  // one resident wave: a multiple of the SM count
     const uint32_t needed = (tiles_total + warps_per_block - 1) / warps_per_block;
@@ -240,6 +244,29 @@ cudaError_t launch_build_accel(const TraceParams& P, unsigned long long* occ_den
     dist_pass_z_kernel<<<dim3(blocks, 4), 256, 0, stream>>>(P, tmp_x, tmp_z, n_bricks);
     dist_pass_y_kernel<<<dim3(blocks, 8), 256, 0, stream>>>(P, tmp_z, any_y, dist, n_bricks);
     if (info) info->launches += 6;
+    return cudaGetLastError();
+}
+
+// Rank-major gather layout -> row-major frame after the all-gather of an interleaved partition: strip k of rank r holds
+// image rows (k * world + r) * 4 ... + 3.  One thread per 16 bytes (4 texels).
+__global__ void __launch_bounds__(256) deinterleave_kernel(const uint4* __restrict__ gathered, uint4* __restrict__ frame, uint32_t width4, uint32_t height,
+                                                           uint32_t world, uint32_t strips_max) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)world * strips_max * kTileH * width4;
+    if (i >= total) return;
+    const uint32_t x = (uint32_t)(i % width4);
+    const uint32_t grow = (uint32_t)(i / width4);  // row in the gather layout
+    const uint32_t r = grow / (strips_max * kTileH), k = (grow / kTileH) % strips_max, ly = grow % kTileH;
+    const uint32_t py = (k * world + r) * kTileH + ly;
+    if (py < height) frame[(size_t)py * width4 + x] = gathered[i];
+}
+
+cudaError_t launch_deinterleave(const uint32_t* gathered, uint32_t* frame, uint32_t width, uint32_t height, uint32_t world, uint32_t strips_max,
+                                cudaStream_t stream, LaunchInfo* info) {
+    const size_t total = (size_t)world * strips_max * kTileH * (width / 4);
+    deinterleave_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const uint4*>(gathered), reinterpret_cast<uint4*>(frame), width / 4,
+                                                                            height, world, strips_max);
+    if (info) info->launches++;
     return cudaGetLastError();
 }
 

@@ -38,6 +38,7 @@ struct NcclApi {
     ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
@@ -56,9 +57,10 @@ bool load_nccl(char* err, size_t err_len) {
     g_nccl.GetUniqueId = reinterpret_cast<decltype(g_nccl.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
     g_nccl.CommInitRank = reinterpret_cast<decltype(g_nccl.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
     g_nccl.AllGather = reinterpret_cast<decltype(g_nccl.AllGather)>(dlsym(h, "ncclAllGather"));
+    g_nccl.AllReduce = reinterpret_cast<decltype(g_nccl.AllReduce)>(dlsym(h, "ncclAllReduce"));
     g_nccl.CommDestroy = reinterpret_cast<decltype(g_nccl.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
     g_nccl.GetErrorString = reinterpret_cast<decltype(g_nccl.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
-    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllGather || !g_nccl.CommDestroy || !g_nccl.GetErrorString) {
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllGather || !g_nccl.AllReduce || !g_nccl.CommDestroy || !g_nccl.GetErrorString) {
         snprintf(err, err_len, "libnccl is missing a required symbol");
         dlclose(h);
         return false;
@@ -72,6 +74,10 @@ bool load_nccl(char* err, size_t err_len) {
 struct vrt_ctx {
     vrt_config cfg;
     uint32_t row_begin, row_end;
+    bool interleave = false;          // VRT_FLAG_INTERLEAVE: strips t % part_world == part_rank
+    uint32_t part_rank = 0, part_world = 1, strips_max = 0;
+    uint32_t* d_gather = nullptr;     // rank-major all-gather buffer of an interleaved partition
+    int* d_barrier = nullptr;         // 4 bytes all-reduced after a peer-store frame
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     bool timing_valid = false;
@@ -182,6 +188,9 @@ void fill_params(const vrt_ctx* c, const vrt_camera* cam, const vrt_sun* sun, Tr
     P.brick_bytes = c->cfg.brick_dim * c->cfg.brick_dim * c->cfg.brick_dim / 8;
     P.brick_voxel_scale = 1.0f / (float)c->cfg.brick_dim;  // Pipeline.zig:313
     P.row_begin = c->row_begin, P.row_end = c->row_end;
+    P.il_world = c->interleave ? c->part_world : 0u;
+    P.il_rank = c->part_rank;
+    P.il_gather = 0u, P.il_strips_max = c->strips_max;
     P.fb = c->d_fb;
     P.aov = c->d_aov;
     P.counters = c->d_counters;
@@ -248,6 +257,12 @@ int vrt_init(vrt_ctx** out_ctx, const vrt_config* cfg) {
         return fail(nullptr, VRT_E_INVALID, "vrt_init: n_bricks out of range");
     if (cfg->row_begin > cfg->row_end || cfg->row_end > cfg->height)
         return fail(nullptr, VRT_E_INVALID, "vrt_init: bad row slab [%u, %u) for height %u", cfg->row_begin, cfg->row_end, cfg->height);
+    if (cfg->flags & VRT_FLAG_INTERLEAVE) {
+        if (cfg->row_begin != 0 || cfg->row_end != 0) return fail(nullptr, VRT_E_INVALID, "vrt_init: VRT_FLAG_INTERLEAVE excludes a row slab");
+        if (cfg->part_world < 1 || cfg->part_world > 8 || cfg->part_rank >= cfg->part_world)
+            return fail(nullptr, VRT_E_INVALID, "vrt_init: bad interleaved partition %u of %u", cfg->part_rank, cfg->part_world);
+        if (cfg->flags & VRT_FLAG_BASELINE) return fail(nullptr, VRT_E_INVALID, "vrt_init: the baseline kernel only supports row slabs");
+    }
 
     int n_dev = 0;
     cudaError_t e = cudaGetDeviceCount(&n_dev);
@@ -262,6 +277,12 @@ int vrt_init(vrt_ctx** out_ctx, const vrt_config* cfg) {
     if (ctx->cfg.n_brick_alloc == 0) ctx->cfg.n_brick_alloc = cfg->n_bricks;  // Grid.zig:51
     ctx->row_begin = cfg->row_begin;
     ctx->row_end = (cfg->row_begin == 0 && cfg->row_end == 0) ? cfg->height : cfg->row_end;
+    if (cfg->flags & VRT_FLAG_INTERLEAVE) {
+        ctx->interleave = true;
+        ctx->part_rank = cfg->part_rank, ctx->part_world = cfg->part_world;
+        const uint32_t strips = (cfg->height + kStripRows - 1) / kStripRows;
+        ctx->strips_max = (strips + cfg->part_world - 1) / cfg->part_world;
+    }
 
     const uint32_t bits = cfg->brick_dim * cfg->brick_dim * cfg->brick_dim;
     ctx->n_materials = ctx->cfg.material_capacity;
@@ -337,7 +358,7 @@ void vrt_deinit(vrt_ctx* ctx) {
     cudaFree(ctx->d_materials), cudaFree(ctx->d_statuses), cudaFree(ctx->d_brick_indices), cudaFree(ctx->d_occupancy);
     cudaFree(ctx->d_start_indices), cudaFree(ctx->d_material_indices), cudaFree(ctx->d_fb_own), cudaFree(ctx->d_aov);
     cudaFree(ctx->d_counters), cudaFree(ctx->d_occ_dense), cudaFree(ctx->d_dist), cudaFree(ctx->d_dist_tmp);
-    cudaFree(ctx->d_tile_counter);
+    cudaFree(ctx->d_tile_counter), cudaFree(ctx->d_gather), cudaFree(ctx->d_barrier);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     cudaFree(ctx->d_fb_ring1);
     for (int i = 0; i < 2; i++) {
@@ -420,16 +441,35 @@ int vrt_trace(vrt_ctx* ctx, const vrt_camera* camera, const vrt_sun* sun) {
         ctx->accel_dirty = false;
     }
     if (aov) VRT_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
+    const bool gather = ctx->world > 1 && ctx->exchange_mode == VRT_EXCHANGE_ALLGATHER;
+    if (ctx->world > 1 && !ctx->comm) return fail(ctx, VRT_E_STATE, "vrt_trace: world > 1 but vrt_comm_init has not been called");
+    if (gather && ctx->interleave) {  // trace straight into this rank's slice of the rank-major gather buffer
+        P.fb = ctx->d_gather;
+        P.il_gather = 1u;
+        P.vec_store_ok = (camera->image_width % 4 == 0) ? 1u : 0u;
+    }
     VRT_CUDA(ctx, launch_trace(P, which, aov, ctx->stream, &info));
     ctx->tile_base += info.counter_advance;
 
-    if (ctx->world > 1 && ctx->exchange_mode == VRT_EXCHANGE_ALLGATHER) {
-        if (!ctx->comm) return fail(ctx, VRT_E_STATE, "vrt_trace: world > 1 but vrt_comm_init has not been called");
-        const size_t slab_bytes = (size_t)(ctx->row_end - ctx->row_begin) * ctx->cfg.width * 4;
-        const uint8_t* send = reinterpret_cast<const uint8_t*>(ctx->d_fb) + (size_t)ctx->row_begin * ctx->cfg.width * 4;
-        // in place: the kernel already wrote this rank's slab at its final offset in the full frame
-        const ncclResult_t r = g_nccl.AllGather(send, ctx->d_fb, slab_bytes, ncclUint8, ctx->comm, ctx->stream);
-        if (r != ncclSuccess) return fail(ctx, VRT_E_NCCL, "ncclAllGather failed: %s", g_nccl.GetErrorString(r));
+    if (gather) {
+        // in place: the kernel already wrote this rank's pixels at their offset in the gathered buffer
+        if (ctx->interleave) {
+            const size_t slab_bytes = (size_t)ctx->strips_max * kStripRows * ctx->cfg.width * 4;
+            const uint8_t* send = reinterpret_cast<const uint8_t*>(ctx->d_gather) + (size_t)ctx->rank * slab_bytes;
+            const ncclResult_t r = g_nccl.AllGather(send, ctx->d_gather, slab_bytes, ncclUint8, ctx->comm, ctx->stream);
+            if (r != ncclSuccess) return fail(ctx, VRT_E_NCCL, "ncclAllGather failed: %s", g_nccl.GetErrorString(r));
+            VRT_CUDA(ctx, launch_deinterleave(ctx->d_gather, ctx->d_fb, ctx->cfg.width, ctx->cfg.height, (uint32_t)ctx->world, ctx->strips_max, ctx->stream, &info));
+        } else {
+            const size_t slab_bytes = (size_t)(ctx->row_end - ctx->row_begin) * ctx->cfg.width * 4;
+            const uint8_t* send = reinterpret_cast<const uint8_t*>(ctx->d_fb) + (size_t)ctx->row_begin * ctx->cfg.width * 4;
+            const ncclResult_t r = g_nccl.AllGather(send, ctx->d_fb, slab_bytes, ncclUint8, ctx->comm, ctx->stream);
+            if (r != ncclSuccess) return fail(ctx, VRT_E_NCCL, "ncclAllGather failed: %s", g_nccl.GetErrorString(r));
+        }
+    } else if (ctx->world > 1) {
+        // peer-store: the pixels are already in every rank's framebuffer; a 4-byte all-reduce makes "every rank has finished
+        // frame k" visible in stream order, so frame k+1's remote stores cannot overtake a peer still reading frame k
+        const ncclResult_t r = g_nccl.AllReduce(ctx->d_barrier, ctx->d_barrier, 1, ncclInt32, ncclSum, ctx->comm, ctx->stream);
+        if (r != ncclSuccess) return fail(ctx, VRT_E_NCCL, "ncclAllReduce failed: %s", g_nccl.GetErrorString(r));
     }
     VRT_CUDA(ctx, cudaEventRecord(ctx->ev_end, ctx->stream));
     ctx->timing_valid = true;
@@ -474,8 +514,9 @@ int vrt_trace_to_host_async(vrt_ctx* ctx, const vrt_camera* camera, const vrt_su
     VRT_CUDA(ctx, cudaEventRecord(ctx->ev_traced[slot], ctx->stream));
     VRT_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_traced[slot], 0));
     const size_t off = (size_t)ctx->row_begin * ctx->cfg.width * 4;
-    const size_t n = (ctx->world > 1) ? ctx->fb_bytes : (size_t)(ctx->row_end - ctx->row_begin) * ctx->cfg.width * 4;
-    const size_t from = (ctx->world > 1) ? 0 : off;
+    const bool whole = ctx->world > 1 || ctx->interleave;
+    const size_t n = whole ? ctx->fb_bytes : (size_t)(ctx->row_end - ctx->row_begin) * ctx->cfg.width * 4;
+    const size_t from = whole ? 0 : off;
     VRT_CUDA(ctx, cudaMemcpyAsync(rgba8_host + from, reinterpret_cast<const uint8_t*>(fb) + from, n, cudaMemcpyDeviceToHost, ctx->copy_stream));
     VRT_CUDA(ctx, cudaEventRecord(ctx->ev_copied[slot], ctx->copy_stream));
     ctx->slot_used[slot] = true;
@@ -498,8 +539,9 @@ int vrt_trace_to_host(vrt_ctx* ctx, const vrt_camera* camera, const vrt_sun* sun
     const int rc = vrt_trace(ctx, camera, sun);
     if (rc != VRT_OK) return rc;
     const size_t off = (size_t)ctx->row_begin * ctx->cfg.width * 4;
-    const size_t n = (ctx->world > 1) ? ctx->fb_bytes : (size_t)(ctx->row_end - ctx->row_begin) * ctx->cfg.width * 4;
-    const size_t from = (ctx->world > 1) ? 0 : off;
+    const bool whole = ctx->world > 1 || ctx->interleave;
+    const size_t n = whole ? ctx->fb_bytes : (size_t)(ctx->row_end - ctx->row_begin) * ctx->cfg.width * 4;
+    const size_t from = whole ? 0 : off;
     VRT_CUDA(ctx, cudaMemcpyAsync(rgba8_host + from, reinterpret_cast<const uint8_t*>(ctx->d_fb) + from, n, cudaMemcpyDeviceToHost, ctx->stream));
     VRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return VRT_OK;
@@ -583,9 +625,15 @@ int vrt_comm_init(vrt_ctx* ctx, int rank, int world, const uint8_t id[VRT_NCCL_I
     if (!ctx) return VRT_E_INVALID;
     if (world < 1 || world > 8 || rank < 0 || rank >= world || !id) return fail(ctx, VRT_E_INVALID, "vrt_comm_init: bad rank/world %d/%d", rank, world);
     const uint32_t rows = ctx->row_end - ctx->row_begin;
-    if (world > 1 && (ctx->cfg.height % (uint32_t)world != 0 || rows != ctx->cfg.height / (uint32_t)world || ctx->row_begin != rows * (uint32_t)rank))
+    if (ctx->interleave) {
+        if ((uint32_t)world != ctx->part_world || (uint32_t)rank != ctx->part_rank)
+            return fail(ctx, VRT_E_INVALID, "vrt_comm_init: rank %d of %d does not match the interleaved partition %u of %u given to vrt_init", rank, world,
+                        ctx->part_rank, ctx->part_world);
+        if (world > 1 && ctx->cfg.width % 4 != 0) return fail(ctx, VRT_E_INVALID, "vrt_comm_init: the interleaved exchange needs width %% 4 == 0");
+    } else if (world > 1 && (ctx->cfg.height % (uint32_t)world != 0 || rows != ctx->cfg.height / (uint32_t)world || ctx->row_begin != rows * (uint32_t)rank)) {
         return fail(ctx, VRT_E_INVALID, "vrt_comm_init: rank %d of %d must own rows [%u, %u)", rank, world, ctx->cfg.height / world * rank,
                     ctx->cfg.height / world * (rank + 1));
+    }
     if (!load_nccl(ctx->err, sizeof(ctx->err))) return VRT_E_NCCL;
     VRT_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
     ncclUniqueId nid;
@@ -593,6 +641,12 @@ int vrt_comm_init(vrt_ctx* ctx, int rank, int world, const uint8_t id[VRT_NCCL_I
     const ncclResult_t r = g_nccl.CommInitRank(&ctx->comm, world, nid, rank);
     if (r != ncclSuccess) return fail(ctx, VRT_E_NCCL, "ncclCommInitRank failed: %s", g_nccl.GetErrorString(r));
     ctx->rank = rank, ctx->world = world;
+    if (world > 1 && !ctx->d_barrier) {
+        VRT_CUDA(ctx, cudaMalloc(&ctx->d_barrier, 4));
+        VRT_CUDA(ctx, cudaMemsetAsync(ctx->d_barrier, 0, 4, ctx->stream));
+    }
+    if (world > 1 && ctx->interleave && !ctx->d_gather)
+        VRT_CUDA(ctx, cudaMalloc(&ctx->d_gather, (size_t)world * ctx->strips_max * kStripRows * ctx->cfg.width * 4));
     return VRT_OK;
 }
 

@@ -15,6 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 VRT_ABI_VERSION = 1
 VRT_FLAG_AOV = 1
 VRT_FLAG_BASELINE = 2
+VRT_FLAG_INTERLEAVE = 4
 VRT_EXCHANGE_ALLGATHER = 0
 VRT_EXCHANGE_PEER_STORE = 1
 VRT_NCCL_ID_BYTES = 128
@@ -92,6 +93,7 @@ class Config(C.Structure):
         ("struct_size", C.c_uint32), ("abi_version", C.c_uint32), ("width", C.c_uint32), ("height", C.c_uint32),
         ("brick_dim", C.c_uint32), ("material_capacity", C.c_uint32), ("n_bricks", C.c_uint64), ("n_brick_alloc", C.c_uint64),
         ("device", C.c_int32), ("flags", C.c_uint32), ("row_begin", C.c_uint32), ("row_end", C.c_uint32),
+        ("part_rank", C.c_uint32), ("part_world", C.c_uint32),
     ]
 
 
@@ -440,12 +442,15 @@ class HostSun:
 class Context:
     """One vrt_ctx: ComputePipeline + its buffers + the target image (include/vrt.h)."""
 
-    def __init__(self, width, height, n_bricks, brick_dim=4, n_brick_alloc=0, material_capacity=256, device=0, flags=0, rows=(0, 0), handle=None):
+    def __init__(self, width, height, n_bricks, brick_dim=4, n_brick_alloc=0, material_capacity=256, device=0, flags=0, rows=(0, 0), part=None, handle=None):
         self._l = lib()
         self.width, self.height = width, height
         self._owned = handle is None
         if handle is None:
-            cfg = Config(C.sizeof(Config), VRT_ABI_VERSION, width, height, brick_dim, material_capacity, n_bricks, n_brick_alloc, device, flags, rows[0], rows[1])
+            if part is not None:  # (rank, world): interleaved 4-row strips
+                flags |= VRT_FLAG_INTERLEAVE
+            cfg = Config(C.sizeof(Config), VRT_ABI_VERSION, width, height, brick_dim, material_capacity, n_bricks, n_brick_alloc, device, flags, rows[0], rows[1],
+                         part[0] if part else 0, part[1] if part else 0)
             h = C.c_void_p()
             rc = self._l.vrt_init(C.byref(h), C.byref(cfg))
             if rc != 0:
