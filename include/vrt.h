@@ -200,8 +200,10 @@ int vrt_trace_to_host(vrt_ctx* ctx, const vrt_camera* camera, const vrt_sun* sun
  * stream), so the copy of frame k overlaps the trace of frame k+1 — the CUDA counterpart of the reference keeping one
  * compute frame in flight while the previous one is presented (ComputePipeline.zig:423-434, Pipeline.zig:494-517).
  * `rgba8_host` must stay valid until vrt_sync() (or until two further async calls have been made) and should be pinned
- * host memory, otherwise the copy is staged and does not overlap.  Not available while a caller-owned framebuffer is
- * attached or in VRT_EXCHANGE_PEER_STORE mode (VRT_E_STATE). */
+ * host memory, otherwise the copy is staged and does not overlap.  `rgba8_host` may be NULL: the frame is traced (and
+ * exchanged) in the same ring slot but not copied — in a multi-GPU run every rank must issue the same sequence of frame
+ * calls, and only the ranks that need the pixels on their host pass a buffer.  Not available while a caller-owned
+ * framebuffer is attached (VRT_E_STATE). */
 int vrt_trace_to_host_async(vrt_ctx* ctx, const vrt_camera* camera, const vrt_sun* sun, uint8_t* rgba8_host, size_t bytes);
 
 /* Debug / parity (requires VRT_FLAG_AOV). */

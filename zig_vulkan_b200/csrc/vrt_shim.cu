@@ -103,6 +103,7 @@ struct vrt_ctx {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_traced[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
     bool slot_used[2] = {false, false};
+    cudaEvent_t barrier_after_copy = nullptr;  // peer-store: the frame barrier must not pass before this copy has finished
     uint64_t async_frames = 0;
 
     // debug
@@ -209,8 +210,9 @@ void fill_params(const vrt_ctx* c, const vrt_camera* cam, const vrt_sun* sun, Tr
     P.vec_store_ok = (cam->image_width % 4 == 0) && ((reinterpret_cast<uintptr_t>(c->d_fb) & 15u) == 0);
     P.n_peers = 0;
     if (c->world > 1 && c->exchange_mode == VRT_EXCHANGE_PEER_STORE && c->peers_open) {
+        const size_t slot_words = (c->d_fb == c->d_fb_ring1) ? c->fb_bytes / 4 : 0;  // same ring slot on every rank
         for (int r = 0; r < c->world; r++)
-            if (r != c->rank) P.peer_fb[P.n_peers++] = static_cast<uint32_t*>(c->peer_fb[r]);
+            if (r != c->rank) P.peer_fb[P.n_peers++] = static_cast<uint32_t*>(c->peer_fb[r]) + slot_words;
     }
 }
 
@@ -315,7 +317,8 @@ int vrt_init(vrt_ctx** out_ctx, const vrt_config* cfg) {
     INIT_CUDA(cudaMalloc(&ctx->d_occupancy, ctx->n_occupancy));
     INIT_CUDA(cudaMalloc(&ctx->d_start_indices, ctx->n_start_indices * 4));
     INIT_CUDA(cudaMalloc(&ctx->d_material_indices, ctx->n_material_indices));
-    INIT_CUDA(cudaMalloc(&ctx->d_fb_own, ctx->fb_bytes));
+    INIT_CUDA(cudaMalloc(&ctx->d_fb_own, 2 * ctx->fb_bytes));  // slot 0 + slot 1 of the frame ring, one allocation = one IPC handle
+    ctx->d_fb_ring1 = ctx->d_fb_own + ctx->fb_bytes / 4;
     INIT_CUDA(cudaMalloc(&ctx->d_tile_counter, 8));
     ctx->d_fb = ctx->d_fb_own;
     ctx->h_materials = new (std::nothrow) vrt_material[ctx->n_materials]();
@@ -331,7 +334,7 @@ int vrt_init(vrt_ctx** out_ctx, const vrt_config* cfg) {
     INIT_CUDA(cudaMemsetAsync(ctx->d_occupancy, 0, ctx->n_occupancy, ctx->stream));
     INIT_CUDA(cudaMemsetAsync(ctx->d_start_indices, 0xff, ctx->n_start_indices * 4, ctx->stream));
     INIT_CUDA(cudaMemsetAsync(ctx->d_material_indices, 0, ctx->n_material_indices, ctx->stream));
-    INIT_CUDA(cudaMemsetAsync(ctx->d_fb_own, 0, ctx->fb_bytes, ctx->stream));
+    INIT_CUDA(cudaMemsetAsync(ctx->d_fb_own, 0, 2 * ctx->fb_bytes, ctx->stream));
     INIT_CUDA(cudaMemsetAsync(ctx->d_tile_counter, 0, 8, ctx->stream));
     if (cfg->brick_dim == 4) INIT_CUDA(cudaMalloc(&ctx->d_occ_dense, cfg->n_bricks * 8));
     if (cfg->flags & VRT_FLAG_AOV) {
@@ -360,7 +363,6 @@ void vrt_deinit(vrt_ctx* ctx) {
     cudaFree(ctx->d_counters), cudaFree(ctx->d_occ_dense), cudaFree(ctx->d_dist), cudaFree(ctx->d_dist_tmp);
     cudaFree(ctx->d_tile_counter), cudaFree(ctx->d_gather), cudaFree(ctx->d_barrier);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
-    cudaFree(ctx->d_fb_ring1);
     for (int i = 0; i < 2; i++) {
         if (ctx->ev_traced[i]) cudaEventDestroy(ctx->ev_traced[i]);
         if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
@@ -468,6 +470,9 @@ int vrt_trace(vrt_ctx* ctx, const vrt_camera* camera, const vrt_sun* sun) {
     } else if (ctx->world > 1) {
         // peer-store: the pixels are already in every rank's framebuffer; a 4-byte all-reduce makes "every rank has finished
         // frame k" visible in stream order, so frame k+1's remote stores cannot overtake a peer still reading frame k
+        // (pipelined frames: the NEXT frame's remote stores land in the other ring slot of every peer, so this barrier also
+        // waits until this rank has copied that slot's previous frame to its host)
+        if (ctx->barrier_after_copy) VRT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->barrier_after_copy, 0));
         const ncclResult_t r = g_nccl.AllReduce(ctx->d_barrier, ctx->d_barrier, 1, ncclInt32, ncclSum, ctx->comm, ctx->stream);
         if (r != ncclSuccess) return fail(ctx, VRT_E_NCCL, "ncclAllReduce failed: %s", g_nccl.GetErrorString(r));
     }
@@ -487,15 +492,11 @@ int vrt_sync(vrt_ctx* ctx) {
 
 int vrt_trace_to_host_async(vrt_ctx* ctx, const vrt_camera* camera, const vrt_sun* sun, uint8_t* rgba8_host, size_t bytes) {
     if (!ctx) return VRT_E_INVALID;
-    if (!rgba8_host || bytes != ctx->fb_bytes) return fail(ctx, VRT_E_INVALID, "vrt_trace_to_host_async: need a %zu-byte buffer", ctx->fb_bytes);
+    if (rgba8_host && bytes != ctx->fb_bytes) return fail(ctx, VRT_E_INVALID, "vrt_trace_to_host_async: need a %zu-byte buffer", ctx->fb_bytes);
     if (ctx->d_fb != ctx->d_fb_own && ctx->d_fb != ctx->d_fb_ring1)
         return fail(ctx, VRT_E_STATE, "vrt_trace_to_host_async: not available while a caller-owned framebuffer is attached");
-    if (ctx->world > 1 && ctx->exchange_mode == VRT_EXCHANGE_PEER_STORE)
-        return fail(ctx, VRT_E_STATE, "vrt_trace_to_host_async: not available in VRT_EXCHANGE_PEER_STORE mode");
     VRT_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
     if (!ctx->copy_stream) {  // first use: second framebuffer, copy stream, events
-        VRT_CUDA(ctx, cudaMalloc(&ctx->d_fb_ring1, ctx->fb_bytes));
-        VRT_CUDA(ctx, cudaMemsetAsync(ctx->d_fb_ring1, 0, ctx->fb_bytes, ctx->stream));
         VRT_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
         for (int i = 0; i < 2; i++) {
             VRT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_traced[i], cudaEventDisableTiming));
@@ -508,7 +509,9 @@ int vrt_trace_to_host_async(vrt_ctx* ctx, const vrt_camera* camera, const vrt_su
     if (ctx->slot_used[slot]) VRT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[slot], 0));
     uint32_t* const saved = ctx->d_fb;
     ctx->d_fb = fb;
+    ctx->barrier_after_copy = ctx->slot_used[slot ^ 1] ? ctx->ev_copied[slot ^ 1] : nullptr;
     const int rc = vrt_trace(ctx, camera, sun);
+    ctx->barrier_after_copy = nullptr;
     ctx->d_fb = saved;
     if (rc != VRT_OK) return rc;
     VRT_CUDA(ctx, cudaEventRecord(ctx->ev_traced[slot], ctx->stream));
@@ -517,7 +520,8 @@ int vrt_trace_to_host_async(vrt_ctx* ctx, const vrt_camera* camera, const vrt_su
     const bool whole = ctx->world > 1 || ctx->interleave;
     const size_t n = whole ? ctx->fb_bytes : (size_t)(ctx->row_end - ctx->row_begin) * ctx->cfg.width * 4;
     const size_t from = whole ? 0 : off;
-    VRT_CUDA(ctx, cudaMemcpyAsync(rgba8_host + from, reinterpret_cast<const uint8_t*>(fb) + from, n, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    if (rgba8_host)  // NULL: take part in the frame ring (multi-GPU ranks that do not need the pixels on their host) without a copy
+        VRT_CUDA(ctx, cudaMemcpyAsync(rgba8_host + from, reinterpret_cast<const uint8_t*>(fb) + from, n, cudaMemcpyDeviceToHost, ctx->copy_stream));
     VRT_CUDA(ctx, cudaEventRecord(ctx->ev_copied[slot], ctx->copy_stream));
     ctx->slot_used[slot] = true;
     ctx->async_frames++;

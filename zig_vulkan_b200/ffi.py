@@ -529,9 +529,10 @@ class Context:
         self._check(self._l.vrt_trace_to_host(self.handle, C.byref(camera), C.byref(sun), _ptr(out), nbytes))
         return out
 
-    def trace_to_host_async(self, camera: CameraDevice, sun: SunDevice, out_ptr: int):
+    def trace_to_host_async(self, camera: CameraDevice, sun: SunDevice, out_ptr: int | None):
         """Pipelined frame: returns after enqueueing; `out_ptr` (pinned host memory, width*height*4 bytes) is valid after sync()."""
-        self._check(self._l.vrt_trace_to_host_async(self.handle, C.byref(camera), C.byref(sun), C.c_void_p(out_ptr), self.width * self.height * 4))
+        self._check(self._l.vrt_trace_to_host_async(self.handle, C.byref(camera), C.byref(sun), C.c_void_p(out_ptr) if out_ptr else None,
+                                                    self.width * self.height * 4))
 
     def read_aov(self) -> np.ndarray:
         out = np.empty(self.height * self.width, dtype=AOV_DTYPE)
