@@ -32,7 +32,8 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--workload", default="C3", choices=["C1", "C2", "C3", "C4", "C5"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--exchange", default="allgather", choices=["allgather", "peer"])
+    ap.add_argument("--exchange", default="peer", choices=["allgather", "peer"],
+                    help="N > 1: fused peer stores from the trace kernel (default) or an NCCL all-gather after it")
     ap.add_argument("--partition", default="interleave", choices=["interleave", "slab"], help="N > 1: 4-row strips round-robin, or one row slab per rank")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--baseline-kernel", action="store_true", help="time the reference-shape kernel instead of the tuned one")
@@ -168,8 +169,8 @@ def main():
         run_reference(args)
         return
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"  # NCCL prints its version banner on stdout; this program's stdout is ONE JSON line
+    # NCCL prints its version banner (and any debug output) on stdout; this program's stdout is ONE JSON line
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if args.gpus > 1 and world == 1:
         # convenience: re-launch under torchrun, one rank per GPU
         port = 29500 + (os.getpid() % 2000)
