@@ -32,8 +32,9 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--workload", default="C3", choices=["C1", "C2", "C3", "C4", "C5"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--exchange", default="peer", choices=["allgather", "peer"],
-                    help="N > 1: fused peer stores from the trace kernel (default) or an NCCL all-gather after it")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "allgather", "peer"],
+                    help="N > 1: fused peer stores from the trace kernel, or an NCCL all-gather after it; auto = peer up to 4 GPUs, "
+                         "all-gather above (measured: profiles/README.md)")
     ap.add_argument("--partition", default="interleave", choices=["interleave", "slab"], help="N > 1: 4-row strips round-robin, or one row slab per rank")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--baseline-kernel", action="store_true", help="time the reference-shape kernel instead of the tuned one")
@@ -170,6 +171,9 @@ def main():
         return
     world = int(os.environ.get("WORLD_SIZE", "1"))
     # NCCL prints its version banner (and any debug output) on stdout; this program's stdout is ONE JSON line
+    # (NCCL only honours NCCL_DEBUG_FILE above the VERSION level)
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if args.gpus > 1 and world == 1:
         # convenience: re-launch under torchrun, one rank per GPU
@@ -194,6 +198,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    if args.exchange == "auto":
+        args.exchange = "peer" if world <= 4 else "allgather"
     wl = scenes.WORKLOADS[args.workload]
     W, H = wl.width, wl.height
     interleave = world > 1 and args.partition == "interleave" and not args.baseline_kernel
