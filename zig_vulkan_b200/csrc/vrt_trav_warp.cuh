@@ -195,45 +195,45 @@ VRT_DI bool grid_hit_warp(const TraceParams& P, const Ray& r, bool active, bool 
     idx += obase;
     const uint8_t* __restrict__ dist = P.dist;
     int last_stride = 0;  // stride of the most recent step (0: none yet -> slab normal)
-    bool parked = false, result = false;
+    bool result = false;
     uint32_t cnt_word = ~0u;  // COUNT: the reference's one-word status cache (:301,:321-326)
     constexpr uint32_t kIdle = 0xffffu;
+    enum : int { kMarching = 0, kParked = 1, kDone = 2 };
+    int mode = marching ? kMarching : kDone;
     // deltas / strides actually applied in the step loop: zero while this lane is parked or finished
     float fdx = marching ? dx : 0.0f, fdy = marching ? dy : 0.0f, fdz = marching ? dz : 0.0f;
     int fsx = stx, fsy = sty, fsz = stz;  // (stx.. are 0 when not marching)
 
-    while (__any_sync(kFullMask, marching)) {
+    while (__any_sync(kFullMask, mode != kDone)) {
         // ---- phase A (:313-373 without the per-cell tests): rounds of { every marching ray looks its cell up; all of
         // them take k = min over the warp of the distances found steps }.  k is warp-uniform, so the step loop has no
         // per-lane counter and no divergence; rays that are parked / finished ride along with zero deltas and strides
         // (x + 0.0f == x), which keeps the parked rays' DDA state intact for the step after a brick miss.
         for (;;) {
             uint32_t d = kIdle;
-            if (marching && !parked) {
+            if (mode == kMarching) {
                 d = __ldg(dist + idx);
-                // left the grid (:313-315), or — exact shortcut — no loaded brick exists anywhere in the octant this
-                // DDA can reach: the shader's loop would only step through empty cells until it leaves the grid.
-                // (COUNT keeps marching so that the step counters equal the shader's.)
-                if (d == kDistBorder || (!COUNT && (d & kDistFree))) {
-                    marching = false;
-                    d = kIdle;
-                } else {
+                // bit 7: left the grid (border byte 255, :313-315), or — exact shortcut — no loaded brick exists anywhere in
+                // the octant this DDA can reach, so the shader's loop would only step through empty cells until it
+                // leaves the grid.  (COUNT keeps marching through free octants so that its step counters equal the shader's.)
+                const bool out = COUNT ? d == kDistBorder : (d & kDistFree) != 0u;
+                if (!out) {
                     d &= 0x7fu;
                     if (COUNT) {  // an in-grid cell = one iteration of the shader's loop; emulate its one-word status cache (:321-326)
                         ti.grid_steps++;
                         const uint32_t gi = cell_grid_index(P, idx - obase, log_px, log_pzx);
                         if ((gi >> 5) != cnt_word) cnt_word = gi >> 5, ti.status_fetches++;
                     }
-                    if (d == 0u) {
-                        parked = true;  // status bit set (:328)
-                        d = kIdle;
-                    }
+                }
+                if (out || d == 0u) {  // d == 0: status bit set (:328) -> park for phase B
+                    mode = out ? kDone : kParked;
+                    d = kIdle;
+                    fdx = fdy = fdz = 0.0f, fsx = fsy = fsz = 0;
                 }
             }
             const uint32_t k = __reduce_min_sync(kFullMask, d);
             if (k == kIdle) break;
             const bool on = d != kIdle;
-            if (!on) fdx = fdy = fdz = 0.0f, fsx = fsy = fsz = 0;
             for (uint32_t i = 1; i < k; i++) {  // k-1 steps onto cells known to be empty and inside
                 march_step(sx, sy, sz, fdx, fdy, fdz, fsx, fsy, fsz, idx);
                 if (COUNT && on) {
@@ -249,8 +249,7 @@ VRT_DI bool grid_hit_warp(const TraceParams& P, const Ray& r, bool active, bool 
             if (on) last_stride = idx - before;
         }
         // ---- phase B: the parked rays test their bricks together (:329-342)
-        if (parked) {
-            parked = false;
+        if (mode == kParked) {
             if (last_stride != 0) {
                 const int a = last_stride < 0 ? -last_stride : last_stride;
                 n = step_normal(a == 1 ? 0 : (a == (1 << log_px) ? 2 : 1), ray_step);
@@ -269,13 +268,14 @@ VRT_DI bool grid_hit_warp(const TraceParams& P, const Ray& r, bool active, bool 
                 if (need_material && !ignore_test) hit.index = material_index_at(P, grid_index, voxel_index);
                 if (COUNT) ti.grid_index = grid_index, ti.voxel_index = (uint32_t)voxel_index;
                 result = true;
-                marching = false;
+                mode = kDone;
             } else {  // :345-372, then the next cell is looked up
                 t_side = fminf(fminf(sx, sy), sz);
                 const int before = idx;
                 march_step(sx, sy, sz, dx, dy, dz, stx, sty, stz, idx);
                 last_stride = idx - before;
                 fdx = dx, fdy = dy, fdz = dz, fsx = stx, fsy = sty, fsz = stz;  // marching again
+                mode = kMarching;
             }
         }
     }
