@@ -50,7 +50,9 @@ __global__ void __launch_bounds__(kTunedThreads, MINB) trace_warp_kernel(const _
         if (lane == 0) t = atomicAdd(P.tile_counter, 1ull) - P.tile_base;
         t = __shfl_sync(kFullMask, t, 0);
         if (t >= (unsigned long long)tiles_total) break;
-        const uint32_t tile = (uint32_t)t;
+        // bottom-up: in the reference's convention image row 0 is up (sky); starting with the ground rows leaves the cheap sky
+        // tiles to fill the tail of the launch
+        const uint32_t tile = P.tile_top_down ? (uint32_t)t : tiles_total - 1u - (uint32_t)t;
         const uint32_t px = (tile % tiles_x) * kTileW + lx;
         const uint32_t strip = tile / tiles_x;  // this launch's k-th strip of kTileH rows
         const uint32_t py = P.il_world ? (strip * P.il_world + P.il_rank) * kTileH + ly : P.row_begin + strip * kTileH + ly;
@@ -136,20 +138,24 @@ __global__ void __launch_bounds__(256) build_occ_dense_kernel(const __grid_const
     occ_dense[g] = occ;
 }
 
-// Directional Chebyshev distance transform.  For each of the 8 direction octants o (bit0: x decreasing, bit1: y
-// decreasing, bit2: z decreasing) dist[o][p] = min over blockers q in the closed octant of p (every coordinate of
-// q - p has the octant's sign or is 0) of max_a |q_a - p_a|; blockers are loaded bricks (status bit set) and every cell
-// outside the grid.  A DDA only ever moves along its own octant, so a ray at p can take dist-1 steps blind.
-// Separable: three one-sided 1-D passes (x, z, y), each a bounded scan with early exit; values are capped at 254.
-constexpr int kDistCap = 126;  // 7 bits; bit 7 of a dist byte = "no loaded brick anywhere in this octant" (kDistFree)
+// Directional distance grids.  For each of the 8 direction octants o (bit0: x decreasing, bit1: y decreasing, bit2: z
+// decreasing) and every cell p:
+//   dist = min over blockers q in the closed octant of p (every coordinate of q - p has the octant's sign or is 0) of the
+//          L1 distance |q - p|_1, capped at 126; blockers are loaded bricks (status bit set) and every cell outside the grid.
+//          A DDA moves one cell along one axis per step and only along its own octant, so after j steps it is at L1
+//          distance exactly j inside the octant: from p it can take dist-1 steps blind, the dist-th lands on a cell to look up.
+//   free = no loaded brick at all in the closed octant (bit 7): the DDA can only leave the grid, an exact instant miss.
+// L1 is separable into three one-sided scans (x, z, y): walking a line from the end the octant looks towards,
+//   d(c) = min(prev(c), 1 + d(next c)),  d(outside) = 0;     free(c) = prev_free(c) && free(next c),  free(outside) = true
+// with prev = the previous pass' value (pass x: 0 / not free at loaded bricks, infinity / free elsewhere).  One thread per
+// line and output variant, O(cells) whatever the scene.  byte = d | free << 7  (0 = loaded brick; never 255 = border).
+//   axis 0 (x): in = status bits,             variants v = xneg                         -> out[v]
+//   axis 1 (z): in = out of axis 0 [xneg],    variants v = xneg | zneg << 1             -> out[v]
+//   axis 2 (y): in = out of axis 1 [x|z<<1],  variants v = xneg | yneg << 1 | zneg << 2 -> padded dist planes
+constexpr uint32_t kDistCap = 126u;
 
-// "Is there any loaded brick in the closed octant of this cell": three OR-scans along x, z, y.  One thread per line and
-// output variant; a line is walked once from its far end, so the cost is O(cells) whatever the scene.
-//   axis 0 (x): in = status bits,            variants v = xneg                       -> out[v]
-//   axis 1 (z): in = out of axis 0 [xneg],   variants v = xneg | zneg << 1           -> out[v]
-//   axis 2 (y): in = out of axis 1 [x|z<<1], variants v = xneg | yneg << 1 | zneg << 2 -> out[v]
-__global__ void __launch_bounds__(128) any_scan_kernel(const __grid_constant__ TraceParams P, const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
-                                                       size_t n_bricks, int axis) {
+__global__ void __launch_bounds__(128) dist_scan_kernel(const __grid_constant__ TraceParams P, const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
+                                                        size_t n_bricks, int axis) {
     const size_t dim_x = P.grid.dim_x, dim_y = P.grid.dim_y, dim_z = P.grid.dim_z;
     const size_t lines = axis == 0 ? dim_z * dim_y : (axis == 1 ? dim_x * dim_y : dim_x * dim_z);
     const size_t line = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -164,66 +170,27 @@ __global__ void __launch_bounds__(128) any_scan_kernel(const __grid_constant__ T
     } else {
         base = line, stride = dim_x * dim_z, len = (int)dim_y, neg = (v >> 1) & 1, vin = (v & 1) | ((v >> 2) << 1);
     }
-    uint8_t acc = 0;
+    uint32_t carry_d = 0u, carry_free = kDistFree;  // the cell beyond the grid: a blocker, but not a brick
     for (int i = 0; i < len; i++) {
-        const size_t g = base + (size_t)(neg ? i : len - 1 - i) * stride;  // walk from the end the octant looks towards
-        acc |= axis == 0 ? (uint8_t)status_bit(P, g) : in[(size_t)vin * n_bricks + g];
-        out[(size_t)v * n_bricks + g] = acc;
+        const int c = neg ? i : len - 1 - i;  // walk from the end the octant looks towards
+        const size_t g = base + (size_t)c * stride;
+        uint32_t prev;
+        if (axis == 0) prev = status_bit(P, g) ? 0u : (kDistCap | kDistFree);
+        else prev = in[(size_t)vin * n_bricks + g];
+        const uint32_t d = min(min(prev & 0x7fu, carry_d + 1u), kDistCap);
+        const uint32_t fr = prev & carry_free & kDistFree;
+        carry_d = d, carry_free = fr;
+        const uint32_t byte = d | fr;
+        if (axis == 2) {
+            const uint32_t x = (uint32_t)(g % dim_x), z = (uint32_t)((g / dim_x) % dim_z);
+            out[(size_t)v * P.dist_plane + (size_t)(x + 1) + ((size_t)(z + 1) << P.dist_log_px) + ((size_t)(c + 1) << (P.dist_log_px + P.dist_log_pz))] = (uint8_t)byte;
+        } else {
+            out[(size_t)v * n_bricks + g] = (uint8_t)byte;
+        }
     }
 }
 
-// pass x: blockIdx.y = 0 scans towards +x, 1 towards -x; out[v][g]
-__global__ void __launch_bounds__(256) dist_pass_x_kernel(const __grid_constant__ TraceParams P, uint8_t* __restrict__ out, size_t n_bricks) {
-    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= n_bricks) return;
-    const int neg = (int)blockIdx.y;
-    const int dim_x = (int)P.grid.dim_x;
-    const int x = (int)(g % dim_x);
-    const size_t row = g - x;
-    int best = min(neg ? x + 1 : dim_x - x, kDistCap);  // distance to the first cell outside the grid
-    for (int k = 0; k < best; k++) {
-        if (status_bit(P, row + (neg ? x - k : x + k))) best = k;
-    }
-    out[(size_t)neg * n_bricks + g] = (uint8_t)best;
-}
-
-// one-sided 1-D pass along an axis with element stride `stride` and extent `dim`; `coord` = this cell's coordinate on it
-VRT_DI int dist_scan(const uint8_t* __restrict__ in, size_t g, int coord, int dim, size_t stride, int neg) {
-    int best = min(neg ? coord + 1 : dim - coord, kDistCap);
-    for (int k = 0; k < best; k++) {
-        const int v = (int)in[neg ? g - (size_t)k * stride : g + (size_t)k * stride];
-        best = min(best, max(k, v));
-    }
-    return best;
-}
-
-// pass z: blockIdx.y = xneg | zneg << 1; in[xneg][g] -> out[xneg | zneg<<1][g]
-__global__ void __launch_bounds__(256) dist_pass_z_kernel(const __grid_constant__ TraceParams P, const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
-                                                          size_t n_bricks) {
-    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= n_bricks) return;
-    const int v = (int)blockIdx.y, xneg = v & 1, zneg = v >> 1;
-    const int z = (int)((g / P.grid.dim_x) % P.grid.dim_z);
-    out[(size_t)v * n_bricks + g] = (uint8_t)dist_scan(in + (size_t)xneg * n_bricks, g, z, (int)P.grid.dim_z, P.grid.dim_x, zneg);
-}
-
-// pass y: blockIdx.y = octant = xneg | yneg << 1 | zneg << 2; writes the padded layout the march indexes:
-// dist[octant * plane + (x+1) + ((z+1) << log_px) + ((y+1) << (log_px+log_pz))]
-__global__ void __launch_bounds__(256) dist_pass_y_kernel(const __grid_constant__ TraceParams P, const uint8_t* __restrict__ in,
-                                                          const uint8_t* __restrict__ any_oct, uint8_t* __restrict__ dist, size_t n_bricks) {
-    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= n_bricks) return;
-    const int oct = (int)blockIdx.y, xneg = oct & 1, yneg = (oct >> 1) & 1, zneg = oct >> 2;
-    const uint32_t x = (uint32_t)(g % P.grid.dim_x);
-    const uint32_t z = (uint32_t)((g / P.grid.dim_x) % P.grid.dim_z);
-    const uint32_t y = (uint32_t)(g / ((size_t)P.grid.dim_x * P.grid.dim_z));
-    const int d = dist_scan(in + (size_t)(xneg | (zneg << 1)) * n_bricks, g, (int)y, (int)P.grid.dim_y, (size_t)P.grid.dim_x * P.grid.dim_z, yneg);
-    const uint32_t free_flag = any_oct[(size_t)oct * n_bricks + g] ? 0u : kDistFree;
-    dist[(size_t)oct * P.dist_plane + (size_t)(x + 1) + ((size_t)(z + 1) << P.dist_log_px) + ((size_t)(y + 1) << (P.dist_log_px + P.dist_log_pz))] =
-        (uint8_t)((uint32_t)d | free_flag);
-}
-
-// tmp: 20 * n_bricks bytes of scratch.  The border bytes of `dist` (255) are written once when it is allocated.
+// tmp: 6 * n_bricks bytes of scratch.  The border bytes of `dist` (255) are written once when it is allocated.
 cudaError_t launch_build_accel(const TraceParams& P, unsigned long long* occ_dense, uint8_t* dist, uint8_t* tmp, size_t n_bricks, cudaStream_t stream,
                                LaunchInfo* info) {
     const unsigned blocks = (unsigned)((n_bricks + 255) / 256);
@@ -231,19 +198,13 @@ cudaError_t launch_build_accel(const TraceParams& P, unsigned long long* occ_den
         build_occ_dense_kernel<<<blocks, 256, 0, stream>>>(P, occ_dense, n_bricks);
         if (info) info->launches++;
     }
-    uint8_t* tmp_x = tmp;                  // [2][n]  distance pass x
-    uint8_t* tmp_z = tmp + 2 * n_bricks;   // [4][n]  distance pass z
-    uint8_t* any_x = tmp + 6 * n_bricks;   // [2][n]  OR-scan x
-    uint8_t* any_z = tmp + 8 * n_bricks;   // [4][n]  OR-scan z
-    uint8_t* any_y = tmp + 12 * n_bricks;  // [8][n]  OR-scan y = "a loaded brick exists in the octant"
+    uint8_t* tmp_x = tmp;                 // [2][n]
+    uint8_t* tmp_z = tmp + 2 * n_bricks;  // [4][n]
     const size_t dx = P.grid.dim_x, dy = P.grid.dim_y, dz = P.grid.dim_z;
-    any_scan_kernel<<<dim3((unsigned)((dz * dy + 127) / 128), 2), 128, 0, stream>>>(P, nullptr, any_x, n_bricks, 0);
-    any_scan_kernel<<<dim3((unsigned)((dx * dy + 127) / 128), 4), 128, 0, stream>>>(P, any_x, any_z, n_bricks, 1);
-    any_scan_kernel<<<dim3((unsigned)((dx * dz + 127) / 128), 8), 128, 0, stream>>>(P, any_z, any_y, n_bricks, 2);
-    dist_pass_x_kernel<<<dim3(blocks, 2), 256, 0, stream>>>(P, tmp_x, n_bricks);
-    dist_pass_z_kernel<<<dim3(blocks, 4), 256, 0, stream>>>(P, tmp_x, tmp_z, n_bricks);
-    dist_pass_y_kernel<<<dim3(blocks, 8), 256, 0, stream>>>(P, tmp_z, any_y, dist, n_bricks);
-    if (info) info->launches += 6;
+    dist_scan_kernel<<<dim3((unsigned)((dz * dy + 127) / 128), 2), 128, 0, stream>>>(P, nullptr, tmp_x, n_bricks, 0);
+    dist_scan_kernel<<<dim3((unsigned)((dx * dy + 127) / 128), 4), 128, 0, stream>>>(P, tmp_x, tmp_z, n_bricks, 1);
+    dist_scan_kernel<<<dim3((unsigned)((dx * dz + 127) / 128), 8), 128, 0, stream>>>(P, tmp_z, dist, n_bricks, 2);
+    if (info) info->launches += 3;
     return cudaGetLastError();
 }
 

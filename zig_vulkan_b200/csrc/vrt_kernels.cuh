@@ -21,7 +21,7 @@ struct LaunchInfo {
 // Enqueue the kernels that trace rows [P.row_begin, P.row_end) into P.fb.
 cudaError_t launch_trace(const TraceParams& P, TraceKernel which, bool aov, cudaStream_t stream, LaunchInfo* info);
 
-// Rebuild the derived structures (occ_dense, dist) from the reference-format buffers.  tmp: 20 * n_bricks bytes.
+// Rebuild the derived structures (occ_dense, dist) from the reference-format buffers.  tmp: 6 * n_bricks bytes.
 cudaError_t launch_build_accel(const TraceParams& P, unsigned long long* occ_dense, uint8_t* dist, uint8_t* tmp, size_t n_bricks, cudaStream_t stream,
                                LaunchInfo* info);
 // After the all-gather of an interleaved partition: rank-major strips -> row-major frame (width % 4 == 0).

@@ -8,6 +8,7 @@
 //   vkQueueSubmit + complete_fence (ComputePipeline.zig:423-459)                   -> stream order + cudaStreamSynchronize
 // NCCL is loaded lazily with dlopen so that the library has no link-time dependency on it.
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <dlfcn.h>
@@ -113,7 +114,7 @@ struct vrt_ctx {
     // derived acceleration structures (vrt_trav_warp.cuh)
     unsigned long long* d_occ_dense = nullptr;
     uint8_t* d_dist = nullptr;
-    uint8_t* d_dist_tmp = nullptr;  // 20 x n_bricks bytes of scratch for the separable distance transform + octant OR-scans
+    uint8_t* d_dist_tmp = nullptr;  // 6 x n_bricks bytes of scratch for the separable distance scans
     size_t dist_plane = 0;          // bytes per octant
     uint32_t dist_log_px = 0, dist_log_pz = 0;
     uint32_t accel_dim[3] = {0, 0, 0};
@@ -205,6 +206,10 @@ void fill_params(const vrt_ctx* c, const vrt_camera* cam, const vrt_sun* sun, Tr
     P.voxel_scale_pow2 = is_pow2(voxel_scale) ? 1u : 0u;
     P.inv_scale = P.scale_pow2 ? 1.0f / scale : 0.0f;
     P.inv_voxel_scale = P.voxel_scale_pow2 ? 1.0f / voxel_scale : 0.0f;
+    {
+        const char* v = getenv("VRT_TUNE_ORDER");
+        P.tile_top_down = (v && v[0] == '0') ? 1u : 0u;
+    }
     P.tile_counter = c->d_tile_counter;
     P.tile_base = c->tile_base;
     P.vec_store_ok = (cam->image_width % 4 == 0) && ((reinterpret_cast<uintptr_t>(c->d_fb) & 15u) == 0);
@@ -231,7 +236,7 @@ int ensure_accel(vrt_ctx* ctx) {
     if (8 * ctx->dist_plane > 0x7fffffffull)
         return fail(ctx, VRT_E_INVALID, "grid %ux%ux%u is too large for the 31-bit cell index of the march (8 padded distance planes)", dx, dy, dz);
     VRT_CUDA(ctx, cudaMalloc(&ctx->d_dist, 8 * ctx->dist_plane));
-    VRT_CUDA(ctx, cudaMalloc(&ctx->d_dist_tmp, 20 * (size_t)dx * dy * dz));
+    VRT_CUDA(ctx, cudaMalloc(&ctx->d_dist_tmp, 6 * (size_t)dx * dy * dz));
     VRT_CUDA(ctx, cudaMemsetAsync(ctx->d_dist, 255, 8 * ctx->dist_plane, ctx->stream));  // the border; interiors are rewritten by every build
     ctx->accel_dim[0] = dx, ctx->accel_dim[1] = dy, ctx->accel_dim[2] = dz;
     ctx->accel_dirty = true;

@@ -6,10 +6,11 @@
 // AROUND that arithmetic:
 //
 //   * Safe-step counts instead of per-cell occupancy tests.  A derived byte grid `dist` holds, per brick cell and per
-//     direction octant, the Chebyshev distance D (in cells) to the nearest loaded brick or grid face lying in that octant
-//     (0 = loaded brick, 255 = the one-cell border around the grid).  A DDA only moves along its own octant, one cell
-//     along one axis per step, so from a cell with distance D the next D-1 steps cannot land on a loaded brick or
-//     leave the grid and run with no memory access and no bounds test:
+//     direction octant, the L1 distance D (in cells) to the nearest loaded brick or grid face lying in that octant
+//     (0 = loaded brick, 255 = the one-cell border around the grid, bit 7 = no loaded brick in the octant at all).
+//     A DDA only moves along its own octant, one cell along one axis per step — after j steps it is at L1 distance
+//     exactly j — so from a cell with distance D the next D-1 steps cannot land on a loaded brick or leave the grid
+//     and run with no memory access and no bounds test:
 //     four compares, predicated FADDs and IADDs.  Only the D-th step is followed by a lookup.
 //     The border makes "left the grid" a byte value, so the march carries ONE linear index, not three coordinates.
 //   * Warp rounds.  The 32 rays of a tile look their cells up TOGETHER, reduce the distances found to the warp minimum
