@@ -37,6 +37,7 @@ def parse_args():
                          "all-gather above (measured: profiles/README.md)")
     ap.add_argument("--partition", default="interleave", choices=["interleave", "slab"], help="N > 1: 4-row strips round-robin, or one row slab per rank")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sweep", action="store_true", help="N = 1: also time the 11 way points of the reference's benchmark fly-through (Benchmark.zig:141-173)")
     ap.add_argument("--baseline-kernel", action="store_true", help="time the reference-shape kernel instead of the tuned one")
     return ap.parse_args()
 
@@ -349,6 +350,26 @@ def main():
                            "L2 flush enqueued between frames inside the timed region; frame_latency_ms = blocking vrt_trace_to_host"},
             "gpu_launches": launches_per_step * args.steps, "wall_ms": wall_ms, "clocks": clocks,
         }
+        if world == 1 and args.sweep:
+            # the reference's own benchmark camera path (offsets are in its world units; our world has the same 64-unit extent)
+            per_pose = []
+            for origin, yaw in scenes.sweep_poses(11):
+                pcam = scenes.camera_from_pose(W, H, origin, yaw)
+                cctx = ffi.Context(W, H, len(grid.brick_indices), brick_dim=wl.brick_dim, n_brick_alloc=grid.brick_alloc, device=local_rank,
+                                   flags=ffi.VRT_FLAG_AOV)
+                cctx.upload_grid(grid, mats)
+                cctx.trace(pcam, sun)
+                prays = cctx.counters()["rays"]
+                cctx.close()
+                ms = []
+                for i in range(3 + 20):
+                    flush.fill_(i & 0xFF)
+                    ctx.trace(pcam, sun)
+                    if i >= 3:
+                        ms.append(ctx.last_trace_ms())
+                per_pose.append({"origin": [round(v, 3) for v in origin], "rays": prays, "ms": sum(ms) / len(ms), "mrays_s": prays / (sum(ms) / len(ms) * 1e-3) / 1e6})
+            line["sweep"] = {"poses": per_pose, "mean_mrays_s": sum(p["mrays_s"] for p in per_pose) / len(per_pose),
+                             "total_mrays_s": sum(p["rays"] for p in per_pose) / sum(p["ms"] * 1e-3 for p in per_pose) / 1e6}
         if world == 1 and not args.no_cpu_baseline:
             crays, ctimes, cores = time_oracle(wl, 12, 1, budget_s=20.0)
             best = min(ctimes)

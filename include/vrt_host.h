@@ -147,6 +147,29 @@ typedef int (*vrt_emit_fn)(void* user, uint32_t x, uint32_t y, uint32_t z, uint8
 int vrt_scene_synthetic(uint32_t n_voxels, uint32_t seed, vrt_emit_fn emit, void* user);
 int vrt_scene_synthetic_fill(vrt_grid* g, uint32_t seed);
 
+/* ------------------------------------------------------------------ MagicaVoxel .vox reader
+ * vox/loader.zig + vox/types.zig (VOX v150: MAIN / PACK / SIZE / XYZI / RGBA, unknown chunks skipped) and the two loops
+ * of main.zig:96-118 that feed a model into the material table and the grid. */
+typedef struct vrt_vox vrt_vox;
+#define VRT_VOX_E_INVALID_ID (-10)            /* ParseError.InvalidId            (loader.zig:33)  */
+#define VRT_VOX_E_EXPECTED_SIZE_HEADER (-11)  /* ParseError.ExpectedSizeHeader                    */
+#define VRT_VOX_E_EXPECTED_XYZI_HEADER (-12)  /* ParseError.ExpectedXyziHeader                    */
+#define VRT_VOX_E_EXPECTED_RGBA_HEADER (-13)  /* ParseError.ExpectedRgbaHeader                    */
+#define VRT_VOX_E_UNEXPECTED_VERSION (-14)    /* ParseError.UnexpectedVersion                     */
+#define VRT_VOX_E_INVALID_FILE_CONTENT (-15)  /* ParseError.InvalidFileContent (also: truncated)  */
+#define VRT_VOX_E_IO (-16)                    /* file could not be opened / read                  */
+int vrt_vox_validate_header(const uint8_t* buffer, size_t len);                       /* validateHeader, loader.zig:215-228 */
+int vrt_vox_parse(vrt_vox** out, const uint8_t* buffer, size_t len, int strict);      /* parseBuffer,    loader.zig:41-197  */
+int vrt_vox_load(vrt_vox** out, const char* path, int strict);                        /* load,           loader.zig:9-30    */
+void vrt_vox_destroy(vrt_vox* v);
+int32_t vrt_vox_num_models(const vrt_vox* v);
+int vrt_vox_model_size(const vrt_vox* v, int32_t model, int32_t size_xyz[3]);
+const uint8_t* vrt_vox_model_xyzi(const vrt_vox* v, int32_t model, uint64_t* count); /* {x,y,z,color_index} bytes */
+const uint8_t* vrt_vox_palette(const vrt_vox* v);                                     /* 256 x {r,g,b,a} */
+uint32_t vrt_vox_materials(const vrt_vox* v, vrt_material* materials, uint32_t capacity, uint32_t material_base);  /* main.zig:96-108 */
+int vrt_vox_insert_into_grid(const vrt_vox* v, int32_t model, vrt_grid* grid, uint32_t off_x, uint32_t off_y, uint32_t off_z,
+                             uint32_t material_base);                                 /* main.zig:110-118 */
+
 /* Benchmark fly-through (Benchmark.zig:141-173): 11 way points x 11 orientations over 60 s.  t in [0,1] is the
  * normalised position along the path; offsets are scaled by `extent_scale` (1 = the reference's own units). */
 #define VRT_BENCH_PATH_POINTS 11

@@ -24,6 +24,7 @@ from .ffi import (  # noqa: F401
     Material,
     Renderer,
     SunDevice,
+    Vox,
     bench_path_pose,
     lib,
     host_lib,

@@ -203,6 +203,16 @@ VRT_HOST_SYMBOLS = {
     "vrt_scene_terrain_materials": (C.c_uint32, [_P, C.c_uint32]),
     "vrt_scene_synthetic": (C.c_int, [C.c_uint32, C.c_uint32, _P, _P]),
     "vrt_scene_synthetic_fill": (C.c_int, [_P, C.c_uint32]),
+    "vrt_vox_validate_header": (C.c_int, [_P, _SZ]),
+    "vrt_vox_parse": (C.c_int, [C.POINTER(_P), _P, _SZ, C.c_int]),
+    "vrt_vox_load": (C.c_int, [C.POINTER(_P), C.c_char_p, C.c_int]),
+    "vrt_vox_destroy": (None, [_P]),
+    "vrt_vox_num_models": (C.c_int32, [_P]),
+    "vrt_vox_model_size": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int32 * 3)]),
+    "vrt_vox_model_xyzi": (_P, [_P, C.c_int32, C.POINTER(C.c_uint64)]),
+    "vrt_vox_palette": (_P, [_P]),
+    "vrt_vox_materials": (C.c_uint32, [_P, _P, C.c_uint32, C.c_uint32]),
+    "vrt_vox_insert_into_grid": (C.c_int, [_P, C.c_int32, _P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]),
     "vrt_bench_path_pose": (None, [C.c_float, C.c_float, C.POINTER(C.c_float * 3), C.POINTER(C.c_float * 4)]),
 }
 
@@ -260,6 +270,64 @@ def bench_path_pose(t: float, extent_scale: float = 1.0):
     q = (C.c_float * 4)()
     host_lib().vrt_bench_path_pose(t, extent_scale, C.byref(o), C.byref(q))
     return list(o), list(q)
+
+
+VOX_ERRORS = {-10: "InvalidId", -11: "ExpectedSizeHeader", -12: "ExpectedXyziHeader", -13: "ExpectedRgbaHeader", -14: "UnexpectedVersion",
+              -15: "InvalidFileContent", -16: "IoError"}
+
+
+class Vox:
+    """A parsed MagicaVoxel file (vox/loader.zig, vox/types.zig)."""
+
+    def __init__(self, data: bytes | None = None, path: str | None = None, strict: bool = True):
+        h = host_lib()
+        self._h = h
+        handle = C.c_void_p()
+        if path is not None:
+            rc = h.vrt_vox_load(C.byref(handle), path.encode(), 1 if strict else 0)
+        else:
+            buf = (C.c_uint8 * len(data)).from_buffer_copy(data)
+            rc = h.vrt_vox_parse(C.byref(handle), buf, len(data), 1 if strict else 0)
+        if rc != 0:
+            raise VrtError(rc, "vox: " + VOX_ERRORS.get(rc, str(rc)))
+        self.handle = handle
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self._h.vrt_vox_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    @property
+    def num_models(self) -> int:
+        return self._h.vrt_vox_num_models(self.handle)
+
+    def size(self, model=0):
+        s = (C.c_int32 * 3)()
+        self._h.vrt_vox_model_size(self.handle, model, C.byref(s))
+        return tuple(s)
+
+    def xyzi(self, model=0) -> np.ndarray:
+        n = C.c_uint64()
+        p = self._h.vrt_vox_model_xyzi(self.handle, model, C.byref(n))
+        if not n.value:
+            return np.zeros((0, 4), dtype=np.uint8)
+        return np.frombuffer((C.c_uint8 * (n.value * 4)).from_address(p), dtype=np.uint8).reshape(-1, 4).copy()
+
+    @property
+    def palette(self) -> np.ndarray:
+        return np.frombuffer((C.c_uint8 * 1024).from_address(self._h.vrt_vox_palette(self.handle)), dtype=np.uint8).reshape(256, 4).copy()
+
+    def materials(self, materials: np.ndarray, material_base: int) -> int:
+        """main.zig:96-108: palette -> materials[material_base:], in place."""
+        assert materials.dtype == MATERIAL_DTYPE and materials.flags["C_CONTIGUOUS"]
+        return self._h.vrt_vox_materials(self.handle, _ptr(materials), materials.shape[0], material_base)
+
+    def insert_into(self, grid: "Grid", offset=(0, 0, 0), material_base=0, model=0) -> int:
+        """main.zig:110-118."""
+        return self._h.vrt_vox_insert_into_grid(self.handle, model, grid.handle, offset[0], offset[1], offset[2], material_base)
 
 
 class Grid:
