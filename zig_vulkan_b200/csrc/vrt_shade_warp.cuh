@@ -62,7 +62,9 @@ VRT_DI V3 ray_color_warp(const TraceParams& P, const Ray& r, bool lane_on, vrt_a
             }  // else: last allowed bounce — the guard at :218 fails next trip whatever `result`/`scattered` are
             if (sun_enabled) {  // :240-244
                 const V2 co = V2{current_ray.direction.x + current_ray.direction.z, current_ray.direction.y + current_ray.direction.z};
-                const V3 sun_sample_position = ld3(P.sun.position) + RandVec3mm(co, -P.sun.radius, P.sun.radius);
+                // radius 0: every component of RandVec3 is (-0) + 0 * Rand = +0 exactly (Rand is finite), so the three sines are skipped
+                const V3 jitter = P.sun.radius == 0.0f ? v3s(0.0f) : RandVec3mm(co, -P.sun.radius, P.sun.radius);
+                const V3 sun_sample_position = ld3(P.sun.position) + jitter;
                 shadow_ray = CreateRay(hit.point, sun_sample_position - hit.point);  // CreateShadowRay: ignore type MAT_NONE when enabled (:188)
             }
         }
@@ -129,7 +131,8 @@ VRT_DI uint32_t shade_pixel_warp(const TraceParams& P, uint32_t px, uint32_t py,
         color = color + ray_color_warp<BD, AOV>(P, ray, inside, &local_aov, pc, sample_i == 0);
     }
     const float fspp = (float)spp;
-    color = v3(sqrtf(color.x / fspp), sqrtf(color.y / fspp), sqrtf(color.z / fspp));  // :176
+    if (spp != 1) color = color / v3s(fspp);  // x / 1.0f == x
+    color = v3(sqrtf(color.x), sqrtf(color.y), sqrtf(color.z));  // :176
     if (AOV && inside && P.aov) P.aov[(size_t)py * P.cam.image_width + px] = local_aov;
     return pack_rgba8(color);
 }
