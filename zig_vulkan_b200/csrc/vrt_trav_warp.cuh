@@ -76,7 +76,7 @@ VRT_DI int dda_step_sel(V3& side, V3 delta, I3& pos, I3 step, float scale, float
 // BD == 4: the brick's 64-bit mask is in `occ`.  Otherwise mask bytes are read from the occupancy buffer (:415).
 template <int BD, bool COUNT>
 VRT_DI int brick_hit_warp(const TraceParams& P, const Ray& r, bool ignore_test, float grid_t_max, V3 ray_delta, I3 ray_step, float g_scale,
-                          V3 brick_position, unsigned long long occ, uint32_t grid_index, HitRecord& hit, AxisNormal& n, TraceInfo& ti) {
+                          V3 brick_position, unsigned long long occ, uint32_t grid_index, unsigned lanes, HitRecord& hit, AxisNormal& n, TraceInfo& ti) {
     const int bd = BD == 4 ? 4 : P.brick_dim;
     const float voxel_scale = g_scale * P.brick_voxel_scale;                                                  // :389
     const V3 fposition = div_scale(RayAt(r, hit.t) - brick_position, voxel_scale, P.inv_voxel_scale, P.voxel_scale_pow2 != 0u);  // :393
@@ -89,6 +89,7 @@ VRT_DI int brick_hit_warp(const TraceParams& P, const Ray& r, bool ignore_test, 
         const uint32_t brick_index = grid_index < P.n_brick_indices ? __ldg(P.brick_indices + grid_index) : 0u;  // :337
         mask_base = (unsigned long long)brick_index * P.brick_bytes;                                            // :390
     }
+    int found = -1;
     while ((uint32_t)pos.x < (uint32_t)bd && (uint32_t)pos.y < (uint32_t)bd && (uint32_t)pos.z < (uint32_t)bd && t_value <= local_t_max) {
         if (COUNT) ti.voxel_steps++;
         const int voxel_index = pos.x + bd * (pos.z + bd * pos.y);  // :412
@@ -109,16 +110,20 @@ VRT_DI int brick_hit_warp(const TraceParams& P, const Ray& r, bool ignore_test, 
                 ignore_brick = (m.type == r.ignore_type_material) && (r.internal_reflection == m.type_data);  // :427
             }
             if (!ignore_brick) {
-                const float t_offset = voxel_scale * 0.05f;           // :431
-                hit.t += t_value - t_offset;                          // :432
-                hit.normal = to_v3(n);
-                hit.point = RayAt(r, hit.t) + hit.normal * t_offset;  // :433
-                return voxel_index;
+                found = voxel_index;
+                break;
             }
         }
         n = step_normal(dda_step_sel(side_dist, ray_delta, pos, ray_step, voxel_scale, t_value), ray_step);  // :440-467
     }
-    return -1;
+    __syncwarp(lanes);  // the rays leave the loop at different trips: finish hits (and, in the caller, misses) together
+    if (found >= 0) {
+        const float t_offset = voxel_scale * 0.05f;           // :431
+        hit.t += t_value - t_offset;                          // :432
+        hit.normal = to_v3(n);
+        hit.point = RayAt(r, hit.t) + hit.normal * t_offset;  // :433
+    }
+    return found;
 }
 
 // Reference grid index (:318) of the padded linear cell index used by the march.
@@ -250,6 +255,7 @@ VRT_DI bool grid_hit_warp(const TraceParams& P, const Ray& r, bool active, bool 
             if (on) last_stride = idx - before;
         }
         // ---- phase B: the parked rays test their bricks together (:329-342)
+        const unsigned parked_lanes = __ballot_sync(kFullMask, mode == kParked);
         if (mode == kParked) {
             if (last_stride != 0) {
                 const int a = last_stride < 0 ? -last_stride : last_stride;
@@ -264,7 +270,7 @@ VRT_DI bool grid_hit_warp(const TraceParams& P, const Ray& r, bool active, bool 
             const float t_value = t_side * g_scale;                                            // :347,353,361,367
             hit.t = (t_value + grid_t_min) + 0.01f * g_scale;                                  // :332-334
             if (COUNT) ti.bricks_entered++;
-            const int voxel_index = brick_hit_warp<BD, COUNT>(P, r, ignore_test, grid_t_max, ray_delta, ray_step, g_scale, brick_min, occ, grid_index, hit, n, ti);
+            const int voxel_index = brick_hit_warp<BD, COUNT>(P, r, ignore_test, grid_t_max, ray_delta, ray_step, g_scale, brick_min, occ, grid_index, parked_lanes, hit, n, ti);
             if (voxel_index >= 0) {
                 if (need_material && !ignore_test) hit.index = material_index_at(P, grid_index, voxel_index);
                 if (COUNT) ti.grid_index = grid_index, ti.voxel_index = (uint32_t)voxel_index;
