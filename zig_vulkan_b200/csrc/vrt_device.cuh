@@ -265,7 +265,6 @@ struct TraceParams {
     float inv_scale, inv_voxel_scale;
     unsigned long long* tile_counter;     // persistent-kernel work counter (monotonic across frames)
     unsigned long long tile_base;         // value of *tile_counter when this launch starts
-    uint32_t tile_top_down;               // EXPERIMENT (env VRT_TUNE_ORDER=0): hand tiles out top row first
     uint32_t vec_store_ok;                // framebuffer rows are 16-B aligned -> 128-bit stores
     // fused peer-store exchange (multi-GPU): framebuffers of every rank, this rank included
     uint32_t* peer_fb[8];

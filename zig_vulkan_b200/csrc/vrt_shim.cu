@@ -8,7 +8,6 @@
 //   vkQueueSubmit + complete_fence (ComputePipeline.zig:423-459)                   -> stream order + cudaStreamSynchronize
 // NCCL is loaded lazily with dlopen so that the library has no link-time dependency on it.
 #include <cstdarg>
-#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <dlfcn.h>
@@ -206,10 +205,6 @@ void fill_params(const vrt_ctx* c, const vrt_camera* cam, const vrt_sun* sun, Tr
     P.voxel_scale_pow2 = is_pow2(voxel_scale) ? 1u : 0u;
     P.inv_scale = P.scale_pow2 ? 1.0f / scale : 0.0f;
     P.inv_voxel_scale = P.voxel_scale_pow2 ? 1.0f / voxel_scale : 0.0f;
-    {
-        const char* v = getenv("VRT_TUNE_ORDER");
-        P.tile_top_down = (v && v[0] == '0') ? 1u : 0u;
-    }
     P.tile_counter = c->d_tile_counter;
     P.tile_base = c->tile_base;
     P.vec_store_ok = (cam->image_width % 4 == 0) && ((reinterpret_cast<uintptr_t>(c->d_fb) & 15u) == 0);
