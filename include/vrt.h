@@ -206,6 +206,32 @@ int vrt_trace_to_host(vrt_ctx* ctx, const vrt_camera* camera, const vrt_sun* sun
  * framebuffer is attached (VRT_E_STATE). */
 int vrt_trace_to_host_async(vrt_ctx* ctx, const vrt_camera* camera, const vrt_sun* sun, uint8_t* rgba8_host, size_t bytes);
 
+/* ---------------------------------------------------------------------------------------------------
+ * Explicit rays (extension).  The reference only ever traces the rays its shader generates from the camera block
+ * (brick_raytracer.comp:474-477); this entry point runs the same GridHit/BrickHit (:271-471) on caller-supplied rays —
+ * picking, collision, light probes.  32 bytes in, 32 bytes out per ray, both moved with 128-bit accesses.
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct vrt_ray {      /* 32 bytes, 16-byte aligned */
+    float origin[3];
+    float _pad0;
+    float direction[3];       /* normalised by the kernel exactly like CreateRay (:180-184) */
+    float _pad1;
+} vrt_ray;
+
+typedef struct vrt_ray_hit {  /* 32 bytes, 16-byte aligned */
+    uint32_t hit;             /* 1 = a voxel was hit                              */
+    uint32_t grid_index;      /* GridHit `grid_index` (:318), ~0 on miss          */
+    uint32_t voxel_index;     /* BrickHit `voxel_index` (:412), ~0 on miss        */
+    uint32_t material;        /* material_indices[] value at the hit, ~0 on miss  */
+    float t;                  /* hit.t                                            */
+    float normal[3];          /* hit.normal                                       */
+} vrt_ray_hit;
+
+/* rays / hits are DEVICE pointers (count elements each); enqueued on the ctx stream like vrt_trace. */
+int vrt_trace_rays(vrt_ctx* ctx, const vrt_ray* rays_device, vrt_ray_hit* hits_device, size_t count);
+/* Same with HOST pointers: copies in, traces, copies out, blocks. */
+int vrt_trace_rays_host(vrt_ctx* ctx, const vrt_ray* rays_host, vrt_ray_hit* hits_host, size_t count);
+
 /* Debug / parity (requires VRT_FLAG_AOV). */
 int vrt_read_aov(vrt_ctx* ctx, vrt_aov* aov_host, size_t count);
 int vrt_get_counters(vrt_ctx* ctx, vrt_counters* out);

@@ -328,3 +328,49 @@ def test_pipelined_frames_match_blocking_frames(materials):
         assert np.array_equal(buf.numpy(), ref)
         assert np.array_equal(ctx.trace_to_host(cam, sun), ref)
     ctx.close()
+
+
+def test_explicit_rays_match_oracle_grid_hit(materials):
+    """vrt_trace_rays (extension): the cooperative GridHit on caller-supplied rays against the oracle's GridHit, ray by ray —
+    random rays from outside and inside the grid, axis-aligned rays (safeInverse path), a zero direction (defined miss),
+    and counts that are not a multiple of the warp size."""
+    import torch
+
+    grid = scenes.build_grid(64)
+    sc = orc.OracleScene.from_grid(grid, materials)
+    rng = np.random.default_rng(11)
+    n = 5000 + 13
+    origins = rng.uniform(-45, 45, (n, 3)).astype(np.float32)
+    origins[: n // 3] = rng.uniform(-30, 30, (n // 3, 3)).astype(np.float32)  # inside the grid
+    directions = rng.normal(size=(n, 3)).astype(np.float32)
+    directions[0] = (0, 0, 0)
+    directions[1:7] = [(1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, -1, 0), (0, 0, 1), (0, 0, -1)]
+    directions[7] = (0, 1, 1)
+    origins[1:8] = (0.3, -40.0, 0.7)
+    origins[3] = (0.3, -40.0, 0.7)  # straight down into the terrain
+    ctx = ffi.Context(16, 16, len(grid.brick_indices))
+    ctx.upload_grid(grid, materials)
+    for count in (1, 31, 33, n):
+        hits = ctx.trace_rays(origins[:count], directions[:count])
+        for i in range(count):
+            got, a = sc.grid_hit(origins[i], directions[i])
+            h = hits[i]
+            assert bool(h["hit"]) == got, i
+            if got:
+                assert (h["grid_index"], h["voxel_index"], h["material"]) == (a["grid_index"], a["voxel_index"], a["material"]), i
+                assert h["t"].view(np.uint32) == a["t"].view(np.uint32), i
+                assert np.array_equal(h["normal"], a["normal"]), i
+            else:
+                assert h["grid_index"] == 0xFFFFFFFF and h["material"] == 0xFFFFFFFF
+    assert hits["hit"].sum() > 500 and (hits["hit"] == 0).sum() > 500
+    # device-pointer entry point on a caller's stream
+    rays = np.zeros(n, dtype=ffi.RAY_DTYPE)
+    rays["origin"], rays["direction"] = origins, directions
+    d_rays = torch.from_numpy(rays.view(np.uint8).reshape(-1)).cuda()
+    d_hits = torch.zeros(n * 32, dtype=torch.uint8, device="cuda")
+    ctx.trace_rays_device(d_rays.data_ptr(), d_hits.data_ptr(), n)
+    ctx.sync()
+    assert np.array_equal(d_hits.cpu().numpy().view(ffi.RAY_HIT_DTYPE), hits)
+    with pytest.raises(ffi.VrtError):
+        ctx.trace_rays_device(d_rays.data_ptr() + 4, d_hits.data_ptr(), 1)  # misaligned
+    ctx.close()

@@ -115,6 +115,51 @@ cudaError_t launch_trace_tuned(const TraceParams& P, bool aov, cudaStream_t stre
 }
 
 // ----------------------------------------------------------------------------------------------------
+// Explicit rays: a warp takes 32 consecutive rays (two 128-bit loads each), runs the cooperative GridHit and writes
+// 32-byte hit records (two 128-bit stores each).  Grid-stride over blocks of 32 rays.
+// ----------------------------------------------------------------------------------------------------
+template <int BD>
+__global__ void __launch_bounds__(kTunedThreads, 3) trace_rays_kernel(const __grid_constant__ TraceParams P, const float4* __restrict__ rays,
+                                                                     uint4* __restrict__ hits, const unsigned long long count) {
+    const unsigned long long warps_total = (unsigned long long)gridDim.x * (kTunedThreads / 32);
+    const unsigned long long warp = (unsigned long long)blockIdx.x * (kTunedThreads / 32) + (threadIdx.x >> 5);
+    const uint32_t lane = threadIdx.x & 31u;
+    const bool ignore_test = P.materials_have_none != 0u;  // CreateRay's ignore type is MAT_NONE (:182)
+    for (unsigned long long base = warp * 32ull; base < count; base += warps_total * 32ull) {  // warp-uniform trip count
+        const unsigned long long i = base + lane;
+        const bool active = i < count;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f), d = make_float4(0.f, 0.f, 1.f, 0.f);
+        if (active) o = __ldg(rays + 2 * i), d = __ldg(rays + 2 * i + 1);
+        const Ray r = CreateRay(v3(o.x, o.y, o.z), v3(d.x, d.y, d.z));
+        HitRecord hit;
+        hit.point = v3s(0.0f), hit.normal = v3s(0.0f), hit.t = 0.0f, hit.index = 0u;
+        TraceInfo ti;
+        reset(ti);
+        const bool got = grid_hit_warp<BD, 1>(P, r, active, true, ignore_test, hit, ti);
+        if (active) {
+            hits[2 * i] = make_uint4(got ? 1u : 0u, got ? ti.grid_index : ~0u, got ? ti.voxel_index : ~0u, got ? hit.index : ~0u);
+            hits[2 * i + 1] = make_uint4(__float_as_uint(got ? hit.t : 0.0f), __float_as_uint(hit.normal.x), __float_as_uint(hit.normal.y), __float_as_uint(hit.normal.z));
+        }
+    }
+}
+
+cudaError_t launch_trace_rays(const TraceParams& P, const vrt_ray* rays, vrt_ray_hit* hits, size_t count, cudaStream_t stream, LaunchInfo* info) {
+    if (count == 0) return cudaSuccess;
+    int dev = 0, sms = 0;
+    cudaError_t e;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+    const unsigned long long warps_needed = (count + 31) / 32;
+    unsigned grid = (unsigned)(sms * 3);
+    const unsigned long long blocks_needed = (warps_needed + kTunedThreads / 32 - 1) / (kTunedThreads / 32);
+    if (grid > blocks_needed) grid = (unsigned)blocks_needed;
+    if (P.brick_dim == 4) trace_rays_kernel<4><<<grid, kTunedThreads, 0, stream>>>(P, reinterpret_cast<const float4*>(rays), reinterpret_cast<uint4*>(hits), count);
+    else trace_rays_kernel<0><<<grid, kTunedThreads, 0, stream>>>(P, reinterpret_cast<const float4*>(rays), reinterpret_cast<uint4*>(hits), count);
+    if (info) info->launches++;
+    return cudaGetLastError();
+}
+
+// ----------------------------------------------------------------------------------------------------
 // Derived acceleration structures (consumed by vrt_trav_warp.cuh).
 // ----------------------------------------------------------------------------------------------------
 VRT_DI bool status_bit(const TraceParams& P, size_t g) { return (__ldg(P.statuses + g / 32) >> (g % 32)) & 1u; }

@@ -24,6 +24,8 @@ cudaError_t launch_trace(const TraceParams& P, TraceKernel which, bool aov, cuda
 // Rebuild the derived structures (occ_dense, dist) from the reference-format buffers.  tmp: 6 * n_bricks bytes.
 cudaError_t launch_build_accel(const TraceParams& P, unsigned long long* occ_dense, uint8_t* dist, uint8_t* tmp, size_t n_bricks, cudaStream_t stream,
                                LaunchInfo* info);
+// Explicit-ray mode: GridHit on caller-supplied rays (device pointers).
+cudaError_t launch_trace_rays(const TraceParams& P, const vrt_ray* rays, vrt_ray_hit* hits, size_t count, cudaStream_t stream, LaunchInfo* info);
 // After the all-gather of an interleaved partition: rank-major strips -> row-major frame (width % 4 == 0).
 cudaError_t launch_deinterleave(const uint32_t* gathered, uint32_t* frame, uint32_t width, uint32_t height, uint32_t world, uint32_t strips_max,
                                 cudaStream_t stream, LaunchInfo* info);

@@ -29,7 +29,7 @@ VRT_DI V3 ray_color_warp(const TraceParams& P, const Ray& r, bool lane_on, vrt_a
         reset(ti);
         // :427 can only pass for rays that carry a real ignore type (after a refraction) or when a type-3 material exists
         const bool ignore_test = current_ray.ignore_type_material != VRT_MAT_NONE || P.materials_have_none != 0u;
-        const bool got = grid_hit_warp<BD, AOV>(P, current_ray, want, true, ignore_test, hit, ti);
+        const bool got = grid_hit_warp<BD, AOV ? 2 : 0>(P, current_ray, want, true, ignore_test, hit, ti);
         if (want) account<AOV>(pc, ti, got, false);
         const bool first = AOV && record_aov && iter == 0 && want;
         if (first) {
@@ -73,7 +73,7 @@ VRT_DI V3 ray_color_warp(const TraceParams& P, const Ray& r, bool lane_on, vrt_a
             shadow_hit.point = v3s(0.0f), shadow_hit.normal = v3s(0.0f), shadow_hit.t = 0.0f, shadow_hit.index = 0u;
             TraceInfo sti;
             reset(sti);
-            const bool blocked = grid_hit_warp<BD, AOV>(P, shadow_ray, alive, false, P.materials_have_none != 0u, shadow_hit, sti);  // :247
+            const bool blocked = grid_hit_warp<BD, AOV ? 2 : 0>(P, shadow_ray, alive, false, P.materials_have_none != 0u, shadow_hit, sti);  // :247
             if (alive) {
                 account<AOV>(pc, sti, blocked, true);
                 if (first) {

@@ -434,7 +434,7 @@ int vrt_trace(vrt_ctx* ctx, const vrt_camera* camera, const vrt_sun* sun) {
     const TraceKernel which = (ctx->cfg.flags & VRT_FLAG_BASELINE) ? KERNEL_REF : KERNEL_TUNED;
 
     VRT_CUDA(ctx, cudaEventRecord(ctx->ev_begin, ctx->stream));
-    if (which == KERNEL_TUNED && ctx->accel_dirty) {
+    if (which == KERNEL_TUNED && ctx->accel_dirty) {  // (vrt_trace_rays does the same)
         // Uploads changed statuses / indices / occupancy: rebuild the derived structures before tracing.  Stream order
         // gives upload -> build -> trace, where the reference has no barrier at all between its staging
         // copy and the next dispatch (edits land one frame late, Pipeline.zig:540).
@@ -548,6 +548,51 @@ int vrt_trace_to_host(vrt_ctx* ctx, const vrt_camera* camera, const vrt_sun* sun
     const size_t from = whole ? 0 : off;
     VRT_CUDA(ctx, cudaMemcpyAsync(rgba8_host + from, reinterpret_cast<const uint8_t*>(ctx->d_fb) + from, n, cudaMemcpyDeviceToHost, ctx->stream));
     VRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VRT_OK;
+}
+
+int vrt_trace_rays(vrt_ctx* ctx, const vrt_ray* rays_device, vrt_ray_hit* hits_device, size_t count) {
+    if (!ctx) return VRT_E_INVALID;
+    if (count == 0) return VRT_OK;
+    if (!rays_device || !hits_device) return fail(ctx, VRT_E_INVALID, "vrt_trace_rays: NULL buffer");
+    if ((reinterpret_cast<uintptr_t>(rays_device) | reinterpret_cast<uintptr_t>(hits_device)) & 15u)
+        return fail(ctx, VRT_E_INVALID, "vrt_trace_rays: buffers must be 16-byte aligned");
+    if (!ctx->have_grid) return fail(ctx, VRT_E_STATE, "vrt_trace_rays: vrt_upload_grid_state has not been called");
+    VRT_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    vrt_camera cam;
+    vrt_sun sun;
+    std::memset(&cam, 0, sizeof(cam));
+    std::memset(&sun, 0, sizeof(sun));
+    TraceParams P;
+    fill_params(ctx, &cam, &sun, P);
+    LaunchInfo info = {0u, 0ull};
+    if (ctx->accel_dirty) {
+        const size_t n_cells = (size_t)ctx->grid.dim_x * ctx->grid.dim_y * ctx->grid.dim_z;
+        VRT_CUDA(ctx, launch_build_accel(P, ctx->d_occ_dense, ctx->d_dist, ctx->d_dist_tmp, n_cells, ctx->stream, &info));
+        ctx->accel_dirty = false;
+    }
+    VRT_CUDA(ctx, launch_trace_rays(P, rays_device, hits_device, count, ctx->stream, &info));
+    ctx->last_launches = info.launches;
+    return VRT_OK;
+}
+
+int vrt_trace_rays_host(vrt_ctx* ctx, const vrt_ray* rays_host, vrt_ray_hit* hits_host, size_t count) {
+    if (!ctx) return VRT_E_INVALID;
+    if (count == 0) return VRT_OK;
+    if (!rays_host || !hits_host) return fail(ctx, VRT_E_INVALID, "vrt_trace_rays_host: NULL buffer");
+    VRT_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    void* d = nullptr;
+    VRT_CUDA(ctx, cudaMalloc(&d, count * 64));
+    vrt_ray* d_rays = static_cast<vrt_ray*>(d);
+    vrt_ray_hit* d_hits = reinterpret_cast<vrt_ray_hit*>(static_cast<uint8_t*>(d) + count * 32);
+    int rc = VRT_OK;
+    cudaError_t e = cudaMemcpyAsync(d_rays, rays_host, count * 32, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) rc = vrt_trace_rays(ctx, d_rays, d_hits, count);
+    if (e == cudaSuccess && rc == VRT_OK) e = cudaMemcpyAsync(hits_host, d_hits, count * 32, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && rc == VRT_OK) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (rc != VRT_OK) return rc;
+    if (e != cudaSuccess) return fail(ctx, VRT_E_CUDA, "vrt_trace_rays_host: %s", cudaGetErrorString(e));
     return VRT_OK;
 }
 

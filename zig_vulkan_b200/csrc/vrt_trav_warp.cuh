@@ -74,7 +74,7 @@ VRT_DI int dda_step_sel(V3& side, V3 delta, I3& pos, I3 step, float scale, float
 
 // Voxel-level DDA inside one brick (brick_raytracer.comp:378-471).  Returns the voxel index hit or -1.
 // BD == 4: the brick's 64-bit mask is in `occ`.  Otherwise mask bytes are read from the occupancy buffer (:415).
-template <int BD, bool COUNT>
+template <int BD, int INFO>
 VRT_DI int brick_hit_warp(const TraceParams& P, const Ray& r, bool ignore_test, float grid_t_max, V3 ray_delta, I3 ray_step, float g_scale,
                           V3 brick_position, unsigned long long occ, uint32_t grid_index, unsigned lanes, HitRecord& hit, AxisNormal& n, TraceInfo& ti) {
     const int bd = BD == 4 ? 4 : P.brick_dim;
@@ -91,7 +91,7 @@ VRT_DI int brick_hit_warp(const TraceParams& P, const Ray& r, bool ignore_test, 
     }
     int found = -1;
     while ((uint32_t)pos.x < (uint32_t)bd && (uint32_t)pos.y < (uint32_t)bd && (uint32_t)pos.z < (uint32_t)bd && t_value <= local_t_max) {
-        if (COUNT) ti.voxel_steps++;
+        if (INFO == 2) ti.voxel_steps++;
         const int voxel_index = pos.x + bd * (pos.z + bd * pos.y);  // :412
         bool solid;
         if (BD == 4) {
@@ -158,7 +158,9 @@ VRT_DI void march_step(float& sx, float& sy, float& sz, float dx, float dy, floa
 // GridHit(r, 0.00001, infinity, ...) (:271-376) for the 32 rays of a warp.  Every lane of the warp must call this;
 // `active` says whether the lane has a ray.  need_material: produce hit.index (camera / bounce rays; sun rays only
 // need the boolean).  ignore_test: the ray can ignore voxels (:427).
-template <int BD, bool COUNT>
+// INFO: 0 = hit record only; 1 = also the hit cell / voxel indices in `ti`; 2 = also the shader's step / fetch counters
+// (disables the free-octant shortcut so that the counters equal the shader's).
+template <int BD, int INFO>
 VRT_DI bool grid_hit_warp(const TraceParams& P, const Ray& r, bool active, bool need_material, bool ignore_test, HitRecord& hit, TraceInfo& ti) {
     const V3 g_min = v3(P.grid.min_point_base_t[0], P.grid.min_point_base_t[1], P.grid.min_point_base_t[2]);
     const float g_scale = P.grid.max_point_scale[3];
@@ -202,6 +204,7 @@ VRT_DI bool grid_hit_warp(const TraceParams& P, const Ray& r, bool active, bool 
     const uint8_t* __restrict__ dist = P.dist;
     int last_stride = 0;  // stride of the most recent step (0: none yet -> slab normal)
     bool result = false;
+    constexpr bool COUNT = INFO == 2;
     uint32_t cnt_word = ~0u;  // COUNT: the reference's one-word status cache (:301,:321-326)
     constexpr uint32_t kIdle = 0xffffu;
     enum : int { kMarching = 0, kParked = 1, kDone = 2 };
@@ -270,10 +273,10 @@ VRT_DI bool grid_hit_warp(const TraceParams& P, const Ray& r, bool active, bool 
             const float t_value = t_side * g_scale;                                            // :347,353,361,367
             hit.t = (t_value + grid_t_min) + 0.01f * g_scale;                                  // :332-334
             if (COUNT) ti.bricks_entered++;
-            const int voxel_index = brick_hit_warp<BD, COUNT>(P, r, ignore_test, grid_t_max, ray_delta, ray_step, g_scale, brick_min, occ, grid_index, parked_lanes, hit, n, ti);
+            const int voxel_index = brick_hit_warp<BD, INFO>(P, r, ignore_test, grid_t_max, ray_delta, ray_step, g_scale, brick_min, occ, grid_index, parked_lanes, hit, n, ti);
             if (voxel_index >= 0) {
                 if (need_material && !ignore_test) hit.index = material_index_at(P, grid_index, voxel_index);
-                if (COUNT) ti.grid_index = grid_index, ti.voxel_index = (uint32_t)voxel_index;
+                if (INFO >= 1) ti.grid_index = grid_index, ti.voxel_index = (uint32_t)voxel_index;
                 result = true;
                 mode = kDone;
             } else {  // :345-372, then the next cell is looked up

@@ -78,6 +78,8 @@ AOV_DTYPE = np.dtype(
         ("grid_steps", "<u4"), ("voxel_steps", "<u4"), ("status_fetches", "<u4"),
     ]
 )
+RAY_DTYPE = np.dtype([("origin", "<f4", 3), ("_pad0", "<f4"), ("direction", "<f4", 3), ("_pad1", "<f4")])
+RAY_HIT_DTYPE = np.dtype([("hit", "<u4"), ("grid_index", "<u4"), ("voxel_index", "<u4"), ("material", "<u4"), ("t", "<f4"), ("normal", "<f4", 3)])
 MATERIAL_DTYPE = np.dtype([("type", "<u4"), ("albedo_r", "<f4"), ("albedo_g", "<f4"), ("albedo_b", "<f4"), ("type_data", "<f4")])
 
 
@@ -138,6 +140,8 @@ VRT_SYMBOLS = {
     "vrt_read_framebuffer": (C.c_int, [_P, _P, _SZ]),
     "vrt_trace_to_host": (C.c_int, [_P, C.POINTER(CameraDevice), C.POINTER(SunDevice), _P, _SZ]),
     "vrt_trace_to_host_async": (C.c_int, [_P, C.POINTER(CameraDevice), C.POINTER(SunDevice), _P, _SZ]),
+    "vrt_trace_rays": (C.c_int, [_P, _P, _P, _SZ]),
+    "vrt_trace_rays_host": (C.c_int, [_P, _P, _P, _SZ]),
     "vrt_read_aov": (C.c_int, [_P, _P, _SZ]),
     "vrt_get_counters": (C.c_int, [_P, C.POINTER(Counters)]),
     "vrt_last_trace_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
@@ -601,6 +605,18 @@ class Context:
         """Pipelined frame: returns after enqueueing; `out_ptr` (pinned host memory, width*height*4 bytes) is valid after sync()."""
         self._check(self._l.vrt_trace_to_host_async(self.handle, C.byref(camera), C.byref(sun), C.c_void_p(out_ptr) if out_ptr else None,
                                                     self.width * self.height * 4))
+
+    def trace_rays(self, origins: np.ndarray, directions: np.ndarray) -> np.ndarray:
+        """Explicit-ray mode (vrt_trace_rays_host): n x 3 origins and directions in, n hit records out."""
+        n = len(origins)
+        rays = np.zeros(n, dtype=RAY_DTYPE)
+        rays["origin"], rays["direction"] = origins, directions
+        hits = np.zeros(n, dtype=RAY_HIT_DTYPE)
+        self._check(self._l.vrt_trace_rays_host(self.handle, _ptr(rays), _ptr(hits), n))
+        return hits
+
+    def trace_rays_device(self, rays_ptr: int, hits_ptr: int, count: int):
+        self._check(self._l.vrt_trace_rays(self.handle, C.c_void_p(rays_ptr), C.c_void_p(hits_ptr), count))
 
     def read_aov(self) -> np.ndarray:
         out = np.empty(self.height * self.width, dtype=AOV_DTYPE)
