@@ -269,6 +269,7 @@ struct TraceParams {
     // fused peer-store exchange (multi-GPU): framebuffers of every rank, this rank included
     uint32_t* peer_fb[8];
     uint32_t n_peers;
+    uint32_t one;  // = 1, opaque to the compiler: multiplier of the march's index IMADs (vrt_trav_warp.cuh march_step)
 };
 
 }  // namespace vrt

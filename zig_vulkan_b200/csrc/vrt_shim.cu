@@ -209,6 +209,7 @@ void fill_params(const vrt_ctx* c, const vrt_camera* cam, const vrt_sun* sun, Tr
     P.tile_base = c->tile_base;
     P.vec_store_ok = (cam->image_width % 4 == 0) && ((reinterpret_cast<uintptr_t>(c->d_fb) & 15u) == 0);
     P.n_peers = 0;
+    P.one = 1u;
     if (c->world > 1 && c->exchange_mode == VRT_EXCHANGE_PEER_STORE && c->peers_open) {
         const size_t slot_words = (c->d_fb == c->d_fb_ring1) ? c->fb_bytes / 4 : 0;  // same ring slot on every rank
         for (int r = 0; r < c->world; r++)

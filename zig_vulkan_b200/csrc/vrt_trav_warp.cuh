@@ -134,25 +134,27 @@ VRT_DI uint32_t cell_grid_index(const TraceParams& P, int idx, int log_px, int l
 
 // One brick-level DDA step (:345-372) on the linear cell index: strict '<', tie order x -> z / y -> z, the picked
 // axis' side value gets its delta added (the shader's own sequence of FP32 additions per axis) and the cell index moves
-// by that axis' stride.  Written in PTX so that the step is exactly 4 setp + 1 predicate op + 3 predicated add.f32 +
-// 3 predicated add.s32: take_x = (sx<sy)&(sx<sz); take_y = !(sx<sy)&(sy<sz); take_z = neither.
-VRT_DI void march_step(float& sx, float& sy, float& sz, float dx, float dy, float dz, int stx, int sty, int stz, int& idx) {
+// by that axis' stride.  take_x = (sx<sy)&(sx<sz); take_y = !(sx<sy)&(sy<sz); take_z = neither.
+// Written in PTX for the instruction mix: on sm_100a the ALU pipe (FSETP, PLOP3, IADD3) issues a warp instruction every
+// 2 cycles per scheduler and the FMA pipe (FADD, IMAD) every cycle, and the march is bound by the ALU pipe — so the step
+// is 3 setp (the second and third take the first as their AND input) + 1 predicate op on the ALU pipe, and 3 predicated
+// add.f32 + 3 predicated mad.lo (stride * 1 + idx, `one` is a register so that it stays an IMAD) on the FMA pipe.
+VRT_DI void march_step(float& sx, float& sy, float& sz, float dx, float dy, float dz, int stx, int sty, int stz, int& idx, int one) {
     asm("{\n\t"
-        ".reg .pred pxz, pyz, px, py, pxy;\n\t"
-        "setp.lt.f32 pxz, %0, %2;\n\t"
-        "setp.lt.f32 pyz, %1, %2;\n\t"
-        "setp.lt.and.f32 px, %0, %1, pxz;\n\t"
-        "setp.geu.and.f32 py, %0, %1, pyz;\n\t"
+        ".reg .pred p1, px, py, pxy;\n\t"
+        "setp.lt.f32 p1, %0, %1;\n\t"
+        "setp.lt.and.f32 px, %0, %2, p1;\n\t"
+        "setp.lt.and.f32 py, %1, %2, !p1;\n\t"
         "or.pred pxy, px, py;\n\t"
         "@px add.rn.f32 %0, %0, %4;\n\t"
         "@py add.rn.f32 %1, %1, %5;\n\t"
         "@!pxy add.rn.f32 %2, %2, %6;\n\t"
-        "@px add.s32 %3, %3, %7;\n\t"
-        "@py add.s32 %3, %3, %8;\n\t"
-        "@!pxy add.s32 %3, %3, %9;\n\t"
+        "@px mad.lo.s32 %3, %7, %10, %3;\n\t"
+        "@py mad.lo.s32 %3, %8, %10, %3;\n\t"
+        "@!pxy mad.lo.s32 %3, %9, %10, %3;\n\t"
         "}"
         : "+f"(sx), "+f"(sy), "+f"(sz), "+r"(idx)
-        : "f"(dx), "f"(dy), "f"(dz), "r"(stx), "r"(sty), "r"(stz));
+        : "f"(dx), "f"(dy), "f"(dz), "r"(stx), "r"(sty), "r"(stz), "r"(one));
 }
 
 // GridHit(r, 0.00001, infinity, ...) (:271-376) for the 32 rays of a warp.  Every lane of the warp must call this;
@@ -202,6 +204,7 @@ VRT_DI bool grid_hit_warp(const TraceParams& P, const Ray& r, bool active, bool 
     const int obase = (int)(((ray_step.x < 0 ? 1u : 0u) | (ray_step.y < 0 ? 2u : 0u) | (ray_step.z < 0 ? 4u : 0u)) * (uint32_t)P.dist_plane);
     idx += obase;
     const uint8_t* __restrict__ dist = P.dist;
+    const int one = (int)P.one;
     int last_stride = 0;  // stride of the most recent step (0: none yet -> slab normal)
     bool result = false;
     constexpr bool COUNT = INFO == 2;
@@ -244,7 +247,7 @@ VRT_DI bool grid_hit_warp(const TraceParams& P, const Ray& r, bool active, bool 
             if (k == kIdle) break;
             const bool on = d != kIdle;
             for (uint32_t i = 1; i < k; i++) {  // k-1 steps onto cells known to be empty and inside
-                march_step(sx, sy, sz, fdx, fdy, fdz, fsx, fsy, fsz, idx);
+                march_step(sx, sy, sz, fdx, fdy, fdz, fsx, fsy, fsz, idx, one);
                 if (COUNT && on) {
                     ti.grid_steps++;
                     const uint32_t gi = cell_grid_index(P, idx - obase, log_px, log_pzx);
@@ -254,7 +257,7 @@ VRT_DI bool grid_hit_warp(const TraceParams& P, const Ray& r, bool active, bool 
             // the k-th step lands on a cell that is looked up next round; remember its side value and axis
             if (on) t_side = fminf(fminf(sx, sy), sz);  // = side_dist.<axis> before the increment (the picked side is the minimum)
             const int before = idx;
-            march_step(sx, sy, sz, fdx, fdy, fdz, fsx, fsy, fsz, idx);
+            march_step(sx, sy, sz, fdx, fdy, fdz, fsx, fsy, fsz, idx, one);
             if (on) last_stride = idx - before;
         }
         // ---- phase B: the parked rays test their bricks together (:329-342)
@@ -282,7 +285,7 @@ VRT_DI bool grid_hit_warp(const TraceParams& P, const Ray& r, bool active, bool 
             } else {  // :345-372, then the next cell is looked up
                 t_side = fminf(fminf(sx, sy), sz);
                 const int before = idx;
-                march_step(sx, sy, sz, dx, dy, dz, stx, sty, stz, idx);
+                march_step(sx, sy, sz, dx, dy, dz, stx, sty, stz, idx, one);
                 last_stride = idx - before;
                 fdx = dx, fdy = dy, fdz = dz, fsx = stx, fsy = sty, fsz = stz;  // marching again
                 mode = kMarching;
