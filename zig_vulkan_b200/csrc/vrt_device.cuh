@@ -245,6 +245,7 @@ struct TraceParams {
     const uint8_t* material_indices;    // binding 7
     unsigned long long n_statuses, n_brick_indices, n_occupancy, n_start_indices, n_material_indices;
     uint32_t n_materials;
+    uint32_t materials_basic;      // every uploaded material is lambertian / metal / dielectric (precondition of the simple shading path)
     uint32_t materials_have_none;  // any uploaded material with type == MAT_NONE(3)? (enables the :427 test for type-3 rays)
     int brick_dim;            // spec const 4
     uint32_t brick_bytes;     // spec const 3

@@ -37,7 +37,8 @@ constexpr int kTunedThreads = 256;
 constexpr uint32_t kTileW = 8, kTileH = 4;
 
 // 3 CTAs of 256 threads per SM (80 registers): measured 10 % faster than 2 (102 registers, no spills) and equal to 4 (64, spills).
-template <int BD, bool AOV>
+// SIMPLE: the configuration shade_pixel_warp_simple covers (chosen per launch by launch_trace_tuned).
+template <int BD, bool AOV, bool SIMPLE>
 __global__ void __launch_bounds__(kTunedThreads, 3) trace_warp_kernel(const __grid_constant__ TraceParams P, const uint32_t tiles_x, const uint32_t tiles_total) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t lx = lane & (kTileW - 1u), ly = lane >> 3;
@@ -56,7 +57,7 @@ __global__ void __launch_bounds__(kTunedThreads, 3) trace_warp_kernel(const __gr
         const uint32_t strip = tile / tiles_x;  // this launch's k-th strip of kTileH rows
         const uint32_t py = P.il_world ? (strip * P.il_world + P.il_rank) * kTileH + ly : P.row_begin + strip * kTileH + ly;
         const bool inside = px < width && py < P.row_end;  // :156-159
-        const uint32_t texel = shade_pixel_warp<BD, AOV>(P, px, py, inside, pc);
+        const uint32_t texel = SIMPLE ? shade_pixel_warp_simple<BD>(P, px, py, inside) : shade_pixel_warp<BD, AOV>(P, px, py, inside, pc);
         const uint32_t out_row = P.il_gather ? (P.il_rank * P.il_strips_max + strip) * kTileH + ly : py;
 
         // 128-bit framebuffer stores: lanes with lx in {0,4} gather the 4 texels to their right
@@ -78,10 +79,10 @@ __global__ void __launch_bounds__(kTunedThreads, 3) trace_warp_kernel(const __gr
     if (AOV) flush_counters(P, pc);
 }
 
-template <int BD, bool AOV>
+template <int BD, bool AOV, bool SIMPLE>
 cudaError_t launch_warp_kernel(const TraceParams& P, int num_sms, cudaStream_t stream, LaunchInfo* info) {
     int blocks_per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, trace_warp_kernel<BD, AOV>, kTunedThreads, 0);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, trace_warp_kernel<BD, AOV, SIMPLE>, kTunedThreads, 0);
     if (e != cudaSuccess) return e;
     if (blocks_per_sm < 1) return cudaErrorLaunchOutOfResources;
     const uint32_t rows = P.row_end - P.row_begin;
@@ -94,7 +95,7 @@ cudaError_t launch_warp_kernel(const TraceParams& P, int num_sms, cudaStream_t s
     uint32_t grid = (uint32_t)(num_sms * blocks_per_sm);  // one resident wave: a multiple of the SM count
     const uint32_t needed = (tiles_total + warps_per_block - 1) / warps_per_block;
     if (grid > needed) grid = needed;
-    trace_warp_kernel<BD, AOV><<<grid, kTunedThreads, 0, stream>>>(P, tiles_x, tiles_total);
+    trace_warp_kernel<BD, AOV, SIMPLE><<<grid, kTunedThreads, 0, stream>>>(P, tiles_x, tiles_total);
     if (info) {
         info->launches++;
         info->counter_advance = (unsigned long long)tiles_total + (unsigned long long)grid * warps_per_block;  // every warp overshoots once
@@ -110,8 +111,14 @@ cudaError_t launch_trace_tuned(const TraceParams& P, bool aov, cudaStream_t stre
     if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
     if (sm_count[dev] == 0 && (e = cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
     const int n = sm_count[dev];
-    if (P.brick_dim == 4) return aov ? launch_warp_kernel<4, true>(P, n, stream, info) : launch_warp_kernel<4, false>(P, n, stream, info);
-    return aov ? launch_warp_kernel<0, true>(P, n, stream, info) : launch_warp_kernel<0, false>(P, n, stream, info);
+    // shade_pixel_warp_simple's preconditions (vrt_shade_warp.cuh)
+    const bool simple = !aov && P.cam.max_bounce == 1 && P.cam.samples_per_pixel == 1 && (P.sun.enabled == 0u || P.sun.radius == 0.0f) && P.materials_basic != 0u;
+    if (P.brick_dim == 4) {
+        if (simple) return launch_warp_kernel<4, false, true>(P, n, stream, info);
+        return aov ? launch_warp_kernel<4, true, false>(P, n, stream, info) : launch_warp_kernel<4, false, false>(P, n, stream, info);
+    }
+    if (simple) return launch_warp_kernel<0, false, true>(P, n, stream, info);
+    return aov ? launch_warp_kernel<0, true, false>(P, n, stream, info) : launch_warp_kernel<0, false, false>(P, n, stream, info);
 }
 
 // ----------------------------------------------------------------------------------------------------

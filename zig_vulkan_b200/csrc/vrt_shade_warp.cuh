@@ -137,4 +137,50 @@ VRT_DI uint32_t shade_pixel_warp(const TraceParams& P, uint32_t px, uint32_t py,
     return pack_rgba8(color);
 }
 
+// The common configuration — device max_bounce == 1, one sample per pixel, sun radius 0 (or sun off), every material of
+// type lambertian / metal / dielectric — needs none of the scatter / RNG code: sample 0 has zero pixel noise (hash12(0,0) = 0,
+// x + 0 = x, :167-170), the scatter result is dead at the last allowed bounce (:218) and the sun jitter is exactly 0.  Per
+// lane the operations below are those of shade_pixel_warp; the camera ray and the sun ray go through ONE copy of the
+// traversal (a two-trip loop), which keeps the kernel small enough for the instruction cache (17 KB instead of 58 KB).
+template <int BD>
+VRT_DI uint32_t shade_pixel_warp_simple(const TraceParams& P, uint32_t px, uint32_t py, bool inside) {
+    const bool sun_enabled = P.sun.enabled > 0;
+    const float u = (float)px / (float)(P.cam.image_width - 1u);   // :168 with noise 0
+    const float v = (float)py / (float)(P.cam.image_height - 1u);  // :170
+    Ray ray = CameraGetRay(P, u, v);
+    const float primary_dir_y = ray.direction.y;
+    V3 attenuation = v3s(0.0f);
+    V3 color = v3s(0.0f);
+    bool on = inside, primary_hit = false;
+    const int trips = sun_enabled ? 2 : 1;
+#pragma unroll 1
+    for (int trip = 0; trip < trips; trip++) {
+        HitRecord hit;
+        hit.point = v3s(0.0f), hit.normal = v3s(0.0f), hit.t = 0.0f, hit.index = 0u;
+        TraceInfo ti;
+        reset(ti);
+        const bool got = grid_hit_warp<BD, 0>(P, ray, on, trip == 0, false, hit, ti);  // :218 / :247
+        if (trip == 0) {
+            primary_hit = on && got;
+            on = primary_hit;
+            if (primary_hit) {
+                const vrt_material material = load_material(P, hit.index);  // :223
+                attenuation = v3(material.albedo_r, material.albedo_g, material.albedo_b);
+                if (sun_enabled) ray = CreateRay(hit.point, (ld3(P.sun.position) + v3s(0.0f)) - hit.point);  // :241-244, jitter = (+0,+0,+0) at radius 0
+                else color = color + attenuation;                                              // :251
+            }
+        } else if (on && !got) {
+            color = color + attenuation * ld3(P.sun.color);  // :248
+        }
+    }
+    if (!primary_hit) {  // :260-262
+        Ray pr = ray;
+        pr.direction.y = primary_dir_y;
+        color = color + BackgroundColor(pr) * (sun_enabled ? ld3(P.sun.color) : v3s(1.0f));
+    }
+    color = color / (color + v3s(1.0f));                          // :264
+    color = v3(sqrtf(color.x), sqrtf(color.y), sqrtf(color.z));  // :176, spp == 1
+    return pack_rgba8(color);
+}
+
 }  // namespace vrt

@@ -182,9 +182,11 @@ void fill_params(const vrt_ctx* c, const vrt_camera* cam, const vrt_sun* sun, Tr
     P.n_statuses = c->n_statuses, P.n_brick_indices = c->n_brick_indices, P.n_occupancy = c->n_occupancy;
     P.n_start_indices = c->n_start_indices, P.n_material_indices = c->n_material_indices;
     P.n_materials = (uint32_t)c->n_materials;
-    P.materials_have_none = 0;
-    for (size_t i = 0; i < c->n_materials; i++)
+    P.materials_have_none = 0, P.materials_basic = 1;
+    for (size_t i = 0; i < c->n_materials; i++) {
         if (c->h_materials[i].type == VRT_MAT_NONE) P.materials_have_none = 1;
+        if (c->h_materials[i].type > VRT_MAT_DIELECTRIC) P.materials_basic = 0;
+    }
     P.brick_dim = (int)c->cfg.brick_dim;
     P.brick_bytes = c->cfg.brick_dim * c->cfg.brick_dim * c->cfg.brick_dim / 8;
     P.brick_voxel_scale = 1.0f / (float)c->cfg.brick_dim;  // Pipeline.zig:313
