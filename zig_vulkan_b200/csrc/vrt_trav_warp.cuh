@@ -72,6 +72,90 @@ VRT_DI int dda_step_sel(V3& side, V3 delta, I3& pos, I3 step, float scale, float
     return take_x ? 0 : (take_y ? 1 : 2);
 }
 
+// One brick-level DDA step (:345-372) on the linear cell index: strict '<', tie order x -> z / y -> z, the picked
+// axis' side value gets its delta added (the shader's own sequence of FP32 additions per axis) and the cell index moves
+// by that axis' stride.  take_x = (sx<sy)&(sx<sz); take_y = !(sx<sy)&(sy<sz); take_z = neither.
+// Written in PTX for the instruction mix: on sm_100a the ALU pipe (FSETP, PLOP3, IADD3) issues a warp instruction every
+// 2 cycles per scheduler and the FMA pipe (FADD, IMAD) every cycle, and the march is bound by the ALU pipe — so the step
+// is 3 setp (the second and third take the first as their AND input) + 1 predicate op on the ALU pipe, and 3 predicated
+// add.f32 + 3 predicated mad.lo (stride * 1 + idx, `one` is a register so that it stays an IMAD) on the FMA pipe.
+VRT_DI void march_step(float& sx, float& sy, float& sz, float dx, float dy, float dz, int stx, int sty, int stz, int& idx, int one) {
+    asm("{\n\t"
+        ".reg .pred p1, px, py, pxy;\n\t"
+        "setp.lt.f32 p1, %0, %1;\n\t"
+        "setp.lt.and.f32 px, %0, %2, p1;\n\t"
+        "setp.lt.and.f32 py, %1, %2, !p1;\n\t"
+        "or.pred pxy, px, py;\n\t"
+        "@px add.rn.f32 %0, %0, %4;\n\t"
+        "@py add.rn.f32 %1, %1, %5;\n\t"
+        "@!pxy add.rn.f32 %2, %2, %6;\n\t"
+        "@px mad.lo.s32 %3, %7, %10, %3;\n\t"
+        "@py mad.lo.s32 %3, %8, %10, %3;\n\t"
+        "@!pxy mad.lo.s32 %3, %9, %10, %3;\n\t"
+        "}"
+        : "+f"(sx), "+f"(sy), "+f"(sz), "+r"(idx)
+        : "f"(dx), "f"(dy), "f"(dz), "r"(stx), "r"(sty), "r"(stz), "r"(one));
+}
+
+// Voxel-level DDA inside one 4^3 brick (brick_raytracer.comp:378-471) with the whole state in registers: the brick's 64-bit
+// mask, and ONE integer that carries both the voxel index and the bounds test —
+//   bits 0-11: (x+4) | (z+4) << 4 | (y+4) << 8   (a coordinate is inside [0,4) iff bit 2 of its field is set: 3 = -1 and 8 = 4
+//              are the only values a single step can leave the brick with, and neither carries into the next field),
+//   bits 12- : voxel_index = x + 4 * (z + 4 * y) (:412), moved by the same predicated add as the fields.
+// The step is march_step (the shader's ladder and additions, :440-467); the axis of the last step — the hit normal — is
+// recovered after the loop from the difference of the last two indices.  Returns the voxel index hit or -1.
+template <int INFO>
+VRT_DI int brick_hit_warp4(const TraceParams& P, const Ray& r, bool ignore_test, float grid_t_max, V3 ray_delta, I3 ray_step, float g_scale,
+                           V3 brick_position, unsigned long long occ, uint32_t grid_index, unsigned lanes, HitRecord& hit, AxisNormal& n, TraceInfo& ti,
+                           int one) {
+    const float voxel_scale = g_scale * P.brick_voxel_scale;                                                  // :389
+    const V3 fposition = div_scale(RayAt(r, hit.t) - brick_position, voxel_scale, P.inv_voxel_scale, P.voxel_scale_pow2 != 0u);  // :393
+    const V3 side_dist = init_side_dist(fposition, ray_step, ray_delta);                                      // :394-395
+    float sx = side_dist.x, sy = side_dist.y, sz = side_dist.z;
+    const int px = (int)floorf(fposition.x), py = (int)floorf(fposition.y), pz = (int)floorf(fposition.z);    // :403
+    const float local_t_max = grid_t_max - hit.t;                                                            // :405
+    float t_value = 0.0f;
+    constexpr int kInside = 0x444;
+    // a start position outside the brick (FP error at the brick face) never enters the loop (:407-410): clear the guard bits
+    const bool start_inside = (uint32_t)px < 4u && (uint32_t)py < 4u && (uint32_t)pz < 4u;
+    int state = start_inside ? ((px + 4) | ((pz + 4) << 4) | ((py + 4) << 8) | ((px + 4 * (pz + 4 * py)) << 12)) : 0;
+    const int stx = ray_step.x * (1 + (1 << 12)), stz = ray_step.z * ((1 << 4) + (4 << 12)), sty = ray_step.y * ((1 << 8) + (16 << 12));
+    int prev = state;
+    int found = -1;
+    while ((state & kInside) == kInside && t_value <= local_t_max) {  // :407-411
+        if (INFO == 2) ti.voxel_steps++;
+        const int voxel_index = state >> 12;  // :412
+        if ((occ >> voxel_index) & 1ull) {    // :415-417
+            bool ignore_brick = false;
+            if (ignore_test) {
+                hit.index = material_index_at(P, grid_index, voxel_index);  // :425
+                const vrt_material m = load_material(P, hit.index);
+                ignore_brick = (m.type == r.ignore_type_material) && (r.internal_reflection == m.type_data);  // :427
+            }
+            if (!ignore_brick) {
+                found = voxel_index;
+                break;
+            }
+        }
+        t_value = fminf(fminf(sx, sy), sz) * voxel_scale;  // the side value of the axis about to step is the minimum (:443,449,457,463)
+        prev = state;
+        march_step(sx, sy, sz, ray_delta.x, ray_delta.y, ray_delta.z, stx, sty, stz, state, one);  // :440-467
+    }
+    __syncwarp(lanes);  // the rays leave the loop at different trips: finish hits (and, in the caller, misses) together
+    if (found >= 0) {
+        const int moved = (state >> 12) - (prev >> 12);  // 0: hit in the entry voxel, the normal stays the brick-level one
+        if (moved != 0) {
+            const int a = moved < 0 ? -moved : moved;
+            n = step_normal(a == 1 ? 0 : (a == 4 ? 2 : 1), ray_step);
+        }
+        const float t_offset = voxel_scale * 0.05f;           // :431
+        hit.t += t_value - t_offset;                          // :432
+        hit.normal = to_v3(n);
+        hit.point = RayAt(r, hit.t) + hit.normal * t_offset;  // :433
+    }
+    return found;
+}
+
 // Voxel-level DDA inside one brick (brick_raytracer.comp:378-471).  Returns the voxel index hit or -1.
 // BD == 4: the brick's 64-bit mask is in `occ`.  Otherwise mask bytes are read from the occupancy buffer (:415).
 template <int BD, int INFO>
@@ -130,31 +214,6 @@ VRT_DI int brick_hit_warp(const TraceParams& P, const Ray& r, bool ignore_test, 
 VRT_DI uint32_t cell_grid_index(const TraceParams& P, int idx, int log_px, int log_pzx) {
     const int x = (idx & ((1 << log_px) - 1)) - 1, z = ((idx >> log_px) & ((1 << (log_pzx - log_px)) - 1)) - 1, y = (idx >> log_pzx) - 1;
     return (uint32_t)(x + (int)P.grid.dim_x * (z + (int)P.grid.dim_z * y));
-}
-
-// One brick-level DDA step (:345-372) on the linear cell index: strict '<', tie order x -> z / y -> z, the picked
-// axis' side value gets its delta added (the shader's own sequence of FP32 additions per axis) and the cell index moves
-// by that axis' stride.  take_x = (sx<sy)&(sx<sz); take_y = !(sx<sy)&(sy<sz); take_z = neither.
-// Written in PTX for the instruction mix: on sm_100a the ALU pipe (FSETP, PLOP3, IADD3) issues a warp instruction every
-// 2 cycles per scheduler and the FMA pipe (FADD, IMAD) every cycle, and the march is bound by the ALU pipe — so the step
-// is 3 setp (the second and third take the first as their AND input) + 1 predicate op on the ALU pipe, and 3 predicated
-// add.f32 + 3 predicated mad.lo (stride * 1 + idx, `one` is a register so that it stays an IMAD) on the FMA pipe.
-VRT_DI void march_step(float& sx, float& sy, float& sz, float dx, float dy, float dz, int stx, int sty, int stz, int& idx, int one) {
-    asm("{\n\t"
-        ".reg .pred p1, px, py, pxy;\n\t"
-        "setp.lt.f32 p1, %0, %1;\n\t"
-        "setp.lt.and.f32 px, %0, %2, p1;\n\t"
-        "setp.lt.and.f32 py, %1, %2, !p1;\n\t"
-        "or.pred pxy, px, py;\n\t"
-        "@px add.rn.f32 %0, %0, %4;\n\t"
-        "@py add.rn.f32 %1, %1, %5;\n\t"
-        "@!pxy add.rn.f32 %2, %2, %6;\n\t"
-        "@px mad.lo.s32 %3, %7, %10, %3;\n\t"
-        "@py mad.lo.s32 %3, %8, %10, %3;\n\t"
-        "@!pxy mad.lo.s32 %3, %9, %10, %3;\n\t"
-        "}"
-        : "+f"(sx), "+f"(sy), "+f"(sz), "+r"(idx)
-        : "f"(dx), "f"(dy), "f"(dz), "r"(stx), "r"(sty), "r"(stz), "r"(one));
 }
 
 // GridHit(r, 0.00001, infinity, ...) (:271-376) for the 32 rays of a warp.  Every lane of the warp must call this;
@@ -276,7 +335,8 @@ VRT_DI bool grid_hit_warp(const TraceParams& P, const Ray& r, bool active, bool 
             const float t_value = t_side * g_scale;                                            // :347,353,361,367
             hit.t = (t_value + grid_t_min) + 0.01f * g_scale;                                  // :332-334
             if (COUNT) ti.bricks_entered++;
-            const int voxel_index = brick_hit_warp<BD, INFO>(P, r, ignore_test, grid_t_max, ray_delta, ray_step, g_scale, brick_min, occ, grid_index, parked_lanes, hit, n, ti);
+            const int voxel_index = BD == 4 ? brick_hit_warp4<INFO>(P, r, ignore_test, grid_t_max, ray_delta, ray_step, g_scale, brick_min, occ, grid_index, parked_lanes, hit, n, ti, one)
+                                             : brick_hit_warp<BD, INFO>(P, r, ignore_test, grid_t_max, ray_delta, ray_step, g_scale, brick_min, occ, grid_index, parked_lanes, hit, n, ti);
             if (voxel_index >= 0) {
                 if (need_material && !ignore_test) hit.index = material_index_at(P, grid_index, voxel_index);
                 if (INFO >= 1) ti.grid_index = grid_index, ti.voxel_index = (uint32_t)voxel_index;
