@@ -242,6 +242,31 @@ int vrt_last_trace_ms(vrt_ctx* ctx, float* out_ms);
 int vrt_last_trace_launches(vrt_ctx* ctx, uint32_t* out);
 
 /* ---------------------------------------------------------------------------------------------------
+ * Post-process: the reference's present pass (assets/shaders/image.frag:31-79, "sirBirdDenoise"), the step right after
+ * the compute dispatch in Pipeline.draw (Pipeline.zig:441-540).  Replaces GraphicsPipeline's full-screen draw: reads the
+ * traced RGBA8 image through a linear / repeat sampler (Pipeline.zig:193-212) and writes one denoised texel per pixel of
+ * an out_width x out_height target (the swapchain extent; it may differ from the trace resolution).
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct vrt_denoise_params { /* GraphicsPipeline.PushConstant (GraphicsPipeline.zig:27-32), 16 bytes */
+    int32_t samples;                /* default 20  (Config, GraphicsPipeline.zig:34-39); 0 <= samples <= 255 */
+    float distribution_bias;        /* default 0.6 */
+    float pixel_multiplier;         /* default 1.5 */
+    float inverse_hue_tolerance;    /* default 20  */
+} vrt_denoise_params;
+
+#define VRT_DENOISE_BGRA 1u /* store B,G,R,A bytes (the reference's B8G8R8A8_UNORM swapchain, swapchain.zig:235) instead of R,G,B,A */
+
+/* Enqueue the pass on the ctx stream, after whatever vrt_trace put there: input = the framebuffer currently traced into,
+ * output = a ctx-owned out_width*out_height*4-byte device image (re-allocated when the size changes). */
+int vrt_denoise(vrt_ctx* ctx, const vrt_denoise_params* params, uint32_t out_width, uint32_t out_height, uint32_t flags);
+/* Blocking read-back of the last vrt_denoise output (bytes = out_width*out_height*4). */
+int vrt_read_denoised(vrt_ctx* ctx, uint8_t* host, size_t bytes);
+/* Device address of the last vrt_denoise output. */
+int vrt_denoised_device_ptr(vrt_ctx* ctx, void** out_device_ptr);
+/* Milliseconds the device spent in the last vrt_denoise. */
+int vrt_last_denoise_ms(vrt_ctx* ctx, float* out_ms);
+
+/* ---------------------------------------------------------------------------------------------------
  * Interop (all optional)
  * ------------------------------------------------------------------------------------------------- */
 

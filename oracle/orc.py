@@ -81,6 +81,10 @@ def lib() -> C.CDLL:
         l.orc_sinf.argtypes = [C.c_float]
         l.orc_hash12.restype = C.c_float
         l.orc_hash12.argtypes = [C.c_float, C.c_float]
+        l.orc_denoise.restype = C.c_int
+        l.orc_denoise.argtypes = [P, C.c_uint32, C.c_uint32, P, C.c_uint32, C.c_uint32, C.c_uint32, P, C.c_int]
+        l.orc_pow.restype = C.c_float
+        l.orc_pow.argtypes = [C.c_float, C.c_float]
         _lib = l
     return _lib
 
@@ -187,6 +191,25 @@ class OracleScene:
         d = (C.c_float * 3)(*[float(v) for v in direction])
         rc = lib().orc_grid_hit(C.byref(self.c), C.byref(o), C.byref(d), _ptr(out))
         return bool(rc), out[0]
+
+
+def denoise(image: np.ndarray, params=(20, 0.6, 1.5, 20.0), out_width=None, out_height=None, flags=0, threads=0) -> np.ndarray:
+    """image.frag:31-79 over an (H, W, 4) uint8 image; params = (samples, distribution_bias, pixel_multiplier,
+    inverse_hue_tolerance) or any ctypes struct of that layout.  Returns the (out_height, out_width, 4) uint8 result."""
+    image = np.ascontiguousarray(image, dtype=np.uint8)
+    h, w = image.shape[:2]
+    ow, oh = out_width or w, out_height or h
+    if isinstance(params, C.Structure):
+        pbuf = params
+    else:
+        class _P(C.Structure):
+            _fields_ = [("samples", C.c_int32), ("distribution_bias", C.c_float), ("pixel_multiplier", C.c_float), ("inverse_hue_tolerance", C.c_float)]
+        pbuf = _P(int(params[0]), float(params[1]), float(params[2]), float(params[3]))
+    out = np.empty((oh, ow, 4), dtype=np.uint8)
+    rc = lib().orc_denoise(_ptr(image), w, h, C.cast(C.pointer(pbuf), C.c_void_p), ow, oh, flags, _ptr(out), threads)
+    if rc != 0:
+        raise ValueError("orc_denoise rejected its arguments")
+    return out
 
 
 def algorithmic_bytes(counters: dict, n_pixels: int, brick_bytes: int) -> int:

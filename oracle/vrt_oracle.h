@@ -71,6 +71,12 @@ float orc_sinf(float x);
 /* rand.comp:22-26 */
 float orc_hash12(float px, float py);
 
+/* ---- post-process pass: restates assets/shaders/image.frag:31-79 (vrt_oracle_denoise.cpp) ---- */
+int orc_denoise(const uint8_t* rgba8_in, uint32_t in_width, uint32_t in_height, const vrt_denoise_params* params, uint32_t out_width,
+                uint32_t out_height, uint32_t flags /* VRT_DENOISE_* */, uint8_t* out, int threads);
+/* The pow() both sides use for that pass (after the shader's max(a, 0) macro); exposed for tests. */
+float orc_pow(float a, float b);
+
 #ifdef __cplusplus
 }
 #endif

@@ -45,6 +45,14 @@ def main():
         _, _, _, img, aov, cnt = render_case(case)
         np.savez_compressed(os.path.join(out_dir, name + ".npz"), rgba=img, aov=aov, counters=np.array([cnt[k] for k in orc.COUNTER_NAMES], dtype=np.uint64))
         print(name, cnt)
+    make_denoise_golden(out_dir)
+
+
+def make_denoise_golden(out_dir):
+    """The present pass (image.frag) over the traced c1 frame: same size RGBA, and a 1.5x BGRA target."""
+    _, _, _, img, _, _ = render_case(CASES["c1_64_256x256"])
+    np.savez_compressed(os.path.join(out_dir, "denoise_c1_64_256x256.npz"), traced=img, denoised=orc.denoise(img),
+                        denoised_384x216_bgra=orc.denoise(img, out_width=384, out_height=216, flags=1))
 
 
 if __name__ == "__main__":

@@ -1,0 +1,155 @@
+// vrt_denoise.cu — the reference's present pass (assets/shaders/image.frag:31-79, "sirBirdDenoise") as an sm_100a kernel.
+//
+// One thread per output texel.  What the fragment shader recomputes for every fragment but depends only on the push
+// constants — the golden-angle spiral offsets (:49-53) and the radial part of the sample weight (:52) — is computed once per
+// CTA into shared memory (same operations, same order, so the values are the ones every fragment would have got), next to a
+// 256-entry table of the UNORM decode byte / 255.0f.  The per-sample work left is the bilinear fetch (4 texels of the RGBA8
+// image, which stays L2 / L1 resident: 8 MB at 1080p), one sqrt + one divide for normalize / length, and two pow.
+//
+// Arithmetic discipline = the oracle's (oracle/vrt_oracle_denoise.cpp header): FP32, no contraction (--fmad=false) except
+// the explicit fmaf of det_log2f / det_exp2f, IEEE sqrt and divide, FP32 bilinear weights.  Bound: FP32 / SFU issue, not HBM
+// (algorithmic traffic is 4 B read + 4 B written per pixel).
+#include <cstdint>
+
+#include "../../include/vrt.h"
+#include "vrt_kernels.cuh"
+
+namespace vrt {
+
+namespace {
+
+constexpr int kDnBlockX = 32, kDnBlockY = 8;
+constexpr int kDnMaxSamples = 255;
+
+__device__ __forceinline__ float dn_max(float a, float b) { return a < b ? b : a; }
+
+// log2 of a finite a >= FLT_MIN: a = 2^e * m, m in [sqrt(1/2), sqrt(2)); ln m = 2 atanh((m-1)/(m+1))
+__device__ __forceinline__ float det_log2f(float a) {
+    const int ia = __float_as_int(a);
+    const int e = (ia - 0x3f3504f3) >> 23;
+    const float m = __int_as_float(ia - e * (1 << 23));
+    const float f = m - 1.0f;
+    const float s = f / (2.0f + f);
+    const float z = s * s;
+    float p = fmaf(z, 0.22222222f, 0.2857143f);
+    p = fmaf(p, z, 0.4f);
+    p = fmaf(p, z, 0.6666667f);
+    const float ln_m = fmaf(s * z, p, s + s);
+    return fmaf(ln_m, 1.442695f, (float)e);
+}
+
+// 2^y, y clamped to [-126, 126]; NaN stays NaN
+__device__ __forceinline__ float det_exp2f(float y) {
+    if (y != y) return y;
+    y = y < -126.0f ? -126.0f : (y > 126.0f ? 126.0f : y);
+    const float n = floorf(y + 0.5f);
+    const float r = y - n;
+    float p = fmaf(0.0001540353f, r, 0.0013333558f);
+    p = fmaf(p, r, 0.009618129f);
+    p = fmaf(p, r, 0.05550411f);
+    p = fmaf(p, r, 0.2402265f);
+    p = fmaf(p, r, 0.6931472f);
+    p = fmaf(p, r, 1.0f);
+    return p * __int_as_float(((int)n + 127) << 23);
+}
+
+// image.frag:29  #define pow(a,b) pow(max(a,0.),b)
+__device__ __forceinline__ float gpow(float a, float b) {
+    a = dn_max(a, 0.0f);
+    if (a != a) return a;
+    if (a < 1.17549435e-38f) return 0.0f;
+    if (a > 3.4028234e38f) return a;
+    return det_exp2f(b * det_log2f(a));
+}
+
+struct Rgb {
+    float x, y, z;
+};
+
+// texture(imageSampler, uv).rgb: linear filter, repeat addressing (Pipeline.zig:193-212); `unorm` = byte / 255.0f table
+__device__ __forceinline__ Rgb sample_linear_repeat(const uint32_t* __restrict__ img, int w, int h, float fw, float fh, const float* unorm, float u, float v) {
+    const float x = u * fw - 0.5f, y = v * fh - 0.5f;
+    const float fx = floorf(x), fy = floorf(y);
+    const float a = x - fx, b = y - fy;
+    int x0 = (int)fx % w, y0 = (int)fy % h;
+    x0 = x0 < 0 ? x0 + w : x0, y0 = y0 < 0 ? y0 + h : y0;
+    const int x1 = x0 + 1 == w ? 0 : x0 + 1, y1 = y0 + 1 == h ? 0 : y0 + 1;
+    const uint32_t p00 = __ldg(img + (size_t)y0 * w + x0), p10 = __ldg(img + (size_t)y0 * w + x1);
+    const uint32_t p01 = __ldg(img + (size_t)y1 * w + x0), p11 = __ldg(img + (size_t)y1 * w + x1);
+    const float w00 = (1.0f - a) * (1.0f - b), w10 = a * (1.0f - b), w01 = (1.0f - a) * b, w11 = a * b;
+    Rgb c;
+    c.x = ((w00 * unorm[p00 & 255u] + w10 * unorm[p10 & 255u]) + w01 * unorm[p01 & 255u]) + w11 * unorm[p11 & 255u];
+    c.y = ((w00 * unorm[(p00 >> 8) & 255u] + w10 * unorm[(p10 >> 8) & 255u]) + w01 * unorm[(p01 >> 8) & 255u]) + w11 * unorm[(p11 >> 8) & 255u];
+    c.z = ((w00 * unorm[(p00 >> 16) & 255u] + w10 * unorm[(p10 >> 16) & 255u]) + w01 * unorm[(p01 >> 16) & 255u]) + w11 * unorm[(p11 >> 16) & 255u];
+    return c;
+}
+
+__device__ __forceinline__ uint32_t dn_unorm8(float c) {
+    if (!(c == c)) return 0u;
+    c = c < 0.0f ? 0.0f : (c > 1.0f ? 1.0f : c);
+    return (uint32_t)(uint8_t)(c * 255.0f + 0.5f);
+}
+
+constexpr float kCosGolden = -0.7373688f, kSinGolden = 0.6754904f;  // cos / sin(2.3999632), image.frag:25,29
+
+__global__ void __launch_bounds__(kDnBlockX* kDnBlockY) denoise_kernel(const uint32_t* __restrict__ img, int w, int h, const vrt_denoise_params pc, uint32_t* __restrict__ out,
+                                                                        uint32_t out_w, uint32_t out_h, uint32_t bgra) {
+    __shared__ float s_unorm[256];
+    __shared__ float s_off_x[kDnMaxSamples + 1], s_off_y[kDnMaxSamples + 1], s_radial[kDnMaxSamples + 1];
+    const int tid = threadIdx.y * kDnBlockX + threadIdx.x;
+    s_unorm[tid] = (float)tid / 255.0f;  // 256 threads
+    if (tid <= pc.samples) {
+        const float sample_radius = sqrtf((float)pc.samples);                       // :35
+        const float sample_true_radius = 0.5f / (sample_radius * sample_radius);    // :36
+        float rot_x = 0.0f, rot_y = 1.0f;                                            // :45
+        for (int i = 0; i <= tid; i++) {                                             // :49, applied tid + 1 times
+            const float nx = rot_x * kCosGolden + rot_y * kSinGolden;
+            const float ny = rot_x * (-kSinGolden) + rot_y * kCosGolden;
+            rot_x = nx, rot_y = ny;
+        }
+        const float sq = sqrtf((float)tid);
+        const float off_x = ((pc.pixel_multiplier * rot_x) * sq) * 0.5f, off_y = ((pc.pixel_multiplier * rot_y) * sq) * 0.5f;  // :51
+        s_radial[tid] = 1.0f - sample_true_radius * gpow(off_x * off_x + off_y * off_y, pc.distribution_bias);                // :52
+        s_off_x[tid] = off_x * (1.0f / (float)w), s_off_y[tid] = off_y * (1.0f / (float)h);                                   // :37,:53
+    }
+    __syncthreads();
+
+    const uint32_t ox = blockIdx.x * kDnBlockX + threadIdx.x, oy = blockIdx.y * kDnBlockY + threadIdx.y;
+    if (ox >= out_w || oy >= out_h) return;
+    const float fw = (float)w, fh = (float)h;
+    const float uvx = ((float)ox + 0.5f) / (float)out_w, uvy = ((float)oy + 0.5f) / (float)out_h;
+
+    const Rgb center = sample_linear_repeat(img, w, h, fw, fh, s_unorm, uvx, uvy);  // :38
+    const float center_sat = sqrtf((center.x * center.x + center.y * center.y) + center.z * center.z);  // :40
+    const float center_inv = 1.0f / center_sat;                                                         // :39 normalize
+    const float cnx = center.x * center_inv, cny = center.y * center_inv, cnz = center.z * center_inv;
+    const float abs_center_sat = fabsf(center_sat);  // length(float), :63
+    float dx = 0.0f, dy = 0.0f, dz = 0.0f, influence_sum = 0.0f;
+    const int samples = pc.samples;
+    for (int k = 0; k <= samples; k++) {  // :47
+        const Rgb c = sample_linear_repeat(img, w, h, fw, fh, s_unorm, uvx + s_off_x[k], uvy + s_off_y[k]);  // :55
+        float influence = s_radial[k];
+        influence *= influence * influence;  // :57
+        const float len = sqrtf((c.x * c.x + c.y * c.y) + c.z * c.z);
+        const float inv = 1.0f / len;
+        const float d = (cnx * (c.x * inv) + cny * (c.y * inv)) + cnz * (c.z * inv);
+        influence *= gpow(0.5f + 0.5f * d, pc.inverse_hue_tolerance) * gpow(1.0f - fabsf(len - abs_center_sat), 8.0f);  // :61-64
+        influence_sum += influence;                                                                                     // :66
+        dx += c.x * influence, dy += c.y * influence, dz += c.z * influence;                                            // :67
+    }
+    const uint32_t r = dn_unorm8(dx / influence_sum), g = dn_unorm8(dy / influence_sum), b = dn_unorm8(dz / influence_sum);  // :70, :77
+    out[(size_t)oy * out_w + ox] = bgra ? (b | (g << 8) | (r << 16) | 0xff000000u) : (r | (g << 8) | (b << 16) | 0xff000000u);
+}
+
+}  // namespace
+
+cudaError_t launch_denoise(const uint32_t* image, uint32_t width, uint32_t height, const vrt_denoise_params& params, uint32_t* out, uint32_t out_width,
+                           uint32_t out_height, bool bgra, cudaStream_t stream, LaunchInfo* info) {
+    const dim3 block(kDnBlockX, kDnBlockY);
+    const dim3 grid((out_width + kDnBlockX - 1) / kDnBlockX, (out_height + kDnBlockY - 1) / kDnBlockY);
+    denoise_kernel<<<grid, block, 0, stream>>>(image, (int)width, (int)height, params, out, out_width, out_height, bgra ? 1u : 0u);
+    if (info) info->launches++;
+    return cudaGetLastError();
+}
+
+}  // namespace vrt

@@ -106,6 +106,12 @@ struct vrt_ctx {
     cudaEvent_t barrier_after_copy = nullptr;  // peer-store: the frame barrier must not pass before this copy has finished
     uint64_t async_frames = 0;
 
+    // post-process output (vrt_denoise)
+    uint32_t* d_denoised = nullptr;
+    uint32_t dn_width = 0, dn_height = 0;
+    cudaEvent_t ev_dn_begin = nullptr, ev_dn_end = nullptr;
+    bool dn_timing_valid = false;
+
     // debug
     vrt_aov* d_aov = nullptr;
     unsigned long long* d_counters = nullptr;
@@ -364,7 +370,9 @@ void vrt_deinit(vrt_ctx* ctx) {
     cudaFree(ctx->d_materials), cudaFree(ctx->d_statuses), cudaFree(ctx->d_brick_indices), cudaFree(ctx->d_occupancy);
     cudaFree(ctx->d_start_indices), cudaFree(ctx->d_material_indices), cudaFree(ctx->d_fb_own), cudaFree(ctx->d_aov);
     cudaFree(ctx->d_counters), cudaFree(ctx->d_occ_dense), cudaFree(ctx->d_dist), cudaFree(ctx->d_dist_tmp);
-    cudaFree(ctx->d_tile_counter), cudaFree(ctx->d_gather), cudaFree(ctx->d_barrier);
+    cudaFree(ctx->d_tile_counter), cudaFree(ctx->d_gather), cudaFree(ctx->d_barrier), cudaFree(ctx->d_denoised);
+    if (ctx->ev_dn_begin) cudaEventDestroy(ctx->ev_dn_begin);
+    if (ctx->ev_dn_end) cudaEventDestroy(ctx->ev_dn_end);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     for (int i = 0; i < 2; i++) {
         if (ctx->ev_traced[i]) cudaEventDestroy(ctx->ev_traced[i]);
@@ -551,6 +559,65 @@ int vrt_trace_to_host(vrt_ctx* ctx, const vrt_camera* camera, const vrt_sun* sun
     const size_t from = whole ? 0 : off;
     VRT_CUDA(ctx, cudaMemcpyAsync(rgba8_host + from, reinterpret_cast<const uint8_t*>(ctx->d_fb) + from, n, cudaMemcpyDeviceToHost, ctx->stream));
     VRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VRT_OK;
+}
+
+int vrt_denoise(vrt_ctx* ctx, const vrt_denoise_params* params, uint32_t out_width, uint32_t out_height, uint32_t flags) {
+    if (!ctx) return VRT_E_INVALID;
+    if (!params) return fail(ctx, VRT_E_INVALID, "vrt_denoise: params is NULL");
+    if (params->samples < 0 || params->samples > 255) return fail(ctx, VRT_E_INVALID, "vrt_denoise: samples %d outside [0, 255]", params->samples);
+    if (out_width == 0 || out_height == 0) return fail(ctx, VRT_E_INVALID, "vrt_denoise: empty output image");
+    if (flags & ~VRT_DENOISE_BGRA) return fail(ctx, VRT_E_INVALID, "vrt_denoise: unknown flags 0x%x", flags);
+    VRT_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    if (out_width != ctx->dn_width || out_height != ctx->dn_height) {
+        if (ctx->d_denoised) {
+            VRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            VRT_CUDA(ctx, cudaFree(ctx->d_denoised));
+            ctx->d_denoised = nullptr, ctx->dn_width = ctx->dn_height = 0;
+        }
+        if (cudaMalloc(&ctx->d_denoised, (size_t)out_width * out_height * 4) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(ctx, VRT_E_OOM, "vrt_denoise: cannot allocate a %ux%u output image", out_width, out_height);
+        }
+        ctx->dn_width = out_width, ctx->dn_height = out_height;
+    }
+    if (!ctx->ev_dn_begin) {
+        VRT_CUDA(ctx, cudaEventCreate(&ctx->ev_dn_begin));
+        VRT_CUDA(ctx, cudaEventCreate(&ctx->ev_dn_end));
+    }
+    LaunchInfo info = {0u, 0ull};
+    VRT_CUDA(ctx, cudaEventRecord(ctx->ev_dn_begin, ctx->stream));
+    VRT_CUDA(ctx, launch_denoise(ctx->d_fb, ctx->cfg.width, ctx->cfg.height, *params, ctx->d_denoised, out_width, out_height, (flags & VRT_DENOISE_BGRA) != 0u,
+                                 ctx->stream, &info));
+    VRT_CUDA(ctx, cudaEventRecord(ctx->ev_dn_end, ctx->stream));
+    ctx->dn_timing_valid = true;
+    return VRT_OK;
+}
+
+int vrt_read_denoised(vrt_ctx* ctx, uint8_t* host, size_t bytes) {
+    if (!ctx) return VRT_E_INVALID;
+    if (!ctx->d_denoised) return fail(ctx, VRT_E_STATE, "vrt_read_denoised: vrt_denoise has not been called");
+    const size_t need = (size_t)ctx->dn_width * ctx->dn_height * 4;
+    if (!host || bytes != need) return fail(ctx, VRT_E_INVALID, "vrt_read_denoised: need a %zu-byte buffer", need);
+    VRT_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    VRT_CUDA(ctx, cudaMemcpyAsync(host, ctx->d_denoised, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    VRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VRT_OK;
+}
+
+int vrt_denoised_device_ptr(vrt_ctx* ctx, void** out_device_ptr) {
+    if (!ctx || !out_device_ptr) return VRT_E_INVALID;
+    if (!ctx->d_denoised) return fail(ctx, VRT_E_STATE, "vrt_denoised_device_ptr: vrt_denoise has not been called");
+    *out_device_ptr = ctx->d_denoised;
+    return VRT_OK;
+}
+
+int vrt_last_denoise_ms(vrt_ctx* ctx, float* out_ms) {
+    if (!ctx || !out_ms) return VRT_E_INVALID;
+    if (!ctx->dn_timing_valid) return fail(ctx, VRT_E_STATE, "vrt_last_denoise_ms: no vrt_denoise yet");
+    VRT_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    VRT_CUDA(ctx, cudaEventSynchronize(ctx->ev_dn_end));
+    VRT_CUDA(ctx, cudaEventElapsedTime(out_ms, ctx->ev_dn_begin, ctx->ev_dn_end));
     return VRT_OK;
 }
 

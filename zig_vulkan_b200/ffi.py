@@ -21,6 +21,7 @@ VRT_EXCHANGE_PEER_STORE = 1
 VRT_NCCL_ID_BYTES = 128
 VRT_IPC_HANDLE_BYTES = 64
 
+VRT_OK, VRT_E_INVALID, VRT_E_OOM, VRT_E_RANGE, VRT_E_CUDA, VRT_E_NCCL, VRT_E_STATE = 0, -1, -2, -3, -4, -5, -6
 STATUS_NAMES = {0: "VRT_OK", -1: "VRT_E_INVALID", -2: "VRT_E_OOM", -3: "VRT_E_RANGE", -4: "VRT_E_CUDA", -5: "VRT_E_NCCL", -6: "VRT_E_STATE"}
 
 
@@ -55,6 +56,17 @@ class CameraDevice(C.Structure):  # Camera.zig:183-193
 
 class SunDevice(C.Structure):  # Sun.zig:13-18
     _fields_ = [("position", C.c_float * 3), ("enabled", C.c_uint32), ("color", C.c_float * 3), ("radius", C.c_float)]
+
+
+class DenoiseParams(C.Structure):  # GraphicsPipeline.zig:27-32 (PushConstant); defaults :34-39
+    _fields_ = [("samples", C.c_int32), ("distribution_bias", C.c_float), ("pixel_multiplier", C.c_float), ("inverse_hue_tolerance", C.c_float)]
+
+    @classmethod
+    def default(cls):
+        return cls(20, 0.6, 1.5, 20.0)
+
+
+VRT_DENOISE_BGRA = 1
 
 
 class Material(C.Structure):  # gpu_types.zig:16-32
@@ -147,6 +159,10 @@ VRT_SYMBOLS = {
     "vrt_last_trace_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "vrt_last_trace_launches": (C.c_int, [_P, C.POINTER(C.c_uint32)]),
     "vrt_set_stream": (C.c_int, [_P, _P]),
+    "vrt_denoise": (C.c_int, [_P, C.POINTER(DenoiseParams), C.c_uint32, C.c_uint32, C.c_uint32]),
+    "vrt_read_denoised": (C.c_int, [_P, _P, _SZ]),
+    "vrt_denoised_device_ptr": (C.c_int, [_P, C.POINTER(_P)]),
+    "vrt_last_denoise_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "vrt_attach_framebuffer": (C.c_int, [_P, _P, _SZ]),
     "vrt_framebuffer_device_ptr": (C.c_int, [_P, C.POINTER(_P)]),
     "vrt_comm_get_unique_id": (C.c_int, [_P]),
@@ -590,6 +606,20 @@ class Context:
         out = np.empty((self.height, self.width, 4), dtype=np.uint8)
         self._check(self._l.vrt_read_framebuffer(self.handle, _ptr(out), out.nbytes))
         return out
+
+    def denoise(self, params: "DenoiseParams | None" = None, out_width: int | None = None, out_height: int | None = None, flags: int = 0) -> np.ndarray:
+        """image.frag over the framebuffer last traced into; returns the (out_height, out_width, 4) uint8 result."""
+        params = params or DenoiseParams.default()
+        ow, oh = out_width or self.width, out_height or self.height
+        self._check(self._l.vrt_denoise(self.handle, C.byref(params), ow, oh, flags))
+        out = np.empty((oh, ow, 4), dtype=np.uint8)
+        self._check(self._l.vrt_read_denoised(self.handle, _ptr(out), out.nbytes))
+        return out
+
+    def last_denoise_ms(self) -> float:
+        ms = C.c_float()
+        self._check(self._l.vrt_last_denoise_ms(self.handle, C.byref(ms)))
+        return ms.value
 
     def trace_to_host(self, camera: CameraDevice, sun: SunDevice, out: np.ndarray | None = None, out_ptr: int | None = None) -> np.ndarray | None:
         nbytes = self.width * self.height * 4
