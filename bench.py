@@ -370,6 +370,17 @@ def main():
                 per_pose.append({"origin": [round(v, 3) for v in origin], "rays": prays, "ms": sum(ms) / len(ms), "mrays_s": prays / (sum(ms) / len(ms) * 1e-3) / 1e6})
             line["sweep"] = {"poses": per_pose, "mean_mrays_s": sum(p["mrays_s"] for p in per_pose) / len(per_pose),
                              "total_mrays_s": sum(p["rays"] for p in per_pose) / sum(p["ms"] * 1e-3 for p in per_pose) / 1e6}
+        if world == 1:
+            # the step after the path: the reference's present pass (image.frag) over the traced frame, same resolution
+            dn = []
+            for i in range(3 + 20):
+                flush.fill_(i & 0xFF)
+                ctx._check(ctx._l.vrt_denoise(ctx.handle, ffi.DenoiseParams.default(), W, H, 0))
+                if i >= 3:
+                    dn.append(ctx.last_denoise_ms())
+            dn_ms = sum(dn) / len(dn)
+            line["denoise"] = {"ms_per_frame": dn_ms, "mpixels_s": n_pixels / (dn_ms * 1e-3) / 1e6, "params": "samples 20, bias 0.6, multiplier 1.5, tolerance 20 (GraphicsPipeline.zig:34-39)",
+                               "algorithmic_gb_s": 8 * n_pixels / (dn_ms * 1e-3) / 1e9, "bound": "ALU/FMA issue (21 samples x 2 pow per pixel), not HBM"}
         if world == 1 and not args.no_cpu_baseline:
             crays, ctimes, cores = time_oracle(wl, 12, 1, budget_s=20.0)
             best = min(ctimes)

@@ -9,6 +9,7 @@
 // Arithmetic discipline = the oracle's (oracle/vrt_oracle_denoise.cpp header): FP32, no contraction (--fmad=false) except
 // the explicit fmaf of det_log2f / det_exp2f, IEEE sqrt and divide, FP32 bilinear weights.  Bound: FP32 / SFU issue, not HBM
 // (algorithmic traffic is 4 B read + 4 B written per pixel).
+#include <cmath>
 #include <cstdint>
 
 #include "../../include/vrt.h"
@@ -66,13 +67,21 @@ struct Rgb {
     float x, y, z;
 };
 
-// texture(imageSampler, uv).rgb: linear filter, repeat addressing (Pipeline.zig:193-212); `unorm` = byte / 255.0f table
+// texture(imageSampler, uv).rgb: linear filter, repeat addressing (Pipeline.zig:193-212); `unorm` = byte / 255.0f table.
+// NEAR: the coordinate is known to lie within one image size of the image (launch_denoise checks the largest sample offset), so
+// the repeat wrap is one conditional add / subtract instead of an integer modulo.
+template <bool NEAR>
 __device__ __forceinline__ Rgb sample_linear_repeat(const uint32_t* __restrict__ img, int w, int h, float fw, float fh, const float* unorm, float u, float v) {
     const float x = u * fw - 0.5f, y = v * fh - 0.5f;
     const float fx = floorf(x), fy = floorf(y);
     const float a = x - fx, b = y - fy;
-    int x0 = (int)fx % w, y0 = (int)fy % h;
-    x0 = x0 < 0 ? x0 + w : x0, y0 = y0 < 0 ? y0 + h : y0;
+    int x0 = (int)fx, y0 = (int)fy;
+    if (NEAR) {
+        x0 = x0 < 0 ? x0 + w : (x0 >= w ? x0 - w : x0), y0 = y0 < 0 ? y0 + h : (y0 >= h ? y0 - h : y0);
+    } else {
+        x0 %= w, y0 %= h;
+        x0 = x0 < 0 ? x0 + w : x0, y0 = y0 < 0 ? y0 + h : y0;
+    }
     const int x1 = x0 + 1 == w ? 0 : x0 + 1, y1 = y0 + 1 == h ? 0 : y0 + 1;
     const uint32_t p00 = __ldg(img + (size_t)y0 * w + x0), p10 = __ldg(img + (size_t)y0 * w + x1);
     const uint32_t p01 = __ldg(img + (size_t)y1 * w + x0), p11 = __ldg(img + (size_t)y1 * w + x1);
@@ -92,6 +101,7 @@ __device__ __forceinline__ uint32_t dn_unorm8(float c) {
 
 constexpr float kCosGolden = -0.7373688f, kSinGolden = 0.6754904f;  // cos / sin(2.3999632), image.frag:25,29
 
+template <bool NEAR>
 __global__ void __launch_bounds__(kDnBlockX* kDnBlockY) denoise_kernel(const uint32_t* __restrict__ img, int w, int h, const vrt_denoise_params pc, uint32_t* __restrict__ out,
                                                                         uint32_t out_w, uint32_t out_h, uint32_t bgra) {
     __shared__ float s_unorm[256];
@@ -119,7 +129,7 @@ __global__ void __launch_bounds__(kDnBlockX* kDnBlockY) denoise_kernel(const uin
     const float fw = (float)w, fh = (float)h;
     const float uvx = ((float)ox + 0.5f) / (float)out_w, uvy = ((float)oy + 0.5f) / (float)out_h;
 
-    const Rgb center = sample_linear_repeat(img, w, h, fw, fh, s_unorm, uvx, uvy);  // :38
+    const Rgb center = sample_linear_repeat<NEAR>(img, w, h, fw, fh, s_unorm, uvx, uvy);  // :38
     const float center_sat = sqrtf((center.x * center.x + center.y * center.y) + center.z * center.z);  // :40
     const float center_inv = 1.0f / center_sat;                                                         // :39 normalize
     const float cnx = center.x * center_inv, cny = center.y * center_inv, cnz = center.z * center_inv;
@@ -127,7 +137,7 @@ __global__ void __launch_bounds__(kDnBlockX* kDnBlockY) denoise_kernel(const uin
     float dx = 0.0f, dy = 0.0f, dz = 0.0f, influence_sum = 0.0f;
     const int samples = pc.samples;
     for (int k = 0; k <= samples; k++) {  // :47
-        const Rgb c = sample_linear_repeat(img, w, h, fw, fh, s_unorm, uvx + s_off_x[k], uvy + s_off_y[k]);  // :55
+        const Rgb c = sample_linear_repeat<NEAR>(img, w, h, fw, fh, s_unorm, uvx + s_off_x[k], uvy + s_off_y[k]);  // :55
         float influence = s_radial[k];
         influence *= influence * influence;  // :57
         const float len = sqrtf((c.x * c.x + c.y * c.y) + c.z * c.z);
@@ -147,7 +157,13 @@ cudaError_t launch_denoise(const uint32_t* image, uint32_t width, uint32_t heigh
                            uint32_t out_height, bool bgra, cudaStream_t stream, LaunchInfo* info) {
     const dim3 block(kDnBlockX, kDnBlockY);
     const dim3 grid((out_width + kDnBlockX - 1) / kDnBlockX, (out_height + kDnBlockY - 1) / kDnBlockY);
-    denoise_kernel<<<grid, block, 0, stream>>>(image, (int)width, (int)height, params, out, out_width, out_height, bgra ? 1u : 0u);
+    // largest sample offset in input texels (:51): |pixelMultiplier| * sqrt(samples) * 0.5, plus the bilinear footprint and slack
+    const float reach = fabsf(params.pixel_multiplier) * sqrtf((float)params.samples) * 0.5f + 3.0f;
+    const bool near = reach < (float)(width < height ? width : height);  // false also for a NaN multiplier
+    if (near)
+        denoise_kernel<true><<<grid, block, 0, stream>>>(image, (int)width, (int)height, params, out, out_width, out_height, bgra ? 1u : 0u);
+    else
+        denoise_kernel<false><<<grid, block, 0, stream>>>(image, (int)width, (int)height, params, out, out_width, out_height, bgra ? 1u : 0u);
     if (info) info->launches++;
     return cudaGetLastError();
 }
