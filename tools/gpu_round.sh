@@ -12,5 +12,6 @@ timeout -k 5 200 python bench.py --impl reference --steps 10 --warmup 1 > gpurun
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_C3.csv timeout -k 5 200 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:trace_warp -s 3 -c 1 -f -o gpurun_out/prof_warp_C3 timeout -k 5 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:trace_ref -s 3 -c 1 -f -o gpurun_out/prof_ref_C3 timeout -k 5 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --baseline-kernel > gpurun_out/ncu_full_ref.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:denoise -s 3 -c 1 -f -o gpurun_out/prof_denoise_1080p timeout -k 5 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_denoise.log 2>&1
 grep -i "error\|traceback" gpurun_out/bench.err | head -5
 ls gpurun_out | head -40

@@ -2,9 +2,10 @@
 //
 // One thread per output texel.  What the fragment shader recomputes for every fragment but depends only on the push
 // constants — the golden-angle spiral offsets (:49-53) and the radial part of the sample weight (:52) — is computed once per
-// CTA into shared memory (same operations, same order, so the values are the ones every fragment would have got), next to a
-// 256-entry table of the UNORM decode byte / 255.0f.  The per-sample work left is the bilinear fetch (4 texels of the RGBA8
-// image, which stays L2 / L1 resident: 8 MB at 1080p), one sqrt + one divide for normalize / length, and two pow.
+// CTA into shared memory (same operations, same order, so the values are the ones every fragment would have got).  The UNORM
+// decode byte / 255.0f is done once per texel by a pre-pass into a float4 image (33 MB at 1080p, L2 resident) instead of 12
+// times per sample.  The per-sample work left is the bilinear fetch (four 128-bit loads), one sqrt + one divide for
+// normalize / length, and two pow.
 //
 // Arithmetic discipline = the oracle's (oracle/vrt_oracle_denoise.cpp header): FP32, no contraction (--fmad=false) except
 // the explicit fmaf of det_log2f / det_exp2f, IEEE sqrt and divide, FP32 bilinear weights.  Bound: FP32 / SFU issue, not HBM
@@ -30,7 +31,12 @@ __device__ __forceinline__ float det_log2f(float a) {
     const int e = (ia - 0x3f3504f3) >> 23;
     const float m = __int_as_float(ia - e * (1 << 23));
     const float f = m - 1.0f;
-    const float s = f / (2.0f + f);
+    // f == 0 (a is a power of two — pow(1, b) is the common case on flat image regions) gives s = 0 / 2 = 0; a zero numerator
+    // would send the whole warp through the division's special-case subroutine, so it is divided as 1 / 2 and selected away
+    float num = f == 0.0f ? 1.0f : f;
+    asm volatile("" : "+f"(num));  // keep the compiler from folding the substitution back into a division of f itself
+    const float q = num / (2.0f + f);
+    const float s = f == 0.0f ? 0.0f : q;
     const float z = s * s;
     float p = fmaf(z, 0.22222222f, 0.2857143f);
     p = fmaf(p, z, 0.4f);
@@ -71,7 +77,7 @@ struct Rgb {
 // NEAR: the coordinate is known to lie within one image size of the image (launch_denoise checks the largest sample offset), so
 // the repeat wrap is one conditional add / subtract instead of an integer modulo.
 template <bool NEAR>
-__device__ __forceinline__ Rgb sample_linear_repeat(const uint32_t* __restrict__ img, int w, int h, float fw, float fh, const float* unorm, float u, float v) {
+__device__ __forceinline__ Rgb sample_linear_repeat(const float4* __restrict__ img, int w, int h, float fw, float fh, float u, float v) {
     const float x = u * fw - 0.5f, y = v * fh - 0.5f;
     const float fx = floorf(x), fy = floorf(y);
     const float a = x - fx, b = y - fy;
@@ -83,14 +89,23 @@ __device__ __forceinline__ Rgb sample_linear_repeat(const uint32_t* __restrict__
         x0 = x0 < 0 ? x0 + w : x0, y0 = y0 < 0 ? y0 + h : y0;
     }
     const int x1 = x0 + 1 == w ? 0 : x0 + 1, y1 = y0 + 1 == h ? 0 : y0 + 1;
-    const uint32_t p00 = __ldg(img + (size_t)y0 * w + x0), p10 = __ldg(img + (size_t)y0 * w + x1);
-    const uint32_t p01 = __ldg(img + (size_t)y1 * w + x0), p11 = __ldg(img + (size_t)y1 * w + x1);
+    const float4* row0 = img + (size_t)y0 * w;
+    const float4* row1 = img + (size_t)y1 * w;
+    const float4 t00 = __ldg(row0 + x0), t10 = __ldg(row0 + x1), t01 = __ldg(row1 + x0), t11 = __ldg(row1 + x1);
     const float w00 = (1.0f - a) * (1.0f - b), w10 = a * (1.0f - b), w01 = (1.0f - a) * b, w11 = a * b;
     Rgb c;
-    c.x = ((w00 * unorm[p00 & 255u] + w10 * unorm[p10 & 255u]) + w01 * unorm[p01 & 255u]) + w11 * unorm[p11 & 255u];
-    c.y = ((w00 * unorm[(p00 >> 8) & 255u] + w10 * unorm[(p10 >> 8) & 255u]) + w01 * unorm[(p01 >> 8) & 255u]) + w11 * unorm[(p11 >> 8) & 255u];
-    c.z = ((w00 * unorm[(p00 >> 16) & 255u] + w10 * unorm[(p10 >> 16) & 255u]) + w01 * unorm[(p01 >> 16) & 255u]) + w11 * unorm[(p11 >> 16) & 255u];
+    c.x = ((w00 * t00.x + w10 * t10.x) + w01 * t01.x) + w11 * t11.x;
+    c.y = ((w00 * t00.y + w10 * t10.y) + w01 * t01.y) + w11 * t11.y;
+    c.z = ((w00 * t00.z + w10 * t10.z) + w01 * t01.z) + w11 * t11.z;
     return c;
+}
+
+// UNORM decode of the whole image, once: texel / 255.0f per channel (IEEE divide, as the oracle's texel())
+__global__ void __launch_bounds__(256) decode_unorm_kernel(const uint32_t* __restrict__ img, float4* __restrict__ out, size_t n) {
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t p = __ldg(img + i);
+    out[i] = make_float4((float)(p & 255u) / 255.0f, (float)((p >> 8) & 255u) / 255.0f, (float)((p >> 16) & 255u) / 255.0f, (float)(p >> 24) / 255.0f);
 }
 
 __device__ __forceinline__ uint32_t dn_unorm8(float c) {
@@ -102,12 +117,10 @@ __device__ __forceinline__ uint32_t dn_unorm8(float c) {
 constexpr float kCosGolden = -0.7373688f, kSinGolden = 0.6754904f;  // cos / sin(2.3999632), image.frag:25,29
 
 template <bool NEAR>
-__global__ void __launch_bounds__(kDnBlockX* kDnBlockY) denoise_kernel(const uint32_t* __restrict__ img, int w, int h, const vrt_denoise_params pc, uint32_t* __restrict__ out,
+__global__ void __launch_bounds__(kDnBlockX* kDnBlockY) denoise_kernel(const float4* __restrict__ img, int w, int h, const vrt_denoise_params pc, uint32_t* __restrict__ out,
                                                                         uint32_t out_w, uint32_t out_h, uint32_t bgra) {
-    __shared__ float s_unorm[256];
     __shared__ float s_off_x[kDnMaxSamples + 1], s_off_y[kDnMaxSamples + 1], s_radial[kDnMaxSamples + 1];
     const int tid = threadIdx.y * kDnBlockX + threadIdx.x;
-    s_unorm[tid] = (float)tid / 255.0f;  // 256 threads
     if (tid <= pc.samples) {
         const float sample_radius = sqrtf((float)pc.samples);                       // :35
         const float sample_true_radius = 0.5f / (sample_radius * sample_radius);    // :36
@@ -129,7 +142,7 @@ __global__ void __launch_bounds__(kDnBlockX* kDnBlockY) denoise_kernel(const uin
     const float fw = (float)w, fh = (float)h;
     const float uvx = ((float)ox + 0.5f) / (float)out_w, uvy = ((float)oy + 0.5f) / (float)out_h;
 
-    const Rgb center = sample_linear_repeat<NEAR>(img, w, h, fw, fh, s_unorm, uvx, uvy);  // :38
+    const Rgb center = sample_linear_repeat<NEAR>(img, w, h, fw, fh, uvx, uvy);  // :38
     const float center_sat = sqrtf((center.x * center.x + center.y * center.y) + center.z * center.z);  // :40
     const float center_inv = 1.0f / center_sat;                                                         // :39 normalize
     const float cnx = center.x * center_inv, cny = center.y * center_inv, cnz = center.z * center_inv;
@@ -137,7 +150,7 @@ __global__ void __launch_bounds__(kDnBlockX* kDnBlockY) denoise_kernel(const uin
     float dx = 0.0f, dy = 0.0f, dz = 0.0f, influence_sum = 0.0f;
     const int samples = pc.samples;
     for (int k = 0; k <= samples; k++) {  // :47
-        const Rgb c = sample_linear_repeat<NEAR>(img, w, h, fw, fh, s_unorm, uvx + s_off_x[k], uvy + s_off_y[k]);  // :55
+        const Rgb c = sample_linear_repeat<NEAR>(img, w, h, fw, fh, uvx + s_off_x[k], uvy + s_off_y[k]);  // :55
         float influence = s_radial[k];
         influence *= influence * influence;  // :57
         const float len = sqrtf((c.x * c.x + c.y * c.y) + c.z * c.z);
@@ -153,17 +166,20 @@ __global__ void __launch_bounds__(kDnBlockX* kDnBlockY) denoise_kernel(const uin
 
 }  // namespace
 
-cudaError_t launch_denoise(const uint32_t* image, uint32_t width, uint32_t height, const vrt_denoise_params& params, uint32_t* out, uint32_t out_width,
-                           uint32_t out_height, bool bgra, cudaStream_t stream, LaunchInfo* info) {
+cudaError_t launch_denoise(const uint32_t* image, float4* decoded, uint32_t width, uint32_t height, const vrt_denoise_params& params, uint32_t* out,
+                           uint32_t out_width, uint32_t out_height, bool bgra, cudaStream_t stream, LaunchInfo* info) {
+    const size_t n = (size_t)width * height;
+    decode_unorm_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(image, decoded, n);
+    if (info) info->launches++;
     const dim3 block(kDnBlockX, kDnBlockY);
     const dim3 grid((out_width + kDnBlockX - 1) / kDnBlockX, (out_height + kDnBlockY - 1) / kDnBlockY);
     // largest sample offset in input texels (:51): |pixelMultiplier| * sqrt(samples) * 0.5, plus the bilinear footprint and slack
     const float reach = fabsf(params.pixel_multiplier) * sqrtf((float)params.samples) * 0.5f + 3.0f;
     const bool near = reach < (float)(width < height ? width : height);  // false also for a NaN multiplier
     if (near)
-        denoise_kernel<true><<<grid, block, 0, stream>>>(image, (int)width, (int)height, params, out, out_width, out_height, bgra ? 1u : 0u);
+        denoise_kernel<true><<<grid, block, 0, stream>>>(decoded, (int)width, (int)height, params, out, out_width, out_height, bgra ? 1u : 0u);
     else
-        denoise_kernel<false><<<grid, block, 0, stream>>>(image, (int)width, (int)height, params, out, out_width, out_height, bgra ? 1u : 0u);
+        denoise_kernel<false><<<grid, block, 0, stream>>>(decoded, (int)width, (int)height, params, out, out_width, out_height, bgra ? 1u : 0u);
     if (info) info->launches++;
     return cudaGetLastError();
 }

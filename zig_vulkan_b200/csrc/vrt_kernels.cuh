@@ -29,9 +29,10 @@ cudaError_t launch_trace_rays(const TraceParams& P, const vrt_ray* rays, vrt_ray
 // After the all-gather of an interleaved partition: rank-major strips -> row-major frame (width % 4 == 0).
 cudaError_t launch_deinterleave(const uint32_t* gathered, uint32_t* frame, uint32_t width, uint32_t height, uint32_t world, uint32_t strips_max,
                                 cudaStream_t stream, LaunchInfo* info);
-// image.frag:31-79 over `image` (width x height RGBA8, linear / repeat sampling) -> out (out_width x out_height RGBA8 or BGRA8); vrt_denoise.cu
-cudaError_t launch_denoise(const uint32_t* image, uint32_t width, uint32_t height, const vrt_denoise_params& params, uint32_t* out, uint32_t out_width,
-                           uint32_t out_height, bool bgra, cudaStream_t stream, LaunchInfo* info);
+// image.frag:31-79 over `image` (width x height RGBA8, linear / repeat sampling) -> out (out_width x out_height RGBA8 or BGRA8); vrt_denoise.cu.
+// decoded: width * height float4 of scratch (the UNORM-decoded image).
+cudaError_t launch_denoise(const uint32_t* image, float4* decoded, uint32_t width, uint32_t height, const vrt_denoise_params& params, uint32_t* out,
+                           uint32_t out_width, uint32_t out_height, bool bgra, cudaStream_t stream, LaunchInfo* info);
 constexpr uint32_t kStripRows = 4;  // rows per strip of the interleaved partition (= the tile height of the trace kernel)
 cudaError_t launch_trace_tuned(const TraceParams& P, bool aov, cudaStream_t stream, LaunchInfo* info);
 

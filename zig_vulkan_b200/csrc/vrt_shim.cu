@@ -108,6 +108,7 @@ struct vrt_ctx {
 
     // post-process output (vrt_denoise)
     uint32_t* d_denoised = nullptr;
+    float4* d_dn_decoded = nullptr;  // the traced image UNORM-decoded to float4 (scratch of the pass)
     uint32_t dn_width = 0, dn_height = 0;
     cudaEvent_t ev_dn_begin = nullptr, ev_dn_end = nullptr;
     bool dn_timing_valid = false;
@@ -370,7 +371,7 @@ void vrt_deinit(vrt_ctx* ctx) {
     cudaFree(ctx->d_materials), cudaFree(ctx->d_statuses), cudaFree(ctx->d_brick_indices), cudaFree(ctx->d_occupancy);
     cudaFree(ctx->d_start_indices), cudaFree(ctx->d_material_indices), cudaFree(ctx->d_fb_own), cudaFree(ctx->d_aov);
     cudaFree(ctx->d_counters), cudaFree(ctx->d_occ_dense), cudaFree(ctx->d_dist), cudaFree(ctx->d_dist_tmp);
-    cudaFree(ctx->d_tile_counter), cudaFree(ctx->d_gather), cudaFree(ctx->d_barrier), cudaFree(ctx->d_denoised);
+    cudaFree(ctx->d_tile_counter), cudaFree(ctx->d_gather), cudaFree(ctx->d_barrier), cudaFree(ctx->d_denoised), cudaFree(ctx->d_dn_decoded);
     if (ctx->ev_dn_begin) cudaEventDestroy(ctx->ev_dn_begin);
     if (ctx->ev_dn_end) cudaEventDestroy(ctx->ev_dn_end);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
@@ -581,13 +582,17 @@ int vrt_denoise(vrt_ctx* ctx, const vrt_denoise_params* params, uint32_t out_wid
         }
         ctx->dn_width = out_width, ctx->dn_height = out_height;
     }
+    if (!ctx->d_dn_decoded && cudaMalloc(&ctx->d_dn_decoded, (size_t)ctx->cfg.width * ctx->cfg.height * sizeof(float4)) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(ctx, VRT_E_OOM, "vrt_denoise: cannot allocate the %ux%u float4 scratch image", ctx->cfg.width, ctx->cfg.height);
+    }
     if (!ctx->ev_dn_begin) {
         VRT_CUDA(ctx, cudaEventCreate(&ctx->ev_dn_begin));
         VRT_CUDA(ctx, cudaEventCreate(&ctx->ev_dn_end));
     }
     LaunchInfo info = {0u, 0ull};
     VRT_CUDA(ctx, cudaEventRecord(ctx->ev_dn_begin, ctx->stream));
-    VRT_CUDA(ctx, launch_denoise(ctx->d_fb, ctx->cfg.width, ctx->cfg.height, *params, ctx->d_denoised, out_width, out_height, (flags & VRT_DENOISE_BGRA) != 0u,
+    VRT_CUDA(ctx, launch_denoise(ctx->d_fb, ctx->d_dn_decoded, ctx->cfg.width, ctx->cfg.height, *params, ctx->d_denoised, out_width, out_height, (flags & VRT_DENOISE_BGRA) != 0u,
                                  ctx->stream, &info));
     VRT_CUDA(ctx, cudaEventRecord(ctx->ev_dn_end, ctx->stream));
     ctx->dn_timing_valid = true;
