@@ -69,6 +69,20 @@ __device__ __forceinline__ float gpow(float a, float b) {
     return det_exp2f(b * det_log2f(a));
 }
 
+// len = sqrt(d), inv = 1 / len for d >= 0 (or NaN): identical to the IEEE operators, but zero — frequent: black texels — takes
+// the fast path with a substituted operand and the exact results (0 and +inf) selected afterwards.
+__device__ __forceinline__ void safe_len_inv(float d, float& len, float& inv) {
+    const bool zero = d == 0.0f;
+    float ds = zero ? 1.0f : d;
+    asm volatile("" : "+f"(ds));
+    const float l = sqrtf(ds);
+    float ls = l;
+    asm volatile("" : "+f"(ls));
+    const float r = 1.0f / ls;
+    len = zero ? 0.0f : l;
+    inv = zero ? __int_as_float(0x7f800000) : r;
+}
+
 struct Rgb {
     float x, y, z;
 };
@@ -153,8 +167,10 @@ __global__ void __launch_bounds__(kDnBlockX* kDnBlockY) denoise_kernel(const flo
         const Rgb c = sample_linear_repeat<NEAR>(img, w, h, fw, fh, uvx + s_off_x[k], uvy + s_off_y[k]);  // :55
         float influence = s_radial[k];
         influence *= influence * influence;  // :57
-        const float len = sqrtf((c.x * c.x + c.y * c.y) + c.z * c.z);
-        const float inv = 1.0f / len;
+        // a black texel (a shadowed pixel of the traced frame) has length 0 and 1 / 0 = inf: same values as the plain
+        // sqrt / divide, computed without their special-case subroutines (safe_len_inv)
+        float len, inv;
+        safe_len_inv((c.x * c.x + c.y * c.y) + c.z * c.z, len, inv);
         const float d = (cnx * (c.x * inv) + cny * (c.y * inv)) + cnz * (c.z * inv);
         influence *= gpow(0.5f + 0.5f * d, pc.inverse_hue_tolerance) * gpow(1.0f - fabsf(len - abs_center_sat), 8.0f);  // :61-64
         influence_sum += influence;                                                                                     // :66
