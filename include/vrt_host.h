@@ -135,6 +135,11 @@ void vrt_renderer_update_sun(vrt_renderer* r, float delta_time);
 int vrt_renderer_draw(vrt_renderer* r);
 /* draw + copy the frame to host memory. */
 int vrt_renderer_draw_to_host(vrt_renderer* r, uint8_t* rgba8_host, size_t bytes);
+/* The graphics half of Pipeline.draw (Pipeline.zig:441-540): draw, then the present pass (image.frag, GraphicsPipeline.zig) into
+ * an out_width x out_height image copied to host memory.  params NULL = GraphicsPipeline.Config defaults (:34-39);
+ * flags = VRT_DENOISE_*. */
+int vrt_renderer_present_to_host(vrt_renderer* r, const vrt_denoise_params* params, uint32_t out_width, uint32_t out_height, uint32_t flags,
+                                 uint8_t* host, size_t bytes);
 
 /* ------------------------------------------------------------------ scene producers */
 /* The 8 terrain materials (terrain/terrain.zig:130-196): water, grass x2, dirt x2, rock x2, iron. */

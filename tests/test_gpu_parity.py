@@ -122,6 +122,31 @@ def test_full_path_trace_modes(materials, kernel):
     assert np.array_equal(img, ref_img)
 
 
+@pytest.mark.parametrize("sun_on", [True, False])
+def test_simple_and_general_shading_paths_agree(materials, sun_on):
+    """The tuned kernel has a specialised shading path for max_bounce 1 / spp 1 / sun radius 0 / only lambert-metal-dielectric
+    materials (shade_pixel_warp_simple).  A material table with an UNUSED entry of an unknown type (4) switches the launch to
+    the general path without changing any pixel: both must give the oracle's frame."""
+    grid = scenes.build_grid(128)
+    cam = scenes.camera(320, 180, **POSE0)
+    sun = scenes.sun(sun_on)
+    ref_img, _, _ = orc.OracleScene.from_grid(grid, materials).render(cam, sun)
+    simple_img, _, _ = trace(grid, materials, cam, sun, 0)
+    mats = materials.copy()
+    assert not (grid.material_indices == 200).any()
+    mats[200]["type"] = 4
+    general_img, _, _ = trace(grid, mats, cam, sun, 0)
+    assert np.array_equal(simple_img, ref_img)
+    assert np.array_equal(general_img, ref_img)
+    # sun disc radius > 0 and spp > 1 leave the simple path as well
+    for spp, radius in [(1, 3.0), (2, 0.0)]:
+        cam2 = scenes.camera(320, 180, spp=spp, max_bounce=0, **POSE0)
+        sun2 = scenes.sun(sun_on, radius)
+        ref2, _, _ = orc.OracleScene.from_grid(grid, materials).render(cam2, sun2)
+        img2, _, _ = trace(grid, materials, cam2, sun2, 0)
+        assert np.array_equal(img2, ref2)
+
+
 def test_material_type_none_disables_the_ignore_shortcut(materials):
     """A material of type 3 (MAT_NONE) with type_data 1.0 is ignored by every camera/sun ray (:427 with CreateRay's
     ignore type 3 and ir 1.0); the tuned kernel must then evaluate the test it normally skips."""
@@ -207,6 +232,9 @@ def test_partial_uploads_and_edit(materials):
     img1 = r.draw_to_host()
     ref1, _, _ = orc.OracleScene.from_grid(grid, materials).render(r.camera.device, r.sun.device)
     assert np.array_equal(img1, ref1) and not np.array_equal(img1, img0)
+    # Pipeline.draw's graphics half: the present pass over that frame, swapchain-sized and BGRA-ordered
+    shown = r.present_to_host(240, 135, flags=ffi.VRT_DENOISE_BGRA)
+    assert np.array_equal(shown, orc.denoise(ref1, out_width=240, out_height=135, flags=ffi.VRT_DENOISE_BGRA))
     r.close()
 
 

@@ -153,4 +153,15 @@ int vrt_renderer_draw_to_host(vrt_renderer* r, uint8_t* rgba8_host, size_t bytes
     return pass(r, vrt_trace_to_host(r->ctx, &r->camera->d_camera, &r->sun->device_data, rgba8_host, bytes));
 }
 
+int vrt_renderer_present_to_host(vrt_renderer* r, const vrt_denoise_params* params, uint32_t out_width, uint32_t out_height, uint32_t flags,
+                                 uint8_t* host, size_t bytes) {
+    if (!r) return VRT_E_INVALID;
+    const vrt_denoise_params defaults = {20, 0.6f, 1.5f, 20.0f};  // GraphicsPipeline.Config (GraphicsPipeline.zig:34-39)
+    int rc = pass(r, vrt_trace(r->ctx, &r->camera->d_camera, &r->sun->device_data));
+    if (rc != VRT_OK) return rc;
+    rc = pass(r, vrt_denoise(r->ctx, params ? params : &defaults, out_width, out_height, flags));
+    if (rc != VRT_OK) return rc;
+    return pass(r, vrt_read_denoised(r->ctx, host, bytes));
+}
+
 }  // extern "C"

@@ -220,6 +220,7 @@ VRT_HOST_SYMBOLS = {
     "vrt_renderer_update_sun": (None, [_P, C.c_float]),
     "vrt_renderer_draw": (C.c_int, [_P]),
     "vrt_renderer_draw_to_host": (C.c_int, [_P, _P, _SZ]),
+    "vrt_renderer_present_to_host": (C.c_int, [_P, C.POINTER(DenoiseParams), C.c_uint32, C.c_uint32, C.c_uint32, _P, _SZ]),
     "vrt_scene_terrain_materials": (C.c_uint32, [_P, C.c_uint32]),
     "vrt_scene_synthetic": (C.c_int, [C.c_uint32, C.c_uint32, _P, _P]),
     "vrt_scene_synthetic_fill": (C.c_int, [_P, C.c_uint32]),
@@ -766,4 +767,11 @@ class Renderer:
         if out is None:
             out = np.empty((self.height, self.width, 4), dtype=np.uint8)
         self._check(self._h.vrt_renderer_draw_to_host(self.handle, _ptr(out), out.nbytes))
+        return out
+
+    def present_to_host(self, out_width: int | None = None, out_height: int | None = None, params: "DenoiseParams | None" = None, flags: int = 0) -> np.ndarray:
+        """Pipeline.draw's graphics half: draw, then image.frag into an (out_height, out_width, 4) image."""
+        ow, oh = out_width or self.width, out_height or self.height
+        out = np.empty((oh, ow, 4), dtype=np.uint8)
+        self._check(self._h.vrt_renderer_present_to_host(self.handle, C.byref(params) if params is not None else None, ow, oh, flags, _ptr(out), out.nbytes))
         return out
