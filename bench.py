@@ -32,9 +32,9 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--workload", default="C3", choices=["C1", "C2", "C3", "C4", "C5"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--exchange", default="auto", choices=["auto", "allgather", "peer"],
-                    help="N > 1: fused peer stores from the trace kernel, or an NCCL all-gather after it; auto = peer up to 4 GPUs, "
-                         "all-gather above (measured: profiles/README.md)")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "allgather", "peer", "peerflags"],
+                    help="N > 1: fused peer stores from the trace kernel (frame barrier = NCCL 4-byte all-reduce, or peer flag words: "
+                         "peerflags), or an NCCL all-gather after it; auto = peerflags up to 4 GPUs, all-gather above (measured: profiles/README.md)")
     ap.add_argument("--partition", default="interleave", choices=["interleave", "slab"], help="N > 1: 4-row strips round-robin, or one row slab per rank")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sweep", action="store_true", help="N = 1: also time the 11 way points of the reference's benchmark fly-through (Benchmark.zig:141-173)")
@@ -200,7 +200,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     if args.exchange == "auto":
-        args.exchange = "peer" if world <= 4 else "allgather"
+        args.exchange = "peerflags" if world <= 4 else "allgather"
     wl = scenes.WORKLOADS[args.workload]
     W, H = wl.width, wl.height
     interleave = world > 1 and args.partition == "interleave" and not args.baseline_kernel
@@ -231,12 +231,12 @@ def main():
             uid = torch.empty(ffi.VRT_NCCL_ID_BYTES, dtype=torch.uint8, device=dev)
         dist.broadcast(uid, 0)
         ctx.comm_init(rank, world, bytes(uid.cpu().numpy().tobytes()))
-        if args.exchange == "peer":
+        if args.exchange in ("peer", "peerflags"):
             mine = torch.frombuffer(bytearray(ctx.comm_ipc_handle()), dtype=torch.uint8).to(dev)
             allh = [torch.empty_like(mine) for _ in range(world)]
             dist.all_gather(allh, mine)
             ctx.comm_open_peers(rank, world, b"".join(bytes(h.cpu().numpy().tobytes()) for h in allh))
-            ctx.comm_set_exchange(ffi.VRT_EXCHANGE_PEER_STORE)
+            ctx.comm_set_exchange(ffi.VRT_EXCHANGE_PEER_STORE if args.exchange == "peer" else ffi.VRT_EXCHANGE_PEER_FLAGS)
 
     # ray / request-byte counters of this rank's rows (identical to the oracle's, tests/test_golden.py): the reference-shape
     # kernel for slabs, the tuned kernel's counting variant for interleaved strips

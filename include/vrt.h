@@ -286,11 +286,14 @@ int vrt_framebuffer_device_ptr(vrt_ctx* ctx, void** out_device_ptr);
  *   exchange mode 1: fused — the trace kernel itself stores its pixels into every peer's framebuffer
  *                    through NVLink peer mappings (vrt_comm_open_peers); the only collective left is a 4-byte
  *                    all-reduce that orders frame k+1's stores after every rank has consumed frame k.
+ *   exchange mode 2: mode 1 without any collective call: the frame barrier is a 32-thread kernel that publishes / polls
+ *                    per-rank flag words through the same NVLink peer mappings (release / acquire at system scope).
  * ------------------------------------------------------------------------------------------------- */
 #define VRT_NCCL_ID_BYTES 128
 #define VRT_IPC_HANDLE_BYTES 64
 #define VRT_EXCHANGE_ALLGATHER 0u
 #define VRT_EXCHANGE_PEER_STORE 1u
+#define VRT_EXCHANGE_PEER_FLAGS 2u
 
 int vrt_comm_get_unique_id(uint8_t id_out[VRT_NCCL_ID_BYTES]);
 int vrt_comm_init(vrt_ctx* ctx, int rank, int world, const uint8_t id[VRT_NCCL_ID_BYTES]);

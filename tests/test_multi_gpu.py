@@ -38,7 +38,7 @@ def _worker(rank, world, port, out_dir):
     refs = [sc.render(c, sun)[0] for c in cams]
     failures = []
     for partition in ("interleave", "slab"):
-        for exchange in ("allgather", "peer"):
+        for exchange in ("allgather", "peer", "peerflags"):
             if partition == "slab":
                 h = H // world
                 ctx = ffi.Context(W, H, len(grid.brick_indices), device=rank, rows=(rank * h, (rank + 1) * h))
@@ -48,11 +48,11 @@ def _worker(rank, world, port, out_dir):
             ids = [ffi.Context.comm_unique_id() if rank == 0 else None]
             dist.broadcast_object_list(ids, 0)
             ctx.comm_init(rank, world, ids[0])
-            if exchange == "peer":
+            if exchange != "allgather":
                 handles = [None] * world
                 dist.all_gather_object(handles, ctx.comm_ipc_handle())
                 ctx.comm_open_peers(rank, world, b"".join(handles))
-                ctx.comm_set_exchange(ffi.VRT_EXCHANGE_PEER_STORE)
+                ctx.comm_set_exchange(ffi.VRT_EXCHANGE_PEER_STORE if exchange == "peer" else ffi.VRT_EXCHANGE_PEER_FLAGS)
             # blocking frames
             for cam, ref in zip(cams, refs):
                 ctx.trace(cam, sun)

@@ -277,6 +277,40 @@ cudaError_t launch_deinterleave(const uint32_t* gathered, uint32_t* frame, uint3
     return cudaGetLastError();
 }
 
+// Frame barrier of the fused peer-store exchange without a collective library: lane r < world publishes "this rank has finished
+// frame `frame`" in rank r's flag array (a system-scope release store through the NVLink peer mapping, after the trace kernel's
+// peer stores, which the kernel boundary + cumulative fence order before it), then waits until rank r's flag for the same frame
+// has arrived in this rank's array (acquire).  After the kernel every peer's pixels of this frame are visible here.  A peer that
+// never arrives trips a ~4 s timeout that raises *error instead of hanging the GPU.
+struct PeerFlags {
+    uint32_t* flags[8];  // flags[r] = rank r's array of 8 words (this rank's own array included)
+};
+__global__ void __launch_bounds__(32) peer_barrier_kernel(const PeerFlags peers, const uint32_t rank, const uint32_t world, const uint32_t frame, int* error) {
+    const uint32_t r = threadIdx.x;
+    if (r >= world) return;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peers.flags[r] + rank), "r"(frame) : "memory");
+    const uint32_t* mine = peers.flags[rank] + r;
+    const long long t0 = clock64();
+    for (;;) {
+        uint32_t seen;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
+        if ((int32_t)(seen - frame) >= 0) break;
+        if (clock64() - t0 > (8ll << 30)) {
+            *reinterpret_cast<volatile int*>(error) = 1;
+            break;
+        }
+    }
+}
+
+cudaError_t launch_peer_barrier(uint32_t* const flags[8], uint32_t rank, uint32_t world, uint32_t frame, int* error, cudaStream_t stream, LaunchInfo* info) {
+    PeerFlags pf;
+    for (int i = 0; i < 8; i++) pf.flags[i] = flags[i];
+    peer_barrier_kernel<<<1, 32, 0, stream>>>(pf, rank, world, frame, error);
+    if (info) info->launches++;
+    return cudaGetLastError();
+}
+
 cudaError_t launch_trace(const TraceParams& P, TraceKernel which, bool aov, cudaStream_t stream, LaunchInfo* info) {
     const uint32_t rows = P.row_end - P.row_begin;
     if (rows == 0 || P.cam.image_width == 0) return cudaSuccess;

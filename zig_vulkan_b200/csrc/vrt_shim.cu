@@ -78,6 +78,8 @@ struct vrt_ctx {
     uint32_t part_rank = 0, part_world = 1, strips_max = 0;
     uint32_t* d_gather = nullptr;     // rank-major all-gather buffer of an interleaved partition
     int* d_barrier = nullptr;         // 4 bytes all-reduced after a peer-store frame
+    int* h_barrier_error = nullptr;   // pinned, device-visible: set by the flag barrier when a peer never arrives
+    uint32_t barrier_frame = 0;       // frames signalled through the flag barrier
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     bool timing_valid = false;
@@ -219,7 +221,7 @@ void fill_params(const vrt_ctx* c, const vrt_camera* cam, const vrt_sun* sun, Tr
     P.vec_store_ok = (cam->image_width % 4 == 0) && ((reinterpret_cast<uintptr_t>(c->d_fb) & 15u) == 0);
     P.n_peers = 0;
     P.one = 1u;
-    if (c->world > 1 && c->exchange_mode == VRT_EXCHANGE_PEER_STORE && c->peers_open) {
+    if (c->world > 1 && (c->exchange_mode == VRT_EXCHANGE_PEER_STORE || c->exchange_mode == VRT_EXCHANGE_PEER_FLAGS) && c->peers_open) {
         const size_t slot_words = (c->d_fb == c->d_fb_ring1) ? c->fb_bytes / 4 : 0;  // same ring slot on every rank
         for (int r = 0; r < c->world; r++)
             if (r != c->rank) P.peer_fb[P.n_peers++] = static_cast<uint32_t*>(c->peer_fb[r]) + slot_words;
@@ -327,7 +329,7 @@ int vrt_init(vrt_ctx** out_ctx, const vrt_config* cfg) {
     INIT_CUDA(cudaMalloc(&ctx->d_occupancy, ctx->n_occupancy));
     INIT_CUDA(cudaMalloc(&ctx->d_start_indices, ctx->n_start_indices * 4));
     INIT_CUDA(cudaMalloc(&ctx->d_material_indices, ctx->n_material_indices));
-    INIT_CUDA(cudaMalloc(&ctx->d_fb_own, 2 * ctx->fb_bytes));  // slot 0 + slot 1 of the frame ring, one allocation = one IPC handle
+    INIT_CUDA(cudaMalloc(&ctx->d_fb_own, 2 * ctx->fb_bytes + kPeerFlagBytes));  // slot 0 + slot 1 of the frame ring + barrier flags, one allocation = one IPC handle
     ctx->d_fb_ring1 = ctx->d_fb_own + ctx->fb_bytes / 4;
     INIT_CUDA(cudaMalloc(&ctx->d_tile_counter, 8));
     ctx->d_fb = ctx->d_fb_own;
@@ -344,7 +346,7 @@ int vrt_init(vrt_ctx** out_ctx, const vrt_config* cfg) {
     INIT_CUDA(cudaMemsetAsync(ctx->d_occupancy, 0, ctx->n_occupancy, ctx->stream));
     INIT_CUDA(cudaMemsetAsync(ctx->d_start_indices, 0xff, ctx->n_start_indices * 4, ctx->stream));
     INIT_CUDA(cudaMemsetAsync(ctx->d_material_indices, 0, ctx->n_material_indices, ctx->stream));
-    INIT_CUDA(cudaMemsetAsync(ctx->d_fb_own, 0, 2 * ctx->fb_bytes, ctx->stream));
+    INIT_CUDA(cudaMemsetAsync(ctx->d_fb_own, 0, 2 * ctx->fb_bytes + kPeerFlagBytes, ctx->stream));
     INIT_CUDA(cudaMemsetAsync(ctx->d_tile_counter, 0, 8, ctx->stream));
     if (cfg->brick_dim == 4) INIT_CUDA(cudaMalloc(&ctx->d_occ_dense, cfg->n_bricks * 8));
     if (cfg->flags & VRT_FLAG_AOV) {
@@ -372,6 +374,7 @@ void vrt_deinit(vrt_ctx* ctx) {
     cudaFree(ctx->d_start_indices), cudaFree(ctx->d_material_indices), cudaFree(ctx->d_fb_own), cudaFree(ctx->d_aov);
     cudaFree(ctx->d_counters), cudaFree(ctx->d_occ_dense), cudaFree(ctx->d_dist), cudaFree(ctx->d_dist_tmp);
     cudaFree(ctx->d_tile_counter), cudaFree(ctx->d_gather), cudaFree(ctx->d_barrier), cudaFree(ctx->d_denoised), cudaFree(ctx->d_dn_decoded);
+    if (ctx->h_barrier_error) cudaFreeHost(ctx->h_barrier_error);
     if (ctx->ev_dn_begin) cudaEventDestroy(ctx->ev_dn_begin);
     if (ctx->ev_dn_end) cudaEventDestroy(ctx->ev_dn_end);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
@@ -456,7 +459,8 @@ int vrt_trace(vrt_ctx* ctx, const vrt_camera* camera, const vrt_sun* sun) {
     }
     if (aov) VRT_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
     const bool gather = ctx->world > 1 && ctx->exchange_mode == VRT_EXCHANGE_ALLGATHER;
-    if (ctx->world > 1 && !ctx->comm) return fail(ctx, VRT_E_STATE, "vrt_trace: world > 1 but vrt_comm_init has not been called");
+    if (ctx->world > 1 && !ctx->comm && ctx->exchange_mode != VRT_EXCHANGE_PEER_FLAGS)  // the flag barrier needs no communicator
+        return fail(ctx, VRT_E_STATE, "vrt_trace: world > 1 but vrt_comm_init has not been called");
     if (gather && ctx->interleave) {  // trace straight into this rank's slice of the rank-major gather buffer
         P.fb = ctx->d_gather;
         P.il_gather = 1u;
@@ -485,8 +489,14 @@ int vrt_trace(vrt_ctx* ctx, const vrt_camera* camera, const vrt_sun* sun) {
         // (pipelined frames: the NEXT frame's remote stores land in the other ring slot of every peer, so this barrier also
         // waits until this rank has copied that slot's previous frame to its host)
         if (ctx->barrier_after_copy) VRT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->barrier_after_copy, 0));
-        const ncclResult_t r = g_nccl.AllReduce(ctx->d_barrier, ctx->d_barrier, 1, ncclInt32, ncclSum, ctx->comm, ctx->stream);
-        if (r != ncclSuccess) return fail(ctx, VRT_E_NCCL, "ncclAllReduce failed: %s", g_nccl.GetErrorString(r));
+        if (ctx->exchange_mode == VRT_EXCHANGE_PEER_FLAGS) {
+            uint32_t* flags[8] = {nullptr};
+            for (int r = 0; r < ctx->world; r++) flags[r] = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(ctx->peer_fb[r]) + 2 * ctx->fb_bytes);
+            VRT_CUDA(ctx, launch_peer_barrier(flags, (uint32_t)ctx->rank, (uint32_t)ctx->world, ++ctx->barrier_frame, ctx->h_barrier_error, ctx->stream, &info));
+        } else {
+            const ncclResult_t r = g_nccl.AllReduce(ctx->d_barrier, ctx->d_barrier, 1, ncclInt32, ncclSum, ctx->comm, ctx->stream);
+            if (r != ncclSuccess) return fail(ctx, VRT_E_NCCL, "ncclAllReduce failed: %s", g_nccl.GetErrorString(r));
+        }
     }
     VRT_CUDA(ctx, cudaEventRecord(ctx->ev_end, ctx->stream));
     ctx->timing_valid = true;
@@ -499,6 +509,8 @@ int vrt_sync(vrt_ctx* ctx) {
     VRT_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
     VRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (ctx->copy_stream) VRT_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    if (ctx->h_barrier_error && *reinterpret_cast<volatile int*>(ctx->h_barrier_error) != 0)
+        return fail(ctx, VRT_E_STATE, "vrt_sync: the peer-flag frame barrier timed out (a rank did not trace the same frame)");
     return VRT_OK;
 }
 
@@ -806,8 +818,14 @@ int vrt_comm_open_peers(vrt_ctx* ctx, int rank, int world, const uint8_t* handle
 
 int vrt_comm_set_exchange(vrt_ctx* ctx, uint32_t mode) {
     if (!ctx) return VRT_E_INVALID;
-    if (mode != VRT_EXCHANGE_ALLGATHER && mode != VRT_EXCHANGE_PEER_STORE) return fail(ctx, VRT_E_INVALID, "vrt_comm_set_exchange: unknown mode %u", mode);
-    if (mode == VRT_EXCHANGE_PEER_STORE && !ctx->peers_open) return fail(ctx, VRT_E_STATE, "vrt_comm_set_exchange: call vrt_comm_open_peers first");
+    if (mode != VRT_EXCHANGE_ALLGATHER && mode != VRT_EXCHANGE_PEER_STORE && mode != VRT_EXCHANGE_PEER_FLAGS)
+        return fail(ctx, VRT_E_INVALID, "vrt_comm_set_exchange: unknown mode %u", mode);
+    if (mode != VRT_EXCHANGE_ALLGATHER && !ctx->peers_open) return fail(ctx, VRT_E_STATE, "vrt_comm_set_exchange: call vrt_comm_open_peers first");
+    if (mode == VRT_EXCHANGE_PEER_FLAGS && !ctx->h_barrier_error) {
+        VRT_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+        VRT_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_barrier_error), sizeof(int), cudaHostAllocMapped));
+        *ctx->h_barrier_error = 0;
+    }
     ctx->exchange_mode = mode;
     return VRT_OK;
 }

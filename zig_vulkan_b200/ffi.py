@@ -18,6 +18,7 @@ VRT_FLAG_BASELINE = 2
 VRT_FLAG_INTERLEAVE = 4
 VRT_EXCHANGE_ALLGATHER = 0
 VRT_EXCHANGE_PEER_STORE = 1
+VRT_EXCHANGE_PEER_FLAGS = 2
 VRT_NCCL_ID_BYTES = 128
 VRT_IPC_HANDLE_BYTES = 64
 
