@@ -57,21 +57,6 @@ VRT_DI uint32_t material_index_at(const TraceParams& P, uint32_t grid_index, int
 // x / s, as a multiplication when s is a power of two (bit-identical, see header)
 VRT_DI V3 div_scale(V3 v, float s, float inv_s, bool exact) { return exact ? v * inv_s : v / v3s(s); }
 
-// The DDA advance (:440-467) without branches: same ladder, same additions; returns the axis stepped.
-VRT_DI int dda_step_sel(V3& side, V3 delta, I3& pos, I3 step, float scale, float& t_value) {
-    const bool pxy = side.x < side.y, pxz = side.x < side.z, pyz = side.y < side.z;
-    const bool take_x = pxy && pxz, take_y = !pxy && pyz;
-    const bool take_z = !take_x && !take_y;
-    t_value = fminf(fminf(side.x, side.y), side.z) * scale;  // the picked side value is the minimum (see march_step)
-    side.x = take_x ? side.x + delta.x : side.x;
-    side.y = take_y ? side.y + delta.y : side.y;
-    side.z = take_z ? side.z + delta.z : side.z;
-    pos.x += take_x ? step.x : 0;
-    pos.y += take_y ? step.y : 0;
-    pos.z += take_z ? step.z : 0;
-    return take_x ? 0 : (take_y ? 1 : 2);
-}
-
 // One brick-level DDA step (:345-372) on the linear cell index: strict '<', tie order x -> z / y -> z, the picked
 // axis' side value gets its delta added (the shader's own sequence of FP32 additions per axis) and the cell index moves
 // by that axis' stride.  take_x = (sx<sy)&(sx<sz); take_y = !(sx<sy)&(sy<sz); take_z = neither.
@@ -156,37 +141,42 @@ VRT_DI int brick_hit_warp4(const TraceParams& P, const Ray& r, bool ignore_test,
     return found;
 }
 
-// Voxel-level DDA inside one brick (brick_raytracer.comp:378-471).  Returns the voxel index hit or -1.
-// BD == 4: the brick's 64-bit mask is in `occ`.  Otherwise mask bytes are read from the occupancy buffer (:415).
-template <int BD, int INFO>
-VRT_DI int brick_hit_warp(const TraceParams& P, const Ray& r, bool ignore_test, float grid_t_max, V3 ray_delta, I3 ray_step, float g_scale,
-                          V3 brick_position, unsigned long long occ, uint32_t grid_index, unsigned lanes, HitRecord& hit, AxisNormal& n, TraceInfo& ti) {
-    const int bd = BD == 4 ? 4 : P.brick_dim;
+// The same for 8^3 and 16^3 bricks (brick_dim is a specialization constant upstream, State.zig:5; 16 is this repo's documented
+// extension).  State layout: 6-bit fields (x+bd) | (z+bd) << 6 | (y+bd) << 12 — inside iff bit log2(bd) of every field is set — and
+// voxel_index in bits 18+.  The brick's mask lives in the occupancy buffer (:415); the 32-bit word holding the current voxel's
+// bit is kept in a register and re-read only when the voxel index leaves it (x steps and most z steps stay inside a word),
+// instead of one byte load per voxel step.  (The shader's uint8_t truncation of voxel_index / 8, :413, cannot trigger for an
+// in-range index at brick_dim 8 and is widened at 16, as in the oracle.)
+template <int INFO>
+VRT_DI int brick_hit_warp_n(const TraceParams& P, const Ray& r, bool ignore_test, float grid_t_max, V3 ray_delta, I3 ray_step, float g_scale,
+                            V3 brick_position, uint32_t grid_index, unsigned lanes, HitRecord& hit, AxisNormal& n, TraceInfo& ti, int one) {
+    const int bd = P.brick_dim;
     const float voxel_scale = g_scale * P.brick_voxel_scale;                                                  // :389
     const V3 fposition = div_scale(RayAt(r, hit.t) - brick_position, voxel_scale, P.inv_voxel_scale, P.voxel_scale_pow2 != 0u);  // :393
-    V3 side_dist = init_side_dist(fposition, ray_step, ray_delta);                                            // :394-395
-    I3 pos = I3{(int)floorf(fposition.x), (int)floorf(fposition.y), (int)floorf(fposition.z)};                // :403
+    const V3 side_dist = init_side_dist(fposition, ray_step, ray_delta);                                      // :394-395
+    float sx = side_dist.x, sy = side_dist.y, sz = side_dist.z;
+    const int px = (int)floorf(fposition.x), py = (int)floorf(fposition.y), pz = (int)floorf(fposition.z);    // :403
     const float local_t_max = grid_t_max - hit.t;                                                            // :405
     float t_value = 0.0f;
-    unsigned long long mask_base = 0ull;
-    if (BD != 4) {
-        const uint32_t brick_index = grid_index < P.n_brick_indices ? __ldg(P.brick_indices + grid_index) : 0u;  // :337
-        mask_base = (unsigned long long)brick_index * P.brick_bytes;                                            // :390
-    }
+    const int inside = bd | (bd << 6) | (bd << 12);
+    const bool start_inside = (uint32_t)px < (uint32_t)bd && (uint32_t)py < (uint32_t)bd && (uint32_t)pz < (uint32_t)bd;  // :407-410
+    int state = start_inside ? ((px + bd) | ((pz + bd) << 6) | ((py + bd) << 12) | ((px + bd * (pz + bd * py)) << 18)) : 0;
+    const int stx = ray_step.x * (1 + (1 << 18)), stz = ray_step.z * ((1 << 6) + (bd << 18)), sty = ray_step.y * ((1 << 12) + ((bd * bd) << 18));
+    const uint32_t brick_index = grid_index < P.n_brick_indices ? __ldg(P.brick_indices + grid_index) : 0u;  // :337
+    const unsigned long long mask_base = (unsigned long long)brick_index * P.brick_bytes;                    // :390
+    int word_at = -1;
+    uint32_t word = 0u;
+    int prev = state;
     int found = -1;
-    while ((uint32_t)pos.x < (uint32_t)bd && (uint32_t)pos.y < (uint32_t)bd && (uint32_t)pos.z < (uint32_t)bd && t_value <= local_t_max) {
+    while ((state & inside) == inside && t_value <= local_t_max) {  // :407-411
         if (INFO == 2) ti.voxel_steps++;
-        const int voxel_index = pos.x + bd * (pos.z + bd * pos.y);  // :412
-        bool solid;
-        if (BD == 4) {
-            solid = ((voxel_index & 32 ? (uint32_t)(occ >> 32) : (uint32_t)occ) >> (voxel_index & 31)) & 1u;  // :415-417
-        } else {
-            const uint32_t mask_index = (bd <= 8) ? (uint32_t)(uint8_t)(voxel_index / 8) : (uint32_t)(voxel_index / 8);  // :413
-            const unsigned long long at = mask_base + mask_index;
-            const uint32_t entry = at < P.n_occupancy ? (uint32_t)__ldg(P.occupancy + at) : 0u;
-            solid = (entry >> (voxel_index % 8)) & 1u;
+        const int voxel_index = state >> 18;  // :412
+        if ((voxel_index >> 5) != word_at) {
+            word_at = voxel_index >> 5;
+            const unsigned long long at = mask_base + 4ull * (unsigned long long)word_at;
+            word = at < P.n_occupancy ? __ldg(reinterpret_cast<const uint32_t*>(P.occupancy + at)) : 0u;  // bytes :415 reads one at a time
         }
-        if (solid) {
+        if ((word >> (voxel_index & 31)) & 1u) {  // :415-417
             bool ignore_brick = false;
             if (ignore_test) {
                 hit.index = material_index_at(P, grid_index, voxel_index);  // :425
@@ -198,10 +188,17 @@ VRT_DI int brick_hit_warp(const TraceParams& P, const Ray& r, bool ignore_test, 
                 break;
             }
         }
-        n = step_normal(dda_step_sel(side_dist, ray_delta, pos, ray_step, voxel_scale, t_value), ray_step);  // :440-467
+        t_value = fminf(fminf(sx, sy), sz) * voxel_scale;
+        prev = state;
+        march_step(sx, sy, sz, ray_delta.x, ray_delta.y, ray_delta.z, stx, sty, stz, state, one);  // :440-467
     }
-    __syncwarp(lanes);  // the rays leave the loop at different trips: finish hits (and, in the caller, misses) together
+    __syncwarp(lanes);
     if (found >= 0) {
+        const int moved = (state >> 18) - (prev >> 18);
+        if (moved != 0) {
+            const int a = moved < 0 ? -moved : moved;
+            n = step_normal(a == 1 ? 0 : (a == bd ? 2 : 1), ray_step);
+        }
         const float t_offset = voxel_scale * 0.05f;           // :431
         hit.t += t_value - t_offset;                          // :432
         hit.normal = to_v3(n);
@@ -336,7 +333,7 @@ VRT_DI bool grid_hit_warp(const TraceParams& P, const Ray& r, bool active, bool 
             hit.t = (t_value + grid_t_min) + 0.01f * g_scale;                                  // :332-334
             if (COUNT) ti.bricks_entered++;
             const int voxel_index = BD == 4 ? brick_hit_warp4<INFO>(P, r, ignore_test, grid_t_max, ray_delta, ray_step, g_scale, brick_min, occ, grid_index, parked_lanes, hit, n, ti, one)
-                                             : brick_hit_warp<BD, INFO>(P, r, ignore_test, grid_t_max, ray_delta, ray_step, g_scale, brick_min, occ, grid_index, parked_lanes, hit, n, ti);
+                                             : brick_hit_warp_n<INFO>(P, r, ignore_test, grid_t_max, ray_delta, ray_step, g_scale, brick_min, grid_index, parked_lanes, hit, n, ti, one);
             if (voxel_index >= 0) {
                 if (need_material && !ignore_test) hit.index = material_index_at(P, grid_index, voxel_index);
                 if (INFO >= 1) ti.grid_index = grid_index, ti.voxel_index = (uint32_t)voxel_index;
