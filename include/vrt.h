@@ -242,6 +242,28 @@ int vrt_last_trace_ms(vrt_ctx* ctx, float* out_ms);
 int vrt_last_trace_launches(vrt_ctx* ctx, uint32_t* out);
 
 /* ---------------------------------------------------------------------------------------------------
+ * Scene edits on the device: BrickGrid.insert (brick/Grid.zig:129-194) for a batch of voxels, the step in front of the
+ * uploads.  The five grid buffers of the ctx end up byte-identical to what the host loop
+ *     for (i < count) grid.insert(x[i], y[i], z[i], material[i])
+ * followed by the transfer* uploads would have produced: new bricks are numbered in order of first occurrence, their
+ * material block starts at brick * brick_dim^3, a voxel inserted twice keeps the last material.  Differences, both stricter:
+ * a voxel outside the grid or a batch that needs more bricks than n_brick_alloc fails with VRT_E_RANGE and changes nothing
+ * (Grid.insert asserts / indexes out of bounds).  The host BrickGrid is not updated; read the buffers back with
+ * vrt_download_buffer if it must follow.
+ * ------------------------------------------------------------------------------------------------- */
+/* xyzm_host: count packed {x, y, z, material} uint32 quadruples (the layout of vrt_grid_insert_many).  *active_bricks: in = bricks
+ * allocated so far (BrickGrid.State.active_bricks; 0 for a fresh ctx), out = after the batch.  Blocks until done. */
+int vrt_insert_voxels(vrt_ctx* ctx, const uint32_t* xyzm_host, size_t count, uint32_t* active_bricks);
+
+#define VRT_BUFFER_STATUSES 3u         /* binding numbers of brick_raytracer.comp:109-134; element = uint32 */
+#define VRT_BUFFER_BRICK_INDICES 4u    /* uint32 */
+#define VRT_BUFFER_OCCUPANCY 5u        /* uint8  */
+#define VRT_BUFFER_START_INDICES 6u    /* uint32 */
+#define VRT_BUFFER_MATERIAL_INDICES 7u /* uint8  */
+/* Copy `count` elements starting at element `offset` of a grid buffer to the host (the inverse of vrt_upload_*).  Blocks. */
+int vrt_download_buffer(vrt_ctx* ctx, uint32_t which, size_t offset, void* host, size_t count);
+
+/* ---------------------------------------------------------------------------------------------------
  * Post-process: the reference's present pass (assets/shaders/image.frag:31-79, "sirBirdDenoise"), the step right after
  * the compute dispatch in Pipeline.draw (Pipeline.zig:441-540).  Replaces GraphicsPipeline's full-screen draw: reads the
  * traced RGBA8 image through a linear / repeat sampler (Pipeline.zig:193-212) and writes one denoised texel per pixel of

@@ -35,6 +35,27 @@ cudaError_t launch_denoise(const uint32_t* image, float4* decoded, uint32_t widt
                            uint32_t out_width, uint32_t out_height, bool bgra, cudaStream_t stream, LaunchInfo* info);
 // Frame barrier over peer-mapped flag words (fused peer-store exchange, VRT_EXCHANGE_PEER_FLAGS); see vrt_kernels.cu.
 cudaError_t launch_peer_barrier(uint32_t* const flags[8], uint32_t rank, uint32_t world, uint32_t frame, int* error, cudaStream_t stream, LaunchInfo* info);
+// BrickGrid.insert for a batch of voxels on the device (vrt_build.cu): `prepare` only reads the grid buffers (first occurrences,
+// flags, scan; totals[0] = new bricks << 32 | touched cells, totals[2] != 0: a voxel outside the grid), `commit` applies the batch.
+struct InsertBuffers {
+    vrt_grid_state state;
+    uint32_t brick_dim;
+    size_t n_cells;
+    uint32_t* statuses;
+    uint32_t* brick_indices;
+    uint8_t* occupancy;
+    uint32_t* start_indices;
+    uint8_t* material_indices;
+    uint32_t* first_pos;               // scratch, n_cells
+    unsigned long long* flags;         // scratch, n voxels
+    unsigned long long* ranks;         // scratch, n voxels
+    unsigned long long* scan_scratch;  // scratch, insert_scan_scratch_entries(n)
+    unsigned long long* totals;        // scratch, 4
+};
+size_t insert_scan_scratch_entries(size_t n);
+cudaError_t launch_insert_prepare(const InsertBuffers& B, const uint32_t* xyzm, size_t n, cudaStream_t stream, LaunchInfo* info);
+cudaError_t launch_insert_commit(const InsertBuffers& B, const uint32_t* xyzm, size_t n, uint32_t active_before, uint32_t* last_writer /* touched * brick_bits, zeroed */,
+                                 cudaStream_t stream, LaunchInfo* info);
 constexpr size_t kPeerFlagBytes = 256;  // flag words appended to the IPC-shared framebuffer allocation
 constexpr uint32_t kStripRows = 4;  // rows per strip of the interleaved partition (= the tile height of the trace kernel)
 cudaError_t launch_trace_tuned(const TraceParams& P, bool aov, cudaStream_t stream, LaunchInfo* info);

@@ -575,6 +575,97 @@ int vrt_trace_to_host(vrt_ctx* ctx, const vrt_camera* camera, const vrt_sun* sun
     return VRT_OK;
 }
 
+int vrt_insert_voxels(vrt_ctx* ctx, const uint32_t* xyzm_host, size_t count, uint32_t* active_bricks) {
+    if (!ctx) return VRT_E_INVALID;
+    if (!active_bricks) return fail(ctx, VRT_E_INVALID, "vrt_insert_voxels: active_bricks is NULL");
+    if (count == 0) return VRT_OK;
+    if (!xyzm_host) return fail(ctx, VRT_E_INVALID, "vrt_insert_voxels: xyzm is NULL");
+    if (!ctx->have_grid) return fail(ctx, VRT_E_STATE, "vrt_insert_voxels: vrt_upload_grid_state has not been called");
+    if (count >= 0xffffffffull) return fail(ctx, VRT_E_RANGE, "vrt_insert_voxels: at most 2^32 - 2 voxels per call");
+    if (*active_bricks > ctx->n_start_indices) return fail(ctx, VRT_E_RANGE, "vrt_insert_voxels: active_bricks %u exceeds n_brick_alloc %zu", *active_bricks, ctx->n_start_indices);
+    VRT_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    const uint32_t bits = ctx->cfg.brick_dim * ctx->cfg.brick_dim * ctx->cfg.brick_dim;
+    InsertBuffers B;
+    B.state = ctx->grid, B.brick_dim = ctx->cfg.brick_dim;
+    B.n_cells = (size_t)ctx->grid.dim_x * ctx->grid.dim_y * ctx->grid.dim_z;
+    if (B.n_cells > ctx->n_brick_indices) return fail(ctx, VRT_E_RANGE, "vrt_insert_voxels: grid state has more cells than n_bricks");
+    B.statuses = ctx->d_statuses, B.brick_indices = ctx->d_brick_indices, B.occupancy = ctx->d_occupancy;
+    B.start_indices = ctx->d_start_indices, B.material_indices = ctx->d_material_indices;
+    // scratch: one allocation for the voxel list + flags + ranks + scan levels + totals + per-cell first positions
+    const size_t scan_entries = insert_scan_scratch_entries(count);
+    const size_t bytes = count * 16 + count * 8 * 2 + scan_entries * 8 + 4 * 8 + B.n_cells * 4;
+    uint8_t* scratch = nullptr;
+    if (cudaMalloc(&scratch, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(ctx, VRT_E_OOM, "vrt_insert_voxels: cannot allocate %zu bytes of scratch", bytes);
+    }
+    uint32_t* d_xyzm = reinterpret_cast<uint32_t*>(scratch);
+    B.flags = reinterpret_cast<unsigned long long*>(scratch + count * 16);
+    B.ranks = B.flags + count;
+    B.scan_scratch = B.ranks + count;
+    B.totals = B.scan_scratch + scan_entries;
+    B.first_pos = reinterpret_cast<uint32_t*>(B.totals + 4);
+    uint32_t* last_writer = nullptr;
+    int rc = VRT_OK;
+    unsigned long long totals[4] = {0, 0, 0, 0};
+    LaunchInfo info = {0u, 0ull};
+    auto cuda_ok = [&](cudaError_t e) {
+        if (e == cudaSuccess) return true;
+        rc = fail(ctx, VRT_E_CUDA, "vrt_insert_voxels: %s", cudaGetErrorString(e));
+        return false;
+    };
+    do {
+        if (!cuda_ok(cudaMemcpyAsync(d_xyzm, xyzm_host, count * 16, cudaMemcpyHostToDevice, ctx->stream))) break;
+        if (!cuda_ok(launch_insert_prepare(B, d_xyzm, count, ctx->stream, &info))) break;
+        if (!cuda_ok(cudaMemcpyAsync(totals, B.totals, sizeof(totals), cudaMemcpyDeviceToHost, ctx->stream))) break;
+        if (!cuda_ok(cudaStreamSynchronize(ctx->stream))) break;
+        if (totals[2] != 0ull) {
+            rc = fail(ctx, VRT_E_RANGE, "vrt_insert_voxels: a voxel lies outside the %ux%ux%u grid (nothing inserted)", ctx->grid.voxel_dim_x, ctx->grid.voxel_dim_y, ctx->grid.voxel_dim_z);
+            break;
+        }
+        const uint32_t new_bricks = (uint32_t)(totals[0] >> 32), touched = (uint32_t)totals[0];
+        if ((size_t)*active_bricks + new_bricks > ctx->n_start_indices) {
+            rc = fail(ctx, VRT_E_RANGE, "vrt_insert_voxels: %u new bricks on top of %u exceed n_brick_alloc %zu (nothing inserted)", new_bricks, *active_bricks, ctx->n_start_indices);
+            break;
+        }
+        const size_t lw_bytes = (size_t)touched * bits * 4;
+        if (cudaMalloc(&last_writer, lw_bytes) != cudaSuccess) {
+            cudaGetLastError();
+            rc = fail(ctx, VRT_E_OOM, "vrt_insert_voxels: cannot allocate %zu bytes of scratch", lw_bytes);
+            break;
+        }
+        if (!cuda_ok(cudaMemsetAsync(last_writer, 0, lw_bytes, ctx->stream))) break;
+        if (!cuda_ok(launch_insert_commit(B, d_xyzm, count, *active_bricks, last_writer, ctx->stream, &info))) break;
+        if (!cuda_ok(cudaStreamSynchronize(ctx->stream))) break;
+        *active_bricks += new_bricks;
+        ctx->accel_dirty = true;
+    } while (false);
+    cudaFree(last_writer);
+    cudaFree(scratch);
+    return rc;
+}
+
+int vrt_download_buffer(vrt_ctx* ctx, uint32_t which, size_t offset, void* host, size_t count) {
+    if (!ctx) return VRT_E_INVALID;
+    const uint8_t* src = nullptr;
+    size_t capacity = 0, elem = 4;
+    switch (which) {
+        case VRT_BUFFER_STATUSES: src = reinterpret_cast<const uint8_t*>(ctx->d_statuses), capacity = ctx->n_statuses; break;
+        case VRT_BUFFER_BRICK_INDICES: src = reinterpret_cast<const uint8_t*>(ctx->d_brick_indices), capacity = ctx->n_brick_indices; break;
+        case VRT_BUFFER_OCCUPANCY: src = ctx->d_occupancy, capacity = ctx->n_occupancy, elem = 1; break;
+        case VRT_BUFFER_START_INDICES: src = reinterpret_cast<const uint8_t*>(ctx->d_start_indices), capacity = ctx->n_start_indices; break;
+        case VRT_BUFFER_MATERIAL_INDICES: src = ctx->d_material_indices, capacity = ctx->n_material_indices, elem = 1; break;
+        default: return fail(ctx, VRT_E_INVALID, "vrt_download_buffer: unknown buffer %u", which);
+    }
+    if (count == 0) return VRT_OK;
+    if (!host) return fail(ctx, VRT_E_INVALID, "vrt_download_buffer: host is NULL");
+    if (offset > capacity || count > capacity - offset) return fail(ctx, VRT_E_RANGE, "vrt_download_buffer: [%zu, %zu) outside capacity %zu", offset, offset + count, capacity);
+    VRT_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    VRT_CUDA(ctx, cudaMemcpyAsync(host, src + offset * elem, count * elem, cudaMemcpyDeviceToHost, ctx->stream));
+    VRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VRT_OK;
+}
+
 int vrt_denoise(vrt_ctx* ctx, const vrt_denoise_params* params, uint32_t out_width, uint32_t out_height, uint32_t flags) {
     if (!ctx) return VRT_E_INVALID;
     if (!params) return fail(ctx, VRT_E_INVALID, "vrt_denoise: params is NULL");

@@ -160,6 +160,8 @@ VRT_SYMBOLS = {
     "vrt_last_trace_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "vrt_last_trace_launches": (C.c_int, [_P, C.POINTER(C.c_uint32)]),
     "vrt_set_stream": (C.c_int, [_P, _P]),
+    "vrt_insert_voxels": (C.c_int, [_P, _P, _SZ, C.POINTER(C.c_uint32)]),
+    "vrt_download_buffer": (C.c_int, [_P, C.c_uint32, _SZ, _P, _SZ]),
     "vrt_denoise": (C.c_int, [_P, C.POINTER(DenoiseParams), C.c_uint32, C.c_uint32, C.c_uint32]),
     "vrt_read_denoised": (C.c_int, [_P, _P, _SZ]),
     "vrt_denoised_device_ptr": (C.c_int, [_P, C.POINTER(_P)]),
@@ -535,6 +537,7 @@ class Context:
     def __init__(self, width, height, n_bricks, brick_dim=4, n_brick_alloc=0, material_capacity=256, device=0, flags=0, rows=(0, 0), part=None, handle=None):
         self._l = lib()
         self.width, self.height = width, height
+        self.n_bricks, self.brick_dim, self.n_brick_alloc = n_bricks, brick_dim, n_brick_alloc or n_bricks
         self._owned = handle is None
         if handle is None:
             if part is not None:  # (rank, world): interleaved 4-row strips
@@ -607,6 +610,28 @@ class Context:
     def read_framebuffer(self) -> np.ndarray:
         out = np.empty((self.height, self.width, 4), dtype=np.uint8)
         self._check(self._l.vrt_read_framebuffer(self.handle, _ptr(out), out.nbytes))
+        return out
+
+    def insert_voxels(self, xyzm: np.ndarray, active_bricks: int) -> int:
+        """BrickGrid.insert for a batch of {x, y, z, material} uint32 quadruples on the device; returns the new active brick count."""
+        xyzm = np.ascontiguousarray(xyzm, dtype=np.uint32).reshape(-1, 4)
+        active = C.c_uint32(active_bricks)
+        self._check(self._l.vrt_insert_voxels(self.handle, _ptr(xyzm), len(xyzm), C.byref(active)))
+        return active.value
+
+    def download_buffer(self, which: int) -> np.ndarray:
+        """One of the five grid buffers (binding number 3..7) as the host would have uploaded it."""
+        n, dt = {3: (self.n_bricks + 31) // 32, 4: self.n_bricks}.get(which), np.uint32
+        bits = self.brick_dim ** 3
+        alloc = self.n_brick_alloc
+        if which == 5:
+            n, dt = alloc * bits // 8, np.uint8
+        elif which == 6:
+            n = alloc
+        elif which == 7:
+            n, dt = alloc * bits, np.uint8
+        out = np.empty(n, dtype=dt)
+        self._check(self._l.vrt_download_buffer(self.handle, which, 0, _ptr(out), n))
         return out
 
     def denoise(self, params: "DenoiseParams | None" = None, out_width: int | None = None, out_height: int | None = None, flags: int = 0) -> np.ndarray:
