@@ -381,6 +381,26 @@ def main():
             dn_ms = sum(dn) / len(dn)
             line["denoise"] = {"ms_per_frame": dn_ms, "mpixels_s": n_pixels / (dn_ms * 1e-3) / 1e6, "params": "samples 20, bias 0.6, multiplier 1.5, tolerance 20 (GraphicsPipeline.zig:34-39)",
                                "algorithmic_gb_s": 8 * n_pixels / (dn_ms * 1e-3) / 1e9, "bound": "ALU/FMA issue (21 samples x 2 pow per pixel), not HBM"}
+        if world == 1:
+            # explicit-ray mode (vrt_trace_rays): this camera's primary rays as a 32 B/ray device buffer in, 32 B/ray hit records out
+            jj, ii = np.meshgrid(np.arange(H, dtype=np.float32), np.arange(W, dtype=np.float32), indexing="ij")
+            u, v = (ii / np.float32(W - 1))[..., None], (jj / np.float32(H - 1))[..., None]
+            hor, ver, llc, org = (np.array(list(getattr(cam, f)), dtype=np.float32) for f in ("horizontal", "vertical", "lower_left_corner", "origin"))
+            d = (hor * u + llc) + (ver * v - org)
+            rays_np = np.zeros(n_pixels, dtype=ffi.RAY_DTYPE)
+            rays_np["origin"], rays_np["direction"] = org, (d / np.linalg.norm(d, axis=-1, keepdims=True)).reshape(-1, 3)
+            d_rays = torch.from_numpy(rays_np.view(np.uint8).reshape(-1)).to(dev)
+            d_hits = torch.zeros(n_pixels * 32, dtype=torch.uint8, device=dev)
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(3 + 20)]
+            for i, (a, b) in enumerate(ev):
+                flush.fill_(i & 0xFF)
+                a.record(stream)
+                ctx.trace_rays_device(d_rays.data_ptr(), d_hits.data_ptr(), n_pixels)
+                b.record(stream)
+            torch.cuda.synchronize(dev)
+            er_ms = sum(a.elapsed_time(b) for a, b in ev[3:]) / 20
+            line["explicit_rays"] = {"rays": n_pixels, "ms": er_ms, "mrays_s": n_pixels / (er_ms * 1e-3) / 1e6, "ray_io_gb_s": 64 * n_pixels / (er_ms * 1e-3) / 1e9,
+                                     "note": "primary rays only; 32 B ray in + 32 B hit record out per ray, 128-bit loads / stores"}
         if world == 1 and not args.no_cpu_baseline:
             crays, ctimes, cores = time_oracle(wl, 12, 1, budget_s=20.0)
             best = min(ctimes)
