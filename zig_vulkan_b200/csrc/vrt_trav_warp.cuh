@@ -11,7 +11,7 @@
 //     A DDA only moves along its own octant, one cell along one axis per step — after j steps it is at L1 distance
 //     exactly j — so from a cell with distance D the next D-1 steps cannot land on a loaded brick or leave the grid
 //     and run with no memory access and no bounds test:
-//     four compares, predicated FADDs and IADDs.  Only the D-th step is followed by a lookup.
+//     three compares, one predicate op, predicated FADDs and IMADs (march_step).  Only the D-th step is followed by a lookup.
 //     The border makes "left the grid" a byte value, so the march carries ONE linear index, not three coordinates.
 //   * Warp rounds.  The 32 rays of a tile look their cells up TOGETHER, reduce the distances found to the warp minimum
 //     k (redux.sync) and all take k steps: the step loop is warp-uniform (no per-lane counters, no divergence) and the
@@ -21,7 +21,9 @@
 //     The expensive brick entry (three divides, a 64-bit mask fetch) is therefore executed coherently instead of once
 //     per ray at 32 different times.
 //   * The 4^3 voxel mask of a brick is one 64-bit load from a grid-indexed copy (`occ_dense`) and the voxel DDA runs in
-//     registers (the shader does a dependent brick_indices load plus one byte load per voxel step, :337,:415).
+//     registers on ONE packed integer (bounds guard + voxel index, brick_hit_warp4); 8^3 / 16^3 bricks keep the current 32-bit
+//     mask word in a register (brick_hit_warp_n).  The shader does a dependent brick_indices load plus one byte load per
+//     voxel step (:337,:415).
 //   * Divisions by the brick/voxel scale become exact multiplications when the scale is a power of two (the result of
 //     x / 2^k and x * 2^-k is the same correctly-rounded number).
 //   * The material chain (brick_indices -> start index -> material index -> material) is walked once per hit, and not at
