@@ -258,6 +258,7 @@ def main():
         torch.cuda.synchronize(dev)
 
     # ---------------------------------------------------------------- device-resident timing
+    barrier()  # ranks enter the first exchanged frame together (set-up time differs from rank to rank)
     for _ in range(max(args.warmup, 3)):
         flush.fill_(1)
         ctx.trace(cam, sun)

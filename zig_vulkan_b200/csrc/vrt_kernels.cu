@@ -281,7 +281,7 @@ cudaError_t launch_deinterleave(const uint32_t* gathered, uint32_t* frame, uint3
 // frame `frame`" in rank r's flag array (a system-scope release store through the NVLink peer mapping, after the trace kernel's
 // peer stores, which the kernel boundary + cumulative fence order before it), then waits until rank r's flag for the same frame
 // has arrived in this rank's array (acquire).  After the kernel every peer's pixels of this frame are visible here.  A peer that
-// never arrives trips a ~4 s timeout that raises *error instead of hanging the GPU.
+// never arrives trips a ~17 s timeout (2^35 cycles) that raises *error instead of hanging the GPU.
 struct PeerFlags {
     uint32_t* flags[8];  // flags[r] = rank r's array of 8 words (this rank's own array included)
 };
@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(32) peer_barrier_kernel(const PeerFlags peers,
         uint32_t seen;
         asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
         if ((int32_t)(seen - frame) >= 0) break;
-        if (clock64() - t0 > (8ll << 30)) {
+        if (clock64() - t0 > (1ll << 35)) {
             *reinterpret_cast<volatile int*>(error) = 1;
             break;
         }
