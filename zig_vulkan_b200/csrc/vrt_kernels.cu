@@ -44,7 +44,6 @@ __global__ void __launch_bounds__(kTunedThreads, 3) trace_warp_kernel(const __gr
     const uint32_t lx = lane & (kTileW - 1u), ly = lane >> 3;
     const uint32_t width = P.cam.image_width;
     PixelCounters pc = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-    if (BD != 4 && P.brick_dim == 16) brick_stage_init();
 
     for (;;) {
         unsigned long long t = 0ull;
@@ -133,7 +132,6 @@ __global__ void __launch_bounds__(kTunedThreads, 3) trace_rays_kernel(const __gr
     const unsigned long long warp = (unsigned long long)blockIdx.x * (kTunedThreads / 32) + (threadIdx.x >> 5);
     const uint32_t lane = threadIdx.x & 31u;
     const bool ignore_test = P.materials_have_none != 0u;  // CreateRay's ignore type is MAT_NONE (:182)
-    if (BD != 4 && P.brick_dim == 16) brick_stage_init();
     for (unsigned long long base = warp * 32ull; base < count; base += warps_total * 32ull) {  // warp-uniform trip count
         const unsigned long long i = base + lane;
         const bool active = i < count;
