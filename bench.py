@@ -390,7 +390,7 @@ def main():
             d = (hor * u + llc) + (ver * v - org)
             d = d / np.linalg.norm(d, axis=-1, keepdims=True)
             if H % 4 == 0 and W % 8 == 0:  # 8x4-pixel tiles, tile after tile: 32 consecutive rays = one coherent tile (the caller chooses the order)
-                d = d.reshape(H // 4, 4, W // 8, 8, 3).transpose(0, 2, 1, 3, 4)
+                d = d.reshape(H // 4, 4, W // 8, 8, 3).transpose(0, 2, 1, 3, 4)[::-1]  # ground tiles first, like the pixel kernel
             rays_np = np.zeros(n_pixels, dtype=ffi.RAY_DTYPE)
             rays_np["origin"], rays_np["direction"] = org, d.reshape(-1, 3)
             d_rays = torch.from_numpy(rays_np.view(np.uint8).reshape(-1)).to(dev)

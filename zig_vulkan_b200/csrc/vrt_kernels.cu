@@ -123,16 +123,20 @@ cudaError_t launch_trace_tuned(const TraceParams& P, bool aov, cudaStream_t stre
 
 // ----------------------------------------------------------------------------------------------------
 // Explicit rays: a warp takes 32 consecutive rays (two 128-bit loads each), runs the cooperative GridHit and writes
-// 32-byte hit records (two 128-bit stores each).  Grid-stride over blocks of 32 rays.
+// 32-byte hit records (two 128-bit stores each).  Persistent warps pull blocks of 32 rays from the work counter.
 // ----------------------------------------------------------------------------------------------------
 template <int BD>
 __global__ void __launch_bounds__(kTunedThreads, 3) trace_rays_kernel(const __grid_constant__ TraceParams P, const float4* __restrict__ rays,
                                                                      uint4* __restrict__ hits, const unsigned long long count) {
-    const unsigned long long warps_total = (unsigned long long)gridDim.x * (kTunedThreads / 32);
-    const unsigned long long warp = (unsigned long long)blockIdx.x * (kTunedThreads / 32) + (threadIdx.x >> 5);
     const uint32_t lane = threadIdx.x & 31u;
     const bool ignore_test = P.materials_have_none != 0u;  // CreateRay's ignore type is MAT_NONE (:182)
-    for (unsigned long long base = warp * 32ull; base < count; base += warps_total * 32ull) {  // warp-uniform trip count
+    const unsigned long long blocks = (count + 31ull) / 32ull;
+    for (;;) {  // blocks of 32 rays from the same work counter as the pixel kernel: rays differ in cost by orders of magnitude
+        unsigned long long t = 0ull;
+        if (lane == 0) t = atomicAdd(P.tile_counter, 1ull) - P.tile_base;
+        t = __shfl_sync(kFullMask, t, 0);
+        if (t >= blocks) break;
+        const unsigned long long base = t * 32ull;
         const unsigned long long i = base + lane;
         const bool active = i < count;
         float4 o = make_float4(0.f, 0.f, 0.f, 0.f), d = make_float4(0.f, 0.f, 1.f, 0.f);
@@ -162,7 +166,10 @@ cudaError_t launch_trace_rays(const TraceParams& P, const vrt_ray* rays, vrt_ray
     if (grid > blocks_needed) grid = (unsigned)blocks_needed;
     if (P.brick_dim == 4) trace_rays_kernel<4><<<grid, kTunedThreads, 0, stream>>>(P, reinterpret_cast<const float4*>(rays), reinterpret_cast<uint4*>(hits), count);
     else trace_rays_kernel<0><<<grid, kTunedThreads, 0, stream>>>(P, reinterpret_cast<const float4*>(rays), reinterpret_cast<uint4*>(hits), count);
-    if (info) info->launches++;
+    if (info) {
+        info->launches++;
+        info->counter_advance = warps_needed + (unsigned long long)grid * (kTunedThreads / 32);  // every warp overshoots once
+    }
     return cudaGetLastError();
 }
 

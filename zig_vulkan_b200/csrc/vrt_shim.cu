@@ -750,6 +750,7 @@ int vrt_trace_rays(vrt_ctx* ctx, const vrt_ray* rays_device, vrt_ray_hit* hits_d
         ctx->accel_dirty = false;
     }
     VRT_CUDA(ctx, launch_trace_rays(P, rays_device, hits_device, count, ctx->stream, &info));
+    ctx->tile_base += info.counter_advance;
     ctx->last_launches = info.launches;
     return VRT_OK;
 }
