@@ -251,3 +251,26 @@ def test_degenerate_direction_is_a_miss(one_voxel):
     assert not hit and a["grid_steps"] == 0
     img, _, cnt = sc.render(scenes.camera(1, 1), scenes.sun(True))  # u = 0/0 (:168)
     assert cnt["hits"] == 0 and tuple(img[0, 0]) == (0, 0, 0, 255)
+
+
+def test_insert_sequence_semantics_hand_computed():
+    """Grid.insert (brick/Grid.zig:129-194) by hand: bricks are numbered in order of first insertion (fetchAdd :147), each new
+    brick takes the next 64-entry material block (MaterialAllocator.zig:34-43), a voxel inserted twice keeps the last material
+    (:173-175), occupancy bits accumulate (:180-182).  These are the semantics vrt_insert_voxels must reproduce on the device."""
+    g = orc.OracleGrid((2, 2, 2), brick_dim=4)  # 8^3 voxels
+    # y is flipped (:135): voxel y = 7 is brick row 0.  Insert into brick cell (1,0,0) first, then (0,0,0), then (1,0,0) again.
+    assert g.insert(4, 7, 0, 11) == 0   # cell 1 -> brick 0, voxel 0
+    assert g.insert(0, 7, 0, 22) == 0   # cell 0 -> brick 1, voxel 0
+    assert g.insert(5, 7, 0, 33) == 0   # cell 1 (brick 0), voxel 1
+    assert g.insert(4, 7, 0, 44) == 0   # same voxel as the first insert: overwrites 11
+    assert g.insert(0, 0, 4, 55) == 0   # y = 0 -> flipped 7 -> brick row 1, z = 4 -> brick z 1: cell 0 + 2*(1 + 2*1) = 6 -> brick 2
+    assert g.active_bricks == 3
+    assert list(g.brick_indices) == [1, 0, 0, 0, 0, 0, 2, 0]
+    assert g.statuses[0] == 0b01000011
+    assert list(g.start_indices[:3]) == [0, 64, 128] and (g.start_indices[3:] == 0xFFFFFFFF).all()
+    assert g.occupancy[0] == 0b00000011 and g.occupancy[8] == 0b00000001   # brick 0: voxels 0 and 1; brick 1: voxel 0
+    # brick 2: x = 0, z = 4 % 4 = 0, flipped y = 7 % 4 = 3 -> voxel 0 + 4*(0 + 4*3) = 48 -> byte 6, bit 0
+    assert g.occupancy[16 + 6] == 0b00000001
+    mi = g.material_indices
+    assert mi[0] == 44 and mi[1] == 33 and mi[64] == 22 and mi[128 + 48] == 55
+    assert g.insert(8, 0, 0, 1) == -1  # outside the grid (:130-132)
