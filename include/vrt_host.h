@@ -180,6 +180,26 @@ int vrt_vox_insert_into_grid(const vrt_vox* v, int32_t model, vrt_grid* grid, ui
 #define VRT_BENCH_PATH_POINTS 11
 void vrt_bench_path_pose(float t, float extent_scale, float origin_out[3], float yaw_wxyz_out[4]);
 
+/* Benchmark (Benchmark.zig:22-139): drives a camera along that path by accumulated frame time and keeps the frame-time report.
+ * duration_s = 60 is the reference's benchmark_duration; extent_scale as above. */
+typedef struct vrt_benchmark vrt_benchmark;
+typedef struct vrt_benchmark_report { /* Benchmark.Report + what Report.print logs (:103-139) */
+    float min_frame_ms, max_frame_ms, avg_frame_ms;
+    uint32_t frames;
+    uint32_t voxel_dim[3];
+    uint32_t sun_enabled;
+    uint32_t image_width, image_height;
+    int32_t max_bounce, samples_per_pixel;
+} vrt_benchmark_report;
+vrt_benchmark* vrt_benchmark_create(vrt_hcam* camera, const vrt_grid* grid /* nullable */, int sun_enabled, float duration_s, float extent_scale);
+void vrt_benchmark_destroy(vrt_benchmark* b);
+/* Benchmark.update: advance by one frame of dt seconds (moves the camera); returns 1 once the path has completed. */
+int vrt_benchmark_update(vrt_benchmark* b, float dt);
+void vrt_benchmark_get_report(const vrt_benchmark* b, vrt_benchmark_report* out);
+/* The reference's benchmark mode (main.zig: VoxelRT.createBenchmark + update per frame): draw frames along the path, each
+ * frame's measured wall time (enqueue + device + sync) is the next dt, until the path completes. */
+int vrt_renderer_run_benchmark(vrt_renderer* r, float duration_s, float extent_scale, vrt_benchmark_report* out);
+
 #ifdef __cplusplus
 }
 #endif

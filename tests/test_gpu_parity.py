@@ -402,3 +402,21 @@ def test_explicit_rays_match_oracle_grid_hit(materials):
     with pytest.raises(ffi.VrtError):
         ctx.trace_rays_device(d_rays.data_ptr() + 4, d_hits.data_ptr(), 1)  # misaligned
     ctx.close()
+
+
+def test_renderer_benchmark_mode(materials):
+    """The reference's benchmark mode (Benchmark.zig + main.zig) through the Renderer facade: frames along the fly-through, each
+    frame's wall time feeds the next update; the report is consistent and the last pose still renders like the oracle."""
+    grid = scenes.build_grid(64)
+    r = ffi.Renderer(grid, width=160, height=90, samples_per_pixel=1, max_bounce=0, sun_enabled=True, sun_radius=0.0, sun_animate=False)
+    r.push_materials(materials)
+    r.update_grid_delta()
+    rep = r.run_benchmark(duration_s=0.05, extent_scale=1.0)
+    assert rep.frames >= 2
+    assert 0.0 < rep.min_frame_ms <= rep.avg_frame_ms <= rep.max_frame_ms
+    assert rep.avg_frame_ms * rep.frames >= 50.0 * 0.999  # the path completes when the frame times add up to the duration
+    assert list(rep.voxel_dim) == [64, 64, 64] and rep.sun_enabled == 1 and (rep.image_width, rep.image_height) == (160, 90)
+    img = r.draw_to_host()
+    ref, _, _ = orc.OracleScene.from_grid(grid, materials).render(r.camera.device, r.sun.device)
+    assert np.array_equal(img, ref)
+    r.close()

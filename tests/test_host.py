@@ -188,3 +188,37 @@ def test_bench_path():
     o2, _ = zv.bench_path_pose(1.5 / 11, 2.0)
     assert o2 == pytest.approx([5, 10, 5], abs=1e-4)
     assert len(scenes.sweep_poses(11)) == 11
+
+
+def test_benchmark_follows_the_reference_update_rule():
+    """Benchmark.init / update / Report (Benchmark.zig:22-101): fixed dt frames over the 60 s path."""
+    cam = ffi.HostCamera(75.0, 64, 36, origin=(9.0, 9.0, 9.0), samples_per_pixel=1, max_bounce=0)
+    grid = ffi.Grid((4, 2, 3))
+    b = ffi.Benchmark(cam, grid, sun_enabled=True)
+    assert list(cam.device.origin) == [0.0, 0.0, 0.0]              # init: origin = path_points[0] (:28)
+    assert not b.update(60.0 / 11 * 1.5)                            # halfway between way points 1 and 2 (:50-56)
+    assert list(cam.device.origin) == pytest.approx([2.5, 5.0, 2.5], abs=1e-4)
+    o_ref, q_ref = zv.bench_path_pose(1.5 / 11)
+    assert list(cam.device.origin) == pytest.approx(o_ref, abs=1e-5)
+    llc = list(cam.device.lower_left_corner)
+    cam.translate(1.0, (1.0, 0.0, 0.0))                             # input is disabled while benchmarking (:27)
+    assert list(cam.device.lower_left_corner) == llc
+    frames = 1
+    while not b.update(0.5):
+        frames += 1
+        assert frames < 1000
+    frames += 1
+    rep = b.report
+    assert rep.frames == frames
+    assert rep.min_frame_ms == pytest.approx(500.0) and rep.max_frame_ms == pytest.approx(60.0 / 11 * 1.5 * 1000.0, rel=1e-5)
+    assert rep.avg_frame_ms == pytest.approx((60.0 / 11 * 1.5 + 0.5 * (frames - 1)) / frames * 1000.0, rel=1e-4)
+    assert list(rep.voxel_dim) == [16, 8, 12] and rep.sun_enabled == 1
+    assert (rep.image_width, rep.image_height, rep.max_bounce, rep.samples_per_pixel) == (64, 36, 1, 1)
+    # the last eleventh of the path keeps the pose the previous segment ended with (:51,:59): close to the last way point
+    assert list(cam.device.origin) == pytest.approx([0.0, 13.0, 0.0], abs=2.2)  # within one 0.5 s frame of the end of the segment
+    b.close()
+    short = ffi.Benchmark(cam, None, sun_enabled=False, duration_s=1.0, extent_scale=2.0)
+    assert short.update(0.25) is False and short.update(0.8) is True
+    assert list(short.report.voxel_dim) == [0, 0, 0] and short.report.sun_enabled == 0
+    with pytest.raises(ValueError):
+        ffi.Benchmark(cam, None, duration_s=0.0)

@@ -116,6 +116,15 @@ struct vrt_hcam {
     vrt_camera d_camera;
 };
 
+struct vrt_benchmark {  // Benchmark.zig:11-20 + Report (:81-101)
+    vrt_hcam* camera;
+    bool sun_enabled;
+    float timer, duration, fraction, extent_scale;
+    float min_dt, max_dt, dt_sum;
+    uint32_t samples;
+    uint32_t voxel_dim[3];
+};
+
 struct vrt_hsun {
     vrt_sun device_data;
     bool animate;

@@ -4,6 +4,8 @@
 #include <cstring>
 #include <new>
 
+#include <chrono>
+
 #include "vrt_host_internal.h"
 
 struct vrt_renderer {
@@ -162,6 +164,26 @@ int vrt_renderer_present_to_host(vrt_renderer* r, const vrt_denoise_params* para
     rc = pass(r, vrt_denoise(r->ctx, params ? params : &defaults, out_width, out_height, flags));
     if (rc != VRT_OK) return rc;
     return pass(r, vrt_read_denoised(r->ctx, host, bytes));
+}
+
+// main.zig's benchmark mode: `while (!benchmark.update(dt)) draw`, dt = the frame's wall time
+int vrt_renderer_run_benchmark(vrt_renderer* r, float duration_s, float extent_scale, vrt_benchmark_report* out) {
+    if (!r || !out) return VRT_E_INVALID;
+    vrt_benchmark* b = vrt_benchmark_create(r->camera, r->grid, r->sun->device_data.enabled != 0u, duration_s, extent_scale);
+    if (!b) return VRT_E_INVALID;
+    int rc = VRT_OK;
+    for (;;) {
+        const auto t0 = std::chrono::steady_clock::now();
+        rc = pass(r, vrt_trace(r->ctx, &r->camera->d_camera, &r->sun->device_data));
+        if (rc == VRT_OK) rc = pass(r, vrt_sync(r->ctx));
+        if (rc != VRT_OK) break;
+        const float dt = std::chrono::duration<float>(std::chrono::steady_clock::now() - t0).count();
+        if (vrt_benchmark_update(b, dt)) break;
+    }
+    vrt_benchmark_get_report(b, out);
+    vrt_benchmark_destroy(b);
+    vrt_hcam_enable_input(r->camera);
+    return rc;
 }
 
 }  // extern "C"

@@ -6,7 +6,10 @@
 // y in [h/2, h) with grass/dirt/rock bands by height, water up to an ocean level, plus a few metal spheres so
 // every material type is on screen — using 32-bit integer arithmetic only, so the same voxels come out on every
 // compiler and CPU.
+#include <cmath>
 #include <cstring>
+#include <limits>
+#include <new>
 
 #include "vrt_host_internal.h"
 
@@ -45,6 +48,13 @@ struct Sphere {
 int emit_to_grid(void* user, uint32_t x, uint32_t y, uint32_t z, uint8_t material) {
     return vrt_grid_insert(static_cast<vrt_grid*>(user), x, y, z, material);
 }
+
+// Benchmark.Configuration (Benchmark.zig:141-173)
+constexpr float kBenchDuration = 60.0f;
+const Vec3 kBenchPoints[VRT_BENCH_PATH_POINTS] = {{0, 0, 0},      {2, 5, 0},      {3, 5, 5},      {5, 2, 1},    {10, 0, 10}, {20, -20, 20},
+                                                  {10, -25, 15}, {10, -22, 20}, {10, -30, 25}, {5, -10, 10}, {0, 13, 0}};
+const Vec3 kBenchEulers[VRT_BENCH_PATH_POINTS] = {{0, 0, 0},    {0, 45, 0},   {10, -20, 0}, {20, 180, 0}, {50, 90, 0}, {60, 0, 0},
+                                                  {80, -10, 0}, {75, -40, 0}, {80, -10, 0}, {80, -90, 0}, {0, -145, 0}};
 
 }  // namespace
 
@@ -129,26 +139,77 @@ int vrt_scene_synthetic_fill(vrt_grid* g, uint32_t seed) {
 // timer = t * benchmark_duration: way points lerp, orientations lerp (the reference lerps the quaternions without
 // renormalising; Camera.orientation normalises afterwards).
 void vrt_bench_path_pose(float t, float extent_scale, float origin_out[3], float yaw_wxyz_out[4]) {
-    static const Vec3 points[VRT_BENCH_PATH_POINTS] = {{0, 0, 0},      {2, 5, 0},      {3, 5, 5},      {5, 2, 1},    {10, 0, 10}, {20, -20, 20},
-                                                       {10, -25, 15}, {10, -22, 20}, {10, -30, 25}, {5, -10, 10}, {0, 13, 0}};
-    static const Vec3 eulers[VRT_BENCH_PATH_POINTS] = {{0, 0, 0},    {0, 45, 0},   {10, -20, 0}, {20, 180, 0}, {50, 90, 0}, {60, 0, 0},
-                                                       {80, -10, 0}, {75, -40, 0}, {80, -10, 0}, {80, -90, 0}, {0, -145, 0}};
     if (t < 0.0f) t = 0.0f;
     if (t > 1.0f) t = 1.0f;
-    const float duration = 60.0f;
+    const float duration = kBenchDuration;
     const float timer = t * duration;
     const float fraction = duration / (float)VRT_BENCH_PATH_POINTS;  // path_point_fraction == path_orientation_fraction
     size_t index = (size_t)std::floor(timer / fraction);
-    Vec3 origin = points[VRT_BENCH_PATH_POINTS - 1];
-    Quat yaw = from_euler(eulers[VRT_BENCH_PATH_POINTS - 1]);
+    Vec3 origin = kBenchPoints[VRT_BENCH_PATH_POINTS - 1];
+    Quat yaw = from_euler(kBenchEulers[VRT_BENCH_PATH_POINTS - 1]);
     if (index < VRT_BENCH_PATH_POINTS - 1) {
         const float pos = std::fmod(timer, fraction) / fraction;
-        origin = lerp(points[index], points[index + 1], pos);
-        const Quat l = index == 0 ? kIdentity : from_euler(eulers[index]);
-        yaw = qlerp(l, from_euler(eulers[index + 1]), pos);
+        origin = lerp(kBenchPoints[index], kBenchPoints[index + 1], pos);
+        const Quat l = index == 0 ? kIdentity : from_euler(kBenchEulers[index]);
+        yaw = qlerp(l, from_euler(kBenchEulers[index + 1]), pos);
     }
     if (origin_out) origin_out[0] = origin.x * extent_scale, origin_out[1] = origin.y * extent_scale, origin_out[2] = origin.z * extent_scale;
     if (yaw_wxyz_out) yaw_wxyz_out[0] = yaw.w, yaw_wxyz_out[1] = yaw.x, yaw_wxyz_out[2] = yaw.y, yaw_wxyz_out[3] = yaw.z;
+}
+
+// Benchmark.init (Benchmark.zig:22-44)
+vrt_benchmark* vrt_benchmark_create(vrt_hcam* camera, const vrt_grid* grid, int sun_enabled, float duration_s, float extent_scale) {
+    if (!camera || !(duration_s > 0.0f)) return nullptr;
+    vrt_benchmark* b = new (std::nothrow) vrt_benchmark();
+    if (!b) return nullptr;
+    b->camera = camera, b->sun_enabled = sun_enabled != 0, b->timer = 0.0f, b->duration = duration_s, b->extent_scale = extent_scale;
+    b->fraction = duration_s / (float)VRT_BENCH_PATH_POINTS;  // path_point_fraction == path_orientation_fraction (:23-24)
+    b->min_dt = std::numeric_limits<float>::max(), b->max_dt = 0.0f, b->dt_sum = 0.0f, b->samples = 0;  // Report.init (:88-101)
+    b->voxel_dim[0] = b->voxel_dim[1] = b->voxel_dim[2] = 0;
+    if (grid) b->voxel_dim[0] = grid->state.voxel_dim_x, b->voxel_dim[1] = grid->state.voxel_dim_y, b->voxel_dim[2] = grid->state.voxel_dim_z;
+    vrt_hcam_disable_input(camera);  // :27
+    const float origin[3] = {kBenchPoints[0].x * extent_scale, kBenchPoints[0].y * extent_scale, kBenchPoints[0].z * extent_scale};
+    const float yaw[4] = {1.0f, 0.0f, 0.0f, 0.0f};
+    vrt_hcam_set_origin(camera, origin);             // :28
+    vrt_hcam_set_orientation(camera, yaw, nullptr);  // :30-32 yaw = orientations[0] = identity, pitch = identity
+    return b;
+}
+
+void vrt_benchmark_destroy(vrt_benchmark* b) { delete b; }
+
+// Benchmark.update (Benchmark.zig:47-75): returns 1 when the fly-through has completed
+int vrt_benchmark_update(vrt_benchmark* b, float dt) {
+    if (!b) return 1;
+    b->timer += dt;
+    const size_t index = (size_t)std::floor(b->timer / b->fraction);  // same index for points and orientations
+    if (index < VRT_BENCH_PATH_POINTS - 1) {                           // the last segment keeps the pose it ended with (:51,:59)
+        const float pos = std::fmod(b->timer, b->fraction) / b->fraction;
+        const Vec3 o = lerp(kBenchPoints[index], kBenchPoints[index + 1], pos);
+        const float origin[3] = {o.x * b->extent_scale, o.y * b->extent_scale, o.z * b->extent_scale};
+        const Quat l = index == 0 ? kIdentity : from_euler(kBenchEulers[index]);
+        const Quat q = qlerp(l, from_euler(kBenchEulers[index + 1]), pos);  // lerp without renormalising, as upstream (:63)
+        const float yaw[4] = {q.w, q.x, q.y, q.z};
+        vrt_hcam_set_origin(b->camera, origin);
+        vrt_hcam_set_orientation(b->camera, yaw, nullptr);
+    }
+    if (dt < b->min_dt) b->min_dt = dt;  // :69-72
+    if (dt > b->max_dt) b->max_dt = dt;
+    b->dt_sum += dt;
+    b->samples += 1;
+    return b->timer >= b->duration ? 1 : 0;
+}
+
+// Benchmark.Report (Benchmark.zig:81-139) as numbers instead of a log line
+void vrt_benchmark_get_report(const vrt_benchmark* b, vrt_benchmark_report* out) {
+    if (!b || !out) return;
+    out->min_frame_ms = b->samples ? b->min_dt * 1000.0f : 0.0f;
+    out->max_frame_ms = b->max_dt * 1000.0f;
+    out->avg_frame_ms = b->samples ? b->dt_sum / (float)b->samples * 1000.0f : 0.0f;
+    out->frames = b->samples;
+    for (int i = 0; i < 3; i++) out->voxel_dim[i] = b->voxel_dim[i];
+    out->sun_enabled = b->sun_enabled ? 1u : 0u;
+    out->image_width = b->camera->d_camera.image_width, out->image_height = b->camera->d_camera.image_height;
+    out->max_bounce = b->camera->d_camera.max_bounce, out->samples_per_pixel = b->camera->d_camera.samples_per_pixel;
 }
 
 }  // extern "C"

@@ -70,6 +70,12 @@ class DenoiseParams(C.Structure):  # GraphicsPipeline.zig:27-32 (PushConstant); 
 VRT_DENOISE_BGRA = 1
 
 
+class BenchmarkReport(C.Structure):  # Benchmark.Report + what Report.print logs (Benchmark.zig:81-139)
+    _fields_ = [("min_frame_ms", C.c_float), ("max_frame_ms", C.c_float), ("avg_frame_ms", C.c_float), ("frames", C.c_uint32),
+                ("voxel_dim", C.c_uint32 * 3), ("sun_enabled", C.c_uint32), ("image_width", C.c_uint32), ("image_height", C.c_uint32),
+                ("max_bounce", C.c_int32), ("samples_per_pixel", C.c_int32)]
+
+
 class Material(C.Structure):  # gpu_types.zig:16-32
     _fields_ = [("type", C.c_uint32), ("albedo_r", C.c_float), ("albedo_g", C.c_float), ("albedo_b", C.c_float), ("type_data", C.c_float)]
 
@@ -238,6 +244,11 @@ VRT_HOST_SYMBOLS = {
     "vrt_vox_materials": (C.c_uint32, [_P, _P, C.c_uint32, C.c_uint32]),
     "vrt_vox_insert_into_grid": (C.c_int, [_P, C.c_int32, _P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]),
     "vrt_bench_path_pose": (None, [C.c_float, C.c_float, C.POINTER(C.c_float * 3), C.POINTER(C.c_float * 4)]),
+    "vrt_benchmark_create": (_P, [_P, _P, C.c_int, C.c_float, C.c_float]),
+    "vrt_benchmark_destroy": (None, [_P]),
+    "vrt_benchmark_update": (C.c_int, [_P, C.c_float]),
+    "vrt_benchmark_get_report": (None, [_P, C.POINTER(BenchmarkReport)]),
+    "vrt_renderer_run_benchmark": (C.c_int, [_P, C.c_float, C.c_float, C.POINTER(BenchmarkReport)]),
 }
 
 
@@ -294,6 +305,37 @@ def bench_path_pose(t: float, extent_scale: float = 1.0):
     q = (C.c_float * 4)()
     host_lib().vrt_bench_path_pose(t, extent_scale, C.byref(o), C.byref(q))
     return list(o), list(q)
+
+
+class Benchmark:
+    """Benchmark (voxel_rt/Benchmark.zig): moves a HostCamera along the reference's fly-through by accumulated frame time."""
+
+    def __init__(self, camera: "HostCamera", grid: "Grid | None" = None, sun_enabled: bool = True, duration_s: float = 60.0, extent_scale: float = 1.0):
+        self._h = host_lib()
+        self.camera = camera
+        self.handle = self._h.vrt_benchmark_create(camera.handle, grid.handle if grid is not None else None, int(sun_enabled), duration_s, extent_scale)
+        if not self.handle:
+            raise ValueError("vrt_benchmark_create rejected its arguments")
+
+    def update(self, dt: float) -> bool:
+        return bool(self._h.vrt_benchmark_update(self.handle, dt))
+
+    @property
+    def report(self) -> BenchmarkReport:
+        r = BenchmarkReport()
+        self._h.vrt_benchmark_get_report(self.handle, C.byref(r))
+        return r
+
+    def close(self):
+        if self.handle:
+            self._h.vrt_benchmark_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 VOX_ERRORS = {-10: "InvalidId", -11: "ExpectedSizeHeader", -12: "ExpectedXyziHeader", -13: "ExpectedRgbaHeader", -14: "UnexpectedVersion",
@@ -794,6 +836,12 @@ class Renderer:
             out = np.empty((self.height, self.width, 4), dtype=np.uint8)
         self._check(self._h.vrt_renderer_draw_to_host(self.handle, _ptr(out), out.nbytes))
         return out
+
+    def run_benchmark(self, duration_s: float = 60.0, extent_scale: float = 1.0) -> BenchmarkReport:
+        """The reference's benchmark mode: frames along the fly-through until `duration_s` of frame time has accumulated."""
+        rep = BenchmarkReport()
+        self._check(self._h.vrt_renderer_run_benchmark(self.handle, duration_s, extent_scale, C.byref(rep)))
+        return rep
 
     def present_to_host(self, out_width: int | None = None, out_height: int | None = None, params: "DenoiseParams | None" = None, flags: int = 0) -> np.ndarray:
         """Pipeline.draw's graphics half: draw, then image.frag into an (out_height, out_width, 4) image."""
