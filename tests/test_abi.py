@@ -42,6 +42,17 @@ def test_material_layout():
     assert ffi.Material.type_data.offset == 16
 
 
+def test_denoise_push_constant_layout():
+    # GraphicsPipeline.PushConstant (GraphicsPipeline.zig:27-32): i32 + 3 x f32 = 16 bytes, pushed as one block
+    assert C.sizeof(ffi.DenoiseParams) == 16
+    assert [ffi.DenoiseParams.samples.offset, ffi.DenoiseParams.distribution_bias.offset, ffi.DenoiseParams.pixel_multiplier.offset,
+            ffi.DenoiseParams.inverse_hue_tolerance.offset] == [0, 4, 8, 12]
+    d = ffi.DenoiseParams.default()  # GraphicsPipeline.Config defaults (:34-39)
+    assert (d.samples, round(d.distribution_bias, 3), d.pixel_multiplier, d.inverse_hue_tolerance) == (20, 0.6, 1.5, 20.0)
+    assert C.sizeof(ffi.BenchmarkReport) == 48
+    assert ffi.RAY_DTYPE.itemsize == 32 and ffi.RAY_HIT_DTYPE.itemsize == 32  # explicit-ray mode: two 128-bit words each
+
+
 def test_aov_and_config_layout():
     assert C.sizeof(ffi.Aov) == 64 and ffi.AOV_DTYPE.itemsize == 64
     assert C.sizeof(ffi.Counters) == 64
