@@ -102,3 +102,18 @@ def test_no_silent_cpu_fallback(has_cuda):
     with pytest.raises(ffi.VrtError) as e:
         ffi.Context(16, 16, 64)
     assert e.value.code == -4 and "no CPU fallback" in str(e.value)
+
+
+def test_headers_are_plain_c(tmp_path):
+    """The drop-in boundary is a C ABI: both public headers must compile as C99 (no C++ constructs, no torch types)."""
+    import shutil
+    import subprocess
+
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "include/vrt.h"\n#include "include/vrt_host.h"\n'
+                   'int main(void) { vrt_config c; vrt_denoise_params p = {20, 0.6f, 1.5f, 20.0f}; (void)c; (void)p; return 0; }\n')
+    r = subprocess.run([cc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", ROOT, str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
