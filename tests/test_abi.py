@@ -117,3 +117,22 @@ def test_headers_are_plain_c(tmp_path):
                    'int main(void) { vrt_config c; vrt_denoise_params p = {20, 0.6f, 1.5f, 20.0f}; (void)c; (void)p; return 0; }\n')
     r = subprocess.run([cc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", ROOT, str(src)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_c_example_builds_and_fails_loudly_without_a_gpu(tmp_path, has_cuda):
+    """examples/render_frame.c (plain C99 against both libraries) compiles and links; without a CUDA device it must stop with
+    the library's own error — there is no CPU path to fall back to."""
+    import shutil
+    import subprocess
+
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    pkg = os.path.join(ROOT, "zig_vulkan_b200")
+    exe = str(tmp_path / "render_frame")
+    r = subprocess.run([cc, "-std=c99", "-O1", "-Wall", "-Wextra", "-Werror", "-I", ROOT, os.path.join(ROOT, "examples", "render_frame.c"), "-L", pkg,
+                        "-lvrt_host", "-lvrt", "-Wl,-rpath," + pkg, "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    if not has_cuda:
+        run = subprocess.run([exe, "64", str(tmp_path / "f")], capture_output=True, text=True, timeout=120)
+        assert run.returncode != 0 and "no CPU fallback" in run.stderr
