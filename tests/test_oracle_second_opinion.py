@@ -160,7 +160,7 @@ def grid_hit(sc, origin, direction):  # CreateRay + GridHit(r, 0.00001, infinity
     return False, None
 
 
-@pytest.mark.parametrize("brick_dim,n_voxels", [(4, 64), (8, 64)])
+@pytest.mark.parametrize("brick_dim,n_voxels", [(4, 64), (8, 64), (16, 128)])
 def test_second_reading_of_the_shader_agrees_with_the_oracle(materials, brick_dim, n_voxels):
     grid = scenes.build_grid(n_voxels, brick_dim=brick_dim)
     mine = Scene(grid, materials)
