@@ -119,31 +119,44 @@ def alloc_for(wl):
 
 
 def time_oracle(wl, steps, warmup, budget_s=None):
+    """Full frames of the workload on the host cores.  With oracle/_ref present (the reference's own shader text compiled by g++,
+    oracle/ref_shim/) that library is what is timed — kind "reference"; its frame is checked against the hand-written oracle's
+    once, outside the timed region.  Otherwise the oracle port is timed — kind "port"."""
+    import numpy as np
     from zig_vulkan_b200 import scenes
+    from oracle import ref
 
     grid, mats, sc = oracle_scene(wl)
     cam = scenes.camera(wl.width, wl.height, **POSE0)
     sun = scenes.sun(wl.sun)
     cores = os.cpu_count() or 1
-    rays = None
+    img, _, cnt = sc.render(cam, sun, threads=cores)
+    rays = cnt["rays"]  # the shader has no counters: rays cast = pixels + one sun ray per primary hit, as the oracle counts them
+    kind = "port"
+    render = lambda: sc.render(cam, sun, threads=cores)
+    if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_shader.so" if wl.brick_dim <= 8 else "libref_shader_wide.so")):
+        rimg, _ = ref.render(sc, cam, sun, threads=cores)
+        if not np.array_equal(rimg, img):
+            raise SystemExit("bench.py: oracle/_ref (the reference's shader text) and the oracle disagree on this frame")
+        kind = "reference"
+        render = lambda: ref.render(sc, cam, sun, threads=cores)
     for _ in range(warmup):
-        _, _, cnt = sc.render(cam, sun, threads=cores)
-        rays = cnt["rays"]
+        render()
     times = []
     t_begin = time.perf_counter()
     for _ in range(steps):
         t0 = time.perf_counter()
-        _, _, cnt = sc.render(cam, sun, threads=cores)
+        render()
         times.append(time.perf_counter() - t0)
-        rays = cnt["rays"]
         if budget_s is not None and time.perf_counter() - t_begin > budget_s:
             break
-    return rays, times, cores
+    return rays, times, cores, kind
 
 
 def run_reference(args):
-    """The reference's own algorithm on the host cores.  The reference ships this path only as a GLSL compute shader
-    and nothing of it builds here (no zig / glslc / Vulkan), so this is the oracle port, all host threads."""
+    """The reference's own implementation of the path on the host cores: its compute shader (brick_raytracer.comp + rand.comp)
+    compiled by g++ under oracle/ref_shim/ (oracle/_ref, kind "reference"), all host threads, one invocation per pixel.  Falls
+    back to the oracle port (kind "port") only if oracle/_ref was not built."""
     from zig_vulkan_b200 import scenes
 
     rank = int(os.environ.get("RANK", "0"))
@@ -151,15 +164,16 @@ def run_reference(args):
         return
     wl = scenes.WORKLOADS[args.workload]
     steps = min(args.steps, 60)
-    rays, times, cores = time_oracle(wl, steps, min(args.warmup, 3), budget_s=150.0)
+    rays, times, cores, kind = time_oracle(wl, steps, min(args.warmup, 3), budget_s=150.0)
     total = sum(times)
     value = rays * len(times) / total / 1e6
     line = {
         "impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": len(times), "warmup": min(args.warmup, 3),
         "ms_per_step": total / len(times) * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": {"workload": f"{wl.name}: {wl.description}", "pose": "pose0", "rays_per_step": rays},
-        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": "port",
-                         "sample": f"{len(times)} full {wl.width}x{wl.height} frames, all rows, oracle/liboracle.so with {cores} threads"},
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": kind,
+                         "sample": f"{len(times)} full {wl.width}x{wl.height} frames, all rows, "
+                                   + ("oracle/_ref/libref_shader.so (the reference's shader text, g++)" if kind == "reference" else "oracle/liboracle.so") + f" with {cores} threads"},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -406,10 +420,12 @@ def main():
             line["explicit_rays"] = {"rays": n_pixels, "ms": er_ms, "mrays_s": n_pixels / (er_ms * 1e-3) / 1e6, "ray_io_gb_s": 64 * n_pixels / (er_ms * 1e-3) / 1e9,
                                      "note": "primary rays only, ordered in 8x4-pixel tiles; 32 B ray in + 32 B hit record out per ray, 128-bit loads / stores"}
         if world == 1 and not args.no_cpu_baseline:
-            crays, ctimes, cores = time_oracle(wl, 12, 1, budget_s=20.0)
+            crays, ctimes, cores, kind = time_oracle(wl, 12, 1, budget_s=20.0)
             best = min(ctimes)
-            line["cpu_baseline"] = {"value": crays / best / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
-                                    "sample": f"best of {len(ctimes)} full {W}x{H} frames of the same workload, oracle/liboracle.so, {cores} threads"}
+            line["cpu_baseline"] = {"value": crays / best / 1e6, "unit": "Mrays/s", "cores": cores, "kind": kind,
+                                    "sample": f"best of {len(ctimes)} full {W}x{H} frames of the same workload, "
+                                              + ("oracle/_ref/libref_shader.so = the reference's shader text compiled by g++" if kind == "reference" else "oracle/liboracle.so")
+                                              + f", {cores} threads"}
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:

@@ -1,7 +1,7 @@
 """ctypes wrapper of the CPU oracle (oracle/liboracle.so).  TEST INFRASTRUCTURE, NOT PRODUCT.
 
 Only tests/, __graft_entry__.smoke() and bench.py (cpu_baseline leg / --impl reference) may import this module.
-PARITY UNPINNED: see oracle/vrt_oracle.h.
+Parity is pinned to the reference's shader text through oracle/_ref (oracle/ref.py, tests/test_ref_shader.py); see oracle/vrt_oracle.h.
 """
 from __future__ import annotations
 

@@ -8,8 +8,9 @@
  *   src/modules/voxel_rt/brick/Grid.zig, brick/MaterialAllocator.zig.
  * Every function cites the reference lines it follows (paths relative to /root/reference).
  *
- * PARITY UNPINNED — see vrt_oracle.h: the reference has no CPU path, no tests and no golden output for this
- * code and cannot run here, so this file is checked against hand-computed known-answer tests only.
+ * PARITY PINNED — see vrt_oracle.h: the reference has no CPU path, no tests and no golden output for this code, but its
+ * shader text compiles under oracle/ref_shim/ (oracle/_ref/libref_shader.so) and tests/test_ref_shader.py holds this file to
+ * it bit for bit, on top of the hand-computed known-answer tests (tests/test_oracle_kat.py).
  *
  * FP discipline (GLSL leaves these implementation-defined; the CUDA kernels are held to the same choices):
  *   - FP32 everywhere; literals are float (GLSL literals are FP32).

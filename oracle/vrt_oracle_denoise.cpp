@@ -9,7 +9,8 @@
  *     (GraphicsPipeline.zig:27-39, defaults 20 / 0.6 / 1.5 / 20),
  *   - output = one B8G8R8A8_UNORM swapchain texel per fragment (swapchain.zig:235), alpha 1.
  *
- * PARITY UNPINNED (see vrt_oracle.h): no CPU path, golden image or test exists upstream for this pass either.
+ * PARITY PINNED (see vrt_oracle.h): no CPU path, golden image or test exists upstream for this pass either, but image.frag itself
+ * compiles under oracle/ref_shim/ and tests/test_ref_shader.py::test_present_pass_matches_reference_text holds this file to it bit for bit.
  *
  * Choices where GLSL / Vulkan leave the arithmetic to the implementation (the CUDA kernel is held to the same ones):
  *   - inUV of the fragment at output pixel (x, y) = ((x + 0.5) / out_width, (y + 0.5) / out_height).

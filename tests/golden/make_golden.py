@@ -1,8 +1,10 @@
 """Regenerates tests/golden/*.npz from the CPU oracle.  Run from the repo root: python tests/golden/make_golden.py
 
-PARITY UNPINNED: the reference has no executable form of this path here (GLSL only; no zig/glslc/Vulkan), so these
-vectors freeze the ORACLE's output (itself checked by the hand-computed cases in tests/test_oracle_kat.py).  They guard
-against regressions of the oracle and give the GPU tests fixed targets that do not depend on the host CPU.
+The vectors are what the REFERENCE'S OWN SHADER TEXT computes: every case is rendered twice — by the hand-written oracle and
+by oracle/_ref/libref_shader.so (brick_raytracer.comp + rand.comp / image.frag compiled by g++, oracle/ref_shim/) — and the
+script refuses to write a file unless the two agree bit for bit (RGBA8 and primary hit records).  The oracle supplies the
+extra AOV fields (cell / voxel indices, step counters) the shader does not output.  /root/reference does not travel to the
+GPU box, these files do.
 """
 import os
 import sys
@@ -39,10 +41,27 @@ def render_case(case):
     return grid, cam, sun, img, aov, cnt
 
 
+def check_against_reference_text(case, img, aov):
+    """The same case through the reference's shader text (oracle/_ref): must be identical."""
+    from oracle import ref
+
+    n, bd, w, h, sun_on, radius, spp, bounce, pose = case
+    grid = scenes.build_grid(n, brick_dim=bd)
+    sc = orc.OracleScene.from_grid(grid, zv.terrain_materials())
+    rimg, hits = ref.render(sc, scenes.camera(w, h, spp=spp, max_bounce=bounce, **pose), scenes.sun(sun_on, radius), hits=True)
+    hit = (aov["flags"] & 1) != 0
+    ok = np.array_equal(rimg, img) and np.array_equal(hit, hits["hit"] != 0) and np.array_equal(aov["material"][hit], hits["index"][hit])
+    for f in ("t", "point", "normal"):
+        ok = ok and np.array_equal(aov[f].view(np.uint32)[hit], hits[f].view(np.uint32)[hit])
+    if not ok:
+        raise SystemExit("make_golden: the oracle and the reference's shader text disagree — nothing written")
+
+
 def main():
     out_dir = os.path.dirname(os.path.abspath(__file__))
     for name, case in CASES.items():
         _, _, _, img, aov, cnt = render_case(case)
+        check_against_reference_text(case, img, aov)
         np.savez_compressed(os.path.join(out_dir, name + ".npz"), rgba=img, aov=aov, counters=np.array([cnt[k] for k in orc.COUNTER_NAMES], dtype=np.uint64))
         print(name, cnt)
     make_denoise_golden(out_dir)
@@ -50,7 +69,12 @@ def main():
 
 def make_denoise_golden(out_dir):
     """The present pass (image.frag) over the traced c1 frame: same size RGBA, and a 1.5x BGRA target."""
+    from oracle import ref
+
     _, _, _, img, _, _ = render_case(CASES["c1_64_256x256"])
+    if not (np.array_equal(ref.present(img), orc.denoise(img)) and
+            np.array_equal(ref.present(img, out_width=384, out_height=216, flags=1), orc.denoise(img, out_width=384, out_height=216, flags=1))):
+        raise SystemExit("make_golden: the denoise oracle and image.frag disagree — nothing written")
     np.savez_compressed(os.path.join(out_dir, "denoise_c1_64_256x256.npz"), traced=img, denoised=orc.denoise(img),
                         denoised_384x216_bgra=orc.denoise(img, out_width=384, out_height=216, flags=1))
 

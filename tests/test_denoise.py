@@ -1,7 +1,7 @@
 """The present pass (assets/shaders/image.frag:31-79): oracle known-answer tests on the CPU, CUDA-vs-oracle parity on the GPU.
 
-The reference has no test, golden image or CPU form of this shader (parity unpinned, oracle/vrt_oracle_denoise.cpp), so the
-oracle is pinned by (i) an independent float64 numpy transcription of the shader written here, compared at +-1 LSB (the two
+The reference has no test, golden image or CPU form of this shader; image.frag itself, compiled under oracle/ref_shim/, pins the
+oracle bit for bit (tests/test_ref_shader.py).  Independently of that the oracle is checked here by (i) an independent float64 numpy transcription of the shader written here, compared at +-1 LSB (the two
 differ in pow / rounding at the 1e-6 level, which can move a value across a rounding boundary), (ii) closed-form cases, and
 (iii) a committed golden frame.  The GPU gate is bit-exact: same FP32 operations in the same order on both sides."""
 import os

@@ -1,7 +1,7 @@
 """A second, independent restatement of GridHit / BrickHit / AdvNormIntersect (assets/shaders/brick_raytracer.comp:267-471,
 :493-536), written in Python straight from the GLSL — numpy float32 scalars for every operation, an exact rational fma — and
 compared ray by ray with the C++ oracle (oracle/vrt_oracle.cpp).  The reference has no executable form of this path here
-(parity unpinned), so this does not pin the oracle to the reference; it pins it to a second reading of the shader in another
+(the shader text itself, compiled under oracle/ref_shim/, is what pins the oracle: tests/test_ref_shader.py); this is a second reading of the shader in another
 language with another arithmetic implementation, which is what catches slips of the C++ restatement."""
 from fractions import Fraction
 
