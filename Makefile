@@ -26,7 +26,10 @@ $(CSRC)/vrt_denoise.o: $(CSRC)/vrt_denoise.cu $(KERNEL_HDRS)
 $(CSRC)/vrt_build.o: $(CSRC)/vrt_build.cu $(KERNEL_HDRS)
 	$(NVCC) $(NVCCFLAGS) -c -o $@ $< 2> $(CSRC)/vrt_build.ptxas.log || (cat $(CSRC)/vrt_build.ptxas.log; false)
 
-$(PKG)/libvrt.so: $(CSRC)/vrt_kernels.o $(CSRC)/vrt_shim.o $(CSRC)/vrt_denoise.o $(CSRC)/vrt_build.o
+$(CSRC)/vrt_sched.o: $(CSRC)/vrt_sched.cu $(KERNEL_HDRS)
+	$(NVCC) $(NVCCFLAGS) -c -o $@ $< 2> $(CSRC)/vrt_sched.ptxas.log || (cat $(CSRC)/vrt_sched.ptxas.log; false)
+
+$(PKG)/libvrt.so: $(CSRC)/vrt_kernels.o $(CSRC)/vrt_shim.o $(CSRC)/vrt_denoise.o $(CSRC)/vrt_build.o $(CSRC)/vrt_sched.o
 	$(NVCC) -gencode arch=compute_100a,code=sm_100a -shared -o $@ $^ -ldl
 
 $(PKG)/libvrt_host.so: $(wildcard $(CSRC)/host/*.cpp) $(wildcard $(CSRC)/host/*.h) include/vrt.h include/vrt_host.h $(PKG)/libvrt.so

@@ -21,7 +21,8 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-POSE0 = dict(origin=(0.0, -10.0, 28.0), euler_deg=(25.0, 0.0, 0.0))
+POSE0 = dict(origin=(0.0, -10.0, 28.0), euler_deg=(25.0, 0.0, 0.0))   # the headline pose: 25 deg down onto the terrain, ~52 % of the pixels hit
+POSE_SURVEY = dict(origin=(0.0, -8.0, 0.0), euler_deg=(0.0, 0.0, 0.0))  # SURVEY.md 8(d)'s "pose 0": level view from above the grid centre
 L2_FLUSH_BYTES = 144 << 20  # > 126 MB L2
 
 
@@ -34,10 +35,13 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--exchange", default="auto", choices=["auto", "allgather", "peer", "peerflags"],
                     help="N > 1: fused peer stores from the trace kernel (frame barrier = NCCL 4-byte all-reduce, or peer flag words: "
-                         "peerflags), or an NCCL all-gather after it; auto = peerflags up to 4 GPUs, all-gather above (measured: profiles/README.md)")
+                         "peerflags), or an NCCL all-gather after it; auto = every combination of exchange and schedule is timed for a few "
+                         "frames on this box and the fastest one runs the timed region")
+    ap.add_argument("--schedule", default="auto", choices=["auto", "static", "lpt", "deal"],
+                    help="tile order: static bottom-up, cost-sorted (longest first), or cost-sorted and dealt across the ranks (peer exchange modes)")
     ap.add_argument("--partition", default="interleave", choices=["interleave", "slab"], help="N > 1: 4-row strips round-robin, or one row slab per rank")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--sweep", action="store_true", help="N = 1: also time the 11 way points of the reference's benchmark fly-through (Benchmark.zig:141-173)")
+    ap.add_argument("--no-extras", action="store_true", help="only the headline measurement (no sweep / REF / C5 / denoise / explicit rays / edit frames)")
     ap.add_argument("--baseline-kernel", action="store_true", help="time the reference-shape kernel instead of the tuned one")
     return ap.parse_args()
 
@@ -179,6 +183,236 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+class Rig:
+    """Per-process plumbing: device, stream, L2 flush buffer, rank barrier."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist, self.args = torch, dist, args
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.stream = torch.cuda.Stream(self.dev)  # a non-default stream: handle 0 would mean "restore the ctx's own stream"
+        torch.cuda.set_stream(self.stream)         # torch.cuda.Event only sees torch's current stream
+        self.flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=self.dev)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
+
+    def reduce(self, values, op="max"):
+        t = self.torch.tensor(values, dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX if op == "max" else self.dist.ReduceOp.SUM)
+        return [float(v) for v in t]
+
+    def make_ctx(self, grid, mats, W, H, brick_dim=4, flags=0, solo=False):
+        """A context on the bench stream with the grid uploaded; world > 1 (and not solo): this rank's part of the frame, NCCL
+        communicator, peer mappings — every exchange mode selectable afterwards."""
+        from zig_vulkan_b200 import ffi
+
+        dist, torch = self.dist, self.torch
+        multi = self.world > 1 and not solo
+        interleave = multi and self.args.partition == "interleave" and not self.args.baseline_kernel
+        if multi and not interleave and H % self.world != 0:
+            raise SystemExit(f"image height {H} is not divisible by {self.world} ranks")
+        rows = (self.rank * (H // self.world), (self.rank + 1) * (H // self.world)) if (multi and not interleave) else (0, 0)
+        ctx = ffi.Context(W, H, len(grid.brick_indices), brick_dim=brick_dim, n_brick_alloc=grid.brick_alloc, device=self.local_rank, flags=flags, rows=rows,
+                          part=(self.rank, self.world) if interleave else None)
+        ctx.set_stream(self.stream.cuda_stream)
+        ctx.upload_grid(grid, mats)
+        ctx.interleaved = interleave
+        if multi:
+            if self.rank == 0:
+                uid = torch.frombuffer(bytearray(ffi.Context.comm_unique_id()), dtype=torch.uint8).to(self.dev)
+            else:
+                uid = torch.empty(ffi.VRT_NCCL_ID_BYTES, dtype=torch.uint8, device=self.dev)
+            dist.broadcast(uid, 0)
+            ctx.comm_init(self.rank, self.world, bytes(uid.cpu().numpy().tobytes()))
+            mine = torch.frombuffer(bytearray(ctx.comm_ipc_handle()), dtype=torch.uint8).to(self.dev)
+            allh = [torch.empty_like(mine) for _ in range(self.world)]
+            dist.all_gather(allh, mine)
+            ctx.comm_open_peers(self.rank, self.world, b"".join(bytes(h.cpu().numpy().tobytes()) for h in allh))
+        return ctx
+
+    def timed(self, ctx, cam, sun, steps, warmup):
+        """`steps` frames after `warmup`, L2 flushed before each (outside the per-step events).  Returns the per-step device times
+        (ms, CUDA events on the launching stream) and the wall time of the region."""
+        torch = self.torch
+        self.barrier()  # ranks enter the first exchanged frame together
+        for i in range(warmup):
+            self.flush.fill_(i & 0xFF)
+            ctx.trace(cam, sun)
+        self.barrier()
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        t0 = time.perf_counter()
+        for i in range(steps):
+            self.flush.fill_(i & 0xFF)
+            starts[i].record(self.stream)
+            ctx.trace(cam, sun)
+            ends[i].record(self.stream)
+        self.barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        return [s.elapsed_time(e) for s, e in zip(starts, ends)], wall_ms
+
+    def set_mode(self, ctx, exchange, schedule, interval=8):
+        from zig_vulkan_b200 import ffi
+
+        if self.world > 1:
+            ctx.comm_set_exchange({"allgather": ffi.VRT_EXCHANGE_ALLGATHER, "peer": ffi.VRT_EXCHANGE_PEER_STORE, "peerflags": ffi.VRT_EXCHANGE_PEER_FLAGS}[exchange])
+        ctx.set_schedule({"static": ffi.VRT_SCHED_STATIC, "lpt": ffi.VRT_SCHED_LPT, "deal": ffi.VRT_SCHED_DEAL}[schedule], interval)
+
+    def choose_mode(self, ctx, cam, sun):
+        """Exchange x schedule by measurement on this box: each candidate runs 4 + 12 flushed frames, the smallest max-over-ranks mean wins."""
+        args = self.args
+        if args.baseline_kernel:
+            return ("allgather" if self.world > 1 else "none", "static"), {}
+        exchanges = (["allgather", "peerflags", "peer"] if args.exchange == "auto" else [args.exchange]) if self.world > 1 else ["none"]
+        cands = []
+        for ex in exchanges:
+            for sc in (["static", "lpt", "deal"] if args.schedule == "auto" else [args.schedule]):
+                if sc == "deal" and (self.world == 1 or ex == "allgather" or not ctx.interleaved):
+                    continue  # dealing needs a peer exchange (a rank's tiles are scattered over the image) and is pointless on one GPU
+                cands.append((ex, sc))
+        if not cands:
+            raise SystemExit("no exchange / schedule combination fits these options")
+        if len(cands) == 1:
+            self.set_mode(ctx, *cands[0])
+            return cands[0], {}
+        table = {}
+        for ex, sc in cands:
+            self.set_mode(ctx, ex, sc)
+            ms, _ = self.timed(ctx, cam, sun, 12, 4)
+            table[f"{ex}/{sc}"] = self.reduce([sum(ms) / len(ms)])[0]
+        best = min(table, key=table.get)
+        ex, sc = best.split("/")
+        self.set_mode(ctx, ex, sc)
+        return (ex, sc), table
+
+
+def stats(ms):
+    s = sorted(ms)
+    return {"min": s[0], "median": s[len(s) // 2], "max": s[-1], "mean": sum(s) / len(s)}
+
+
+def frame_counters(rig, grid, mats, W, H, brick_dim, cam, sun):
+    """Rays cast and the request-byte model of the whole frame (identical to the oracle's counters, tests/test_golden.py): the
+    reference-shape kernel with VRT_FLAG_AOV on this GPU."""
+    from zig_vulkan_b200 import ffi
+
+    cctx = ffi.Context(W, H, len(grid.brick_indices), brick_dim=brick_dim, n_brick_alloc=grid.brick_alloc, device=rig.local_rank, flags=ffi.VRT_FLAG_AOV | ffi.VRT_FLAG_BASELINE)
+    cctx.upload_grid(grid, mats)
+    cctx.trace(cam, sun)
+    c = cctx.counters()
+    cctx.close()
+    brick_bytes = brick_dim ** 3 // 8
+    c["alg_bytes"] = 4 * W * H + 4 * c["status_fetches"] + (4 + brick_bytes) * c["bricks_entered"] + 25 * c["hits"]
+    return c
+
+
+def measure(rig, grid, mats, W, H, brick_dim, cam, sun, steps, warmup, with_e2e=True):
+    """One workload at this world size: mode selection, the timed region, per-rank kernel / exchange split, frame CRC against the
+    single-GPU frame, end-to-end through host buffers."""
+    import zlib
+
+    import numpy as np
+    torch, dist = rig.torch, rig.dist
+    world, rank = rig.world, rig.rank
+    n_pixels = W * H
+    flags = 0
+    if rig.args.baseline_kernel:
+        from zig_vulkan_b200 import ffi
+        flags = ffi.VRT_FLAG_BASELINE
+    ctx = rig.make_ctx(grid, mats, W, H, brick_dim, flags)
+    (exchange, schedule), table = rig.choose_mode(ctx, cam, sun)
+
+    step_ms, wall_ms = rig.timed(ctx, cam, sun, steps, max(warmup, 3))
+    launches_per_step = ctx.last_trace_launches()
+    total_ms = rig.reduce([sum(step_ms)])[0]  # max over ranks of the summed device time
+    step_max = rig.reduce(step_ms)            # per-step max over ranks
+
+    # where the time goes: (rebuild +) trace kernel alone vs the exchange behind it, per rank (a short separate loop that reads the
+    # ctx's own events after every frame; not part of `value`)
+    kms, xms = [], []
+    for i in range(3 + 16):
+        rig.flush.fill_(i & 0xFF)
+        ctx.trace(cam, sun)
+        if i >= 3:
+            k, t = ctx.last_trace_kernel_ms(), ctx.last_trace_ms()
+            kms.append(k), xms.append(t - k)
+    my_kernel = sum(kms) / len(kms)
+    my_exch = sum(xms) / len(xms)
+    kmax, xmax = rig.reduce([my_kernel, my_exch])
+    kmin = -rig.reduce([-my_kernel])[0]
+
+    # the frame itself: identical on every rank, identical to one GPU tracing it alone
+    img = ctx.read_framebuffer()
+    crc = zlib.crc32(img.tobytes())
+    crcs = [crc]
+    if world > 1:
+        t = torch.tensor([crc], dtype=torch.int64, device=rig.dev)
+        out = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        crcs = [int(o[0]) for o in out]
+    solo_crc = None
+    if rank == 0:
+        if world > 1:
+            solo = rig.make_ctx(grid, mats, W, H, brick_dim, flags, solo=True)
+            solo_crc = zlib.crc32(solo.trace_to_host(cam, sun).tobytes())
+            solo.close()
+        else:
+            solo_crc = crc
+
+    res = {"ctx": ctx, "exchange": exchange, "schedule": schedule, "candidates_ms": table, "step_ms": step_ms, "step_max": step_max, "total_ms": total_ms,
+           "wall_ms": wall_ms, "launches_per_step": launches_per_step, "kernel_ms_max": kmax, "kernel_ms_min": kmin, "exchange_ms": xmax,
+           "crc": {"value": f"{crc:08x}", "all_ranks_equal": len(set(crcs)) == 1, "equals_single_gpu_frame": (solo_crc == crc) if rank == 0 else None}}
+    if not with_e2e:
+        return res
+
+    # ---------------------------------------------------------------- end-to-end through the C ABI with host buffers
+    # (a) frame latency: vrt_trace_to_host per frame, blocking (camera+sun from host structs -> frame in pinned host memory)
+    host_frames = [torch.empty(n_pixels * 4, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    lat_s, n_lat = 0.0, min(steps, 50)
+    for i in range(3 + n_lat):
+        rig.flush.fill_(i & 0xFF)
+        rig.barrier()
+        t0 = time.perf_counter()
+        if rank == 0:
+            ctx.trace_to_host(cam, sun, out_ptr=host_frames[0].data_ptr())
+        else:
+            ctx.trace(cam, sun)
+            ctx.sync()
+        if world > 1:
+            dist.barrier()
+        if i >= 3:
+            lat_s += time.perf_counter() - t0
+    # (b) frame throughput: the same call pipelined (vrt_trace_to_host_async, 2 frames in flight: the copy of frame k overlaps the
+    # trace of frame k+1).  The L2 flush is enqueued between frames INSIDE the timed region.  Rank 0 receives the frames on its
+    # host; the other ranks take part in the same frame ring without a host copy.
+    for i in range(4):
+        ctx.trace_to_host_async(cam, sun, host_frames[i & 1].data_ptr() if rank == 0 else None)
+    ctx.sync()
+    rig.barrier()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        rig.flush.fill_(i & 0xFF)
+        ctx.trace_to_host_async(cam, sun, host_frames[i & 1].data_ptr() if rank == 0 else None)
+    ctx.sync()
+    rig.barrier()
+    e2e_s = rig.reduce([time.perf_counter() - t0])[0]
+    res["e2e_s"], res["latency_ms"] = e2e_s, lat_s / n_lat * 1e3
+    res["e2e_frame_ok"] = bool(np.array_equal(host_frames[(steps - 1) & 1].numpy().reshape(H, W, 4), img)) if rank == 0 else None
+    return res
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
@@ -196,240 +430,260 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
                "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
     import numpy as np
     import torch
-    import torch.distributed as dist
 
     import zig_vulkan_b200 as zv
     from zig_vulkan_b200 import ffi, scenes
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the trace path has no CPU fallback (use --impl reference for the host-core baseline)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
-    if args.exchange == "auto":
-        args.exchange = "peerflags" if world <= 4 else "allgather"
+    rig = Rig(args)
+    rank, dev, stream = rig.rank, rig.dev, rig.stream
     wl = scenes.WORKLOADS[args.workload]
     W, H = wl.width, wl.height
-    interleave = world > 1 and args.partition == "interleave" and not args.baseline_kernel
-    if not interleave and H % world != 0:
-        raise SystemExit(f"image height {H} is not divisible by {world} ranks")
-    rows = (rank * (H // world), (rank + 1) * (H // world)) if (world > 1 and not interleave) else (0, 0)
-    part = (rank, world) if interleave else None
     n_pixels = W * H
-
     grid = scenes.build_grid(wl.n_voxels, wl.brick_dim, brick_alloc=alloc_for(wl))
     mats = zv.terrain_materials()
     cam = scenes.camera(W, H, **POSE0)
     sun = scenes.sun(wl.sun)
-    brick_bytes = wl.brick_dim ** 3 // 8
 
-    flags = ffi.VRT_FLAG_BASELINE if args.baseline_kernel else 0
-    ctx = ffi.Context(W, H, len(grid.brick_indices), brick_dim=wl.brick_dim, n_brick_alloc=grid.brick_alloc, device=local_rank, flags=flags,
-                      rows=rows, part=part)
-    stream = torch.cuda.Stream(dev)  # a non-default stream: handle 0 would mean "restore the ctx's own stream"
-    torch.cuda.set_stream(stream)
-    ctx.set_stream(stream.cuda_stream)  # torch.cuda.Event only sees torch's current stream
-    ctx.upload_grid(grid, mats)
-
-    if world > 1:
-        if rank == 0:
-            uid = torch.frombuffer(bytearray(ffi.Context.comm_unique_id()), dtype=torch.uint8).to(dev)
-        else:
-            uid = torch.empty(ffi.VRT_NCCL_ID_BYTES, dtype=torch.uint8, device=dev)
-        dist.broadcast(uid, 0)
-        ctx.comm_init(rank, world, bytes(uid.cpu().numpy().tobytes()))
-        if args.exchange in ("peer", "peerflags"):
-            mine = torch.frombuffer(bytearray(ctx.comm_ipc_handle()), dtype=torch.uint8).to(dev)
-            allh = [torch.empty_like(mine) for _ in range(world)]
-            dist.all_gather(allh, mine)
-            ctx.comm_open_peers(rank, world, b"".join(bytes(h.cpu().numpy().tobytes()) for h in allh))
-            ctx.comm_set_exchange(ffi.VRT_EXCHANGE_PEER_STORE if args.exchange == "peer" else ffi.VRT_EXCHANGE_PEER_FLAGS)
-
-    # ray / request-byte counters of this rank's rows (identical to the oracle's, tests/test_golden.py): the reference-shape
-    # kernel for slabs, the tuned kernel's counting variant for interleaved strips
-    cctx = ffi.Context(W, H, len(grid.brick_indices), brick_dim=wl.brick_dim, n_brick_alloc=grid.brick_alloc, device=local_rank,
-                       flags=ffi.VRT_FLAG_AOV | (0 if interleave else ffi.VRT_FLAG_BASELINE), rows=rows, part=part)
-    cctx.upload_grid(grid, mats)
-    cctx.trace(cam, sun)
-    counters = cctx.counters()
-    cctx.close()
-    my_rays = counters["rays"]
-    my_rows = (sum(min(4, H - t * 4) for t in range(rank, (H + 3) // 4, world)) if interleave else (rows[1] - rows[0] if world > 1 else H))
-    my_alg_bytes = 4 * my_rows * W + 4 * counters["status_fetches"] + (4 + brick_bytes) * counters["bricks_entered"] + 25 * counters["hits"]
-
-    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    # ---------------------------------------------------------------- device-resident timing
-    barrier()  # ranks enter the first exchanged frame together (set-up time differs from rank to rank)
-    for _ in range(max(args.warmup, 3)):
-        flush.fill_(1)
-        ctx.trace(cam, sun)
-    launches_per_step = ctx.last_trace_launches()
-    barrier()
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(rig.local_rank)
     sampler.start()
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    t_wall0 = time.perf_counter()
-    for i in range(args.steps):
-        flush.fill_(i & 0xFF)  # L2 flush between timed iterations (outside the per-step events)
-        starts[i].record(stream)
-        ctx.trace(cam, sun)
-        ends[i].record(stream)
-    barrier()
-    wall_ms = (time.perf_counter() - t_wall0) * 1e3
+    m = measure(rig, grid, mats, W, H, wl.brick_dim, cam, sun, args.steps, args.warmup)
     clocks = sampler.stop()
-    step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
-    total_ms = float(sum(step_ms))
-
-    # ---------------------------------------------------------------- end-to-end through the C ABI with host buffers
-    # (a) frame latency: vrt_trace_to_host per frame, blocking (camera+sun from host structs -> frame in pinned host memory)
-    host_frames = [torch.empty(n_pixels * 4, dtype=torch.uint8).pin_memory() for _ in range(2)]
-    lat_s = 0.0
-    n_lat = min(args.steps, 50)
-    for i in range(3 + n_lat):
-        flush.fill_(i & 0xFF)
-        barrier()
-        t0 = time.perf_counter()
-        if rank == 0:
-            ctx.trace_to_host(cam, sun, out_ptr=host_frames[0].data_ptr())
-        else:
-            ctx.trace(cam, sun)
-            ctx.sync()
-        if world > 1:
-            dist.barrier()
-        if i >= 3:
-            lat_s += time.perf_counter() - t0
-    # (b) frame throughput: the same call pipelined (vrt_trace_to_host_async, 2 frames in flight: the copy of frame k
-    # overlaps the trace of frame k+1).  The L2 flush is enqueued between frames INSIDE the timed region.
-    # Rank 0 receives the frames on its host; the other ranks take part in the same frame ring without a host copy.
-    for i in range(4):
-        ctx.trace_to_host_async(cam, sun, host_frames[i & 1].data_ptr() if rank == 0 else None)
-    ctx.sync()
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        flush.fill_(i & 0xFF)
-        ctx.trace_to_host_async(cam, sun, host_frames[i & 1].data_ptr() if rank == 0 else None)
-    ctx.sync()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-
-    t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev)
-    r = torch.tensor([float(my_rays), float(my_alg_bytes)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(r, op=dist.ReduceOp.SUM)
-    total_ms, e2e_s = float(t[0]), float(t[1])
-    rays, alg_bytes = float(r[0]), float(r[1])
-
+    ctx = m["ctx"]
+    line = None
     if rank == 0:
+        cnt = frame_counters(rig, grid, mats, W, H, wl.brick_dim, cam, sun)
+        rays, alg_bytes = cnt["rays"], cnt["alg_bytes"]
         peak, peak_kind = peaks()
-        ms_per_step = total_ms / args.steps
+        ms_per_step = m["total_ms"] / args.steps
         value = rays / (ms_per_step * 1e-3) / 1e6
-        # roofline of the dominant kernel = the trace kernel; at N=1 the step IS that one launch
-        achieved = (my_alg_bytes / (ms_per_step * 1e-3)) / 1e9
-        traffic = None
+        # roofline of the dominant kernel = the trace kernel (at N = 1 the step IS that one launch; at N > 1 each rank's launch
+        # covers 1/N of the frame's algorithmic bytes and `kernel_ms` is the slowest rank's)
+        kernel_ms = ms_per_step if world == 1 else m["kernel_ms_max"]
+        achieved = (alg_bytes / world / (kernel_ms * 1e-3)) / 1e9
+        prof = {}
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                traffic = json.load(f).get(args.workload)
+                prof = json.load(f).get(args.workload) or {}
         except Exception:
             pass
+        if not isinstance(prof, dict):
+            prof = {"dram_bytes": prof}
+        issue = None
+        if prof.get("warp_instructions") and world == 1:
+            # the bound this kernel actually runs against: one warp instruction per scheduler per cycle, 4 schedulers x 148 SMs
+            sm_mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965
+            floor_ms = prof["warp_instructions"] / (148 * 4 * sm_mhz * 1e6) * 1e3
+            issue = {"bound": "issue", "warp_instructions": prof["warp_instructions"], "floor_ms": floor_ms, "frac": floor_ms / kernel_ms, "sm_mhz": sm_mhz,
+                     "source": prof.get("source"), "note": "instruction count from the committed ncu capture of this command; clock sampled live"}
         line = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
                 "workload": f"{wl.name}: {wl.description}", "pose": "pose0 origin (0,-10,28) pitch 25deg", "rays_per_step": int(rays),
                 "grid_bricks": len(grid.brick_indices), "active_bricks": grid.active_bricks, "l2": f"flushed between steps ({L2_FLUSH_BYTES >> 20} MiB fill)",
-                "kernel": "baseline" if args.baseline_kernel else "tuned", "partition": (f"4-row strips round-robin over {world} ranks" if interleave else f"{world} row slabs") if world > 1 else "whole frame",
-                "exchange": args.exchange if world > 1 else "none",
+                "kernel": "baseline" if args.baseline_kernel else "tuned",
+                "partition": ("4-row strips round-robin" if ctx.interleaved else "row slabs") + f" over {world} ranks" if world > 1 else "whole frame",
+                "exchange": m["exchange"], "schedule": m["schedule"], "mode_candidates_ms": m["candidates_ms"],
             },
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "peak_kind": peak_kind, "algorithmic_bytes_per_launch": int(my_alg_bytes), "kernel_ms": ms_per_step,
-                         "note": "request-byte model of the reference algorithm (DESIGN.md); rank 0's launch"},
-            "e2e": {"value": rays * args.steps / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 128, "d2h_bytes_per_step": n_pixels * 4,
-                    "ms_per_step": e2e_s / args.steps * 1e3, "frame_latency_ms": lat_s / n_lat * 1e3,
+            "step_ms": stats(m["step_max"]),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": prof.get("dram_bytes"),
+                         "traffic_source": prof.get("source"), "peak_kind": peak_kind, "algorithmic_bytes_per_launch": int(alg_bytes // world), "kernel_ms": kernel_ms,
+                         "note": "request-byte model of the reference algorithm (DESIGN.md); DRAM is ~0.3 % busy — the kernel is issue-bound, see `issue`",
+                         "issue": issue},
+            "e2e": {"value": rays * args.steps / m["e2e_s"] / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 128, "d2h_bytes_per_step": n_pixels * 4,
+                    "ms_per_step": m["e2e_s"] / args.steps * 1e3, "frame_latency_ms": m["latency_ms"], "frame_ok": m["e2e_frame_ok"],
                     "how": "vrt_trace_to_host_async per frame (camera+sun host structs in, RGBA8 frame into pinned host memory, 2 frames in flight), "
                            "L2 flush enqueued between frames inside the timed region; frame_latency_ms = blocking vrt_trace_to_host"},
-            "gpu_launches": launches_per_step * args.steps, "wall_ms": wall_ms, "clocks": clocks,
+            "gpu_launches": m["launches_per_step"] * args.steps, "wall_ms": m["wall_ms"], "clocks": clocks,
+            "frame_crc": m["crc"],
         }
-        if world == 1 and args.sweep:
-            # the reference's own benchmark camera path (offsets are in its world units; our world has the same 64-unit extent)
-            per_pose = []
-            for origin, yaw in scenes.sweep_poses(11):
-                pcam = scenes.camera_from_pose(W, H, origin, yaw)
-                cctx = ffi.Context(W, H, len(grid.brick_indices), brick_dim=wl.brick_dim, n_brick_alloc=grid.brick_alloc, device=local_rank,
-                                   flags=ffi.VRT_FLAG_AOV)
-                cctx.upload_grid(grid, mats)
-                cctx.trace(pcam, sun)
-                prays = cctx.counters()["rays"]
-                cctx.close()
-                ms = []
-                for i in range(3 + 20):
-                    flush.fill_(i & 0xFF)
-                    ctx.trace(pcam, sun)
-                    if i >= 3:
-                        ms.append(ctx.last_trace_ms())
-                per_pose.append({"origin": [round(v, 3) for v in origin], "rays": prays, "ms": sum(ms) / len(ms), "mrays_s": prays / (sum(ms) / len(ms) * 1e-3) / 1e6})
-            line["sweep"] = {"poses": per_pose, "mean_mrays_s": sum(p["mrays_s"] for p in per_pose) / len(per_pose),
-                             "total_mrays_s": sum(p["rays"] for p in per_pose) / sum(p["ms"] * 1e-3 for p in per_pose) / 1e6}
-        if world == 1:
-            # the step after the path: the reference's present pass (image.frag) over the traced frame, same resolution
-            dn = []
-            for i in range(3 + 20):
-                flush.fill_(i & 0xFF)
-                ctx._check(ctx._l.vrt_denoise(ctx.handle, ffi.DenoiseParams.default(), W, H, 0))
-                if i >= 3:
-                    dn.append(ctx.last_denoise_ms())
-            dn_ms = sum(dn) / len(dn)
-            line["denoise"] = {"ms_per_frame": dn_ms, "mpixels_s": n_pixels / (dn_ms * 1e-3) / 1e6, "params": "samples 20, bias 0.6, multiplier 1.5, tolerance 20 (GraphicsPipeline.zig:34-39)",
-                               "algorithmic_gb_s": 8 * n_pixels / (dn_ms * 1e-3) / 1e9, "bound": "ALU/FMA issue (21 samples x 2 pow per pixel), not HBM"}
-        if world == 1:
-            # explicit-ray mode (vrt_trace_rays): this camera's primary rays as a 32 B/ray device buffer in, 32 B/ray hit records out
-            jj, ii = np.meshgrid(np.arange(H, dtype=np.float32), np.arange(W, dtype=np.float32), indexing="ij")
-            u, v = (ii / np.float32(W - 1))[..., None], (jj / np.float32(H - 1))[..., None]
-            hor, ver, llc, org = (np.array(list(getattr(cam, f)), dtype=np.float32) for f in ("horizontal", "vertical", "lower_left_corner", "origin"))
-            d = (hor * u + llc) + (ver * v - org)
-            d = d / np.linalg.norm(d, axis=-1, keepdims=True)
-            if H % 4 == 0 and W % 8 == 0:  # 8x4-pixel tiles, tile after tile: 32 consecutive rays = one coherent tile (the caller chooses the order)
-                d = d.reshape(H // 4, 4, W // 8, 8, 3).transpose(0, 2, 1, 3, 4)[::-1]  # ground tiles first, like the pixel kernel
-            rays_np = np.zeros(n_pixels, dtype=ffi.RAY_DTYPE)
-            rays_np["origin"], rays_np["direction"] = org, d.reshape(-1, 3)
-            d_rays = torch.from_numpy(rays_np.view(np.uint8).reshape(-1)).to(dev)
-            d_hits = torch.zeros(n_pixels * 32, dtype=torch.uint8, device=dev)
-            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(3 + 20)]
-            for i, (a, b) in enumerate(ev):
-                flush.fill_(i & 0xFF)
-                a.record(stream)
-                ctx.trace_rays_device(d_rays.data_ptr(), d_hits.data_ptr(), n_pixels)
-                b.record(stream)
-            torch.cuda.synchronize(dev)
-            er_ms = sum(a.elapsed_time(b) for a, b in ev[3:]) / 20
-            line["explicit_rays"] = {"rays": n_pixels, "ms": er_ms, "mrays_s": n_pixels / (er_ms * 1e-3) / 1e6, "ray_io_gb_s": 64 * n_pixels / (er_ms * 1e-3) / 1e9,
-                                     "note": "primary rays only, ordered in 8x4-pixel tiles; 32 B ray in + 32 B hit record out per ray, 128-bit loads / stores"}
-        if world == 1 and not args.no_cpu_baseline:
-            crays, ctimes, cores, kind = time_oracle(wl, 12, 1, budget_s=20.0)
-            best = min(ctimes)
-            line["cpu_baseline"] = {"value": crays / best / 1e6, "unit": "Mrays/s", "cores": cores, "kind": kind,
-                                    "sample": f"best of {len(ctimes)} full {W}x{H} frames of the same workload, "
-                                              + ("oracle/_ref/libref_shader.so = the reference's shader text compiled by g++" if kind == "reference" else "oracle/liboracle.so")
-                                              + f", {cores} threads"}
+        if world > 1:
+            line["per_rank_kernel_ms"] = {"max": m["kernel_ms_max"], "min": m["kernel_ms_min"]}
+            line["exchange_ms"] = m["exchange_ms"]
+
+    extras = not args.no_extras and not args.baseline_kernel
+    if extras and args.workload == "C3":
+        # BASELINE config 5 beside it: the same scene at 3840x2160 (at N > 1: its own contexts, communicator and peer mappings)
+        ctx.close()
+        cam5 = scenes.camera(3840, 2160, **POSE0)
+        m5 = measure(rig, grid, mats, 3840, 2160, wl.brick_dim, cam5, sun, max(20, args.steps // 4), 5)
+        if rank == 0:
+            c5 = frame_counters(rig, grid, mats, 3840, 2160, wl.brick_dim, cam5, sun)
+            ms5 = m5["total_ms"] / max(20, args.steps // 4)
+            line["c5"] = {"workload": scenes.WORKLOADS["C5"].description, "rays_per_step": c5["rays"], "ms_per_step": ms5, "value": c5["rays"] / (ms5 * 1e-3) / 1e6,
+                          "unit": "Mrays/s", "step_ms": stats(m5["step_max"]), "exchange": m5["exchange"], "schedule": m5["schedule"], "mode_candidates_ms": m5["candidates_ms"],
+                          "per_rank_kernel_ms": {"max": m5["kernel_ms_max"], "min": m5["kernel_ms_min"]}, "exchange_ms": m5["exchange_ms"], "frame_crc": m5["crc"],
+                          "e2e": {"value": c5["rays"] * max(20, args.steps // 4) / m5["e2e_s"] / 1e6, "ms_per_step": m5["e2e_s"] / max(20, args.steps // 4) * 1e3,
+                                  "d2h_bytes_per_step": 3840 * 2160 * 4, "frame_ok": m5["e2e_frame_ok"]}}
+        m5["ctx"].close()
+        ctx = None
+    if rank == 0 and world == 1 and extras:
+        if ctx is None:
+            ctx = rig.make_ctx(grid, mats, W, H, wl.brick_dim)
+            rig.set_mode(ctx, "none", m["schedule"])
+        single_gpu_extras(rig, line, ctx, wl, grid, mats, cam, sun)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        crays, ctimes, cores, kind = time_oracle(wl, 12, 1, budget_s=20.0)
+        best = min(ctimes)
+        line["cpu_baseline"] = {"value": crays / best / 1e6, "unit": "Mrays/s", "cores": cores, "kind": kind,
+                                "sample": f"best of {len(ctimes)} full {W}x{H} frames of the same workload, "
+                                          + ("oracle/_ref/libref_shader.so = the reference's shader text compiled by g++" if kind == "reference" else "oracle/liboracle.so")
+                                          + f", {cores} threads"}
+    if rank == 0:
         print(json.dumps(line), flush=True)
-    ctx.close()
+    if ctx is not None:
+        ctx.close()
     if world > 1:
-        dist.destroy_process_group()
+        rig.barrier()
+        rig.dist.destroy_process_group()
+
+
+def single_gpu_extras(rig, line, ctx, wl, grid, mats, cam, sun):
+    """What sits around the headline, N = 1 only: the reference's own fly-through, the survey's pose, the reference application's
+    default configuration (general shading path), scene edits, the present pass, explicit rays."""
+    import numpy as np
+    import torch
+
+    import zig_vulkan_b200 as zv
+    from zig_vulkan_b200 import ffi, scenes
+
+    W, H = wl.width, wl.height
+    n_pixels = W * H
+    dev, stream, flush = rig.dev, rig.stream, rig.flush
+
+    def trace_ms(c, pcam, psun, n=20, warm=3):
+        ms = []
+        for i in range(warm + n):
+            flush.fill_(i & 0xFF)
+            c.trace(pcam, psun)
+            if i >= warm:
+                ms.append(c.last_trace_ms())
+        return ms
+
+    # ---- the reference's own benchmark camera path (Benchmark.zig:141-173; offsets are in its world units, our world has the same
+    # 64-unit extent) + the survey's pose 0.  Rays per pose from the counting kernel.
+    cctx = ffi.Context(W, H, len(grid.brick_indices), brick_dim=wl.brick_dim, n_brick_alloc=grid.brick_alloc, device=rig.local_rank, flags=ffi.VRT_FLAG_AOV | ffi.VRT_FLAG_BASELINE)
+    cctx.upload_grid(grid, mats)
+
+    def pose_record(pcam, label):
+        cctx.trace(pcam, sun)
+        prays = cctx.counters()["rays"]
+        ms = trace_ms(ctx, pcam, sun, n=24, warm=9)  # the schedule re-sorts every 8 frames: the first sort for this pose is inside the warm-up
+        mean = sum(ms) / len(ms)
+        return {"pose": label, "rays": prays, "ms": mean, "ms_min": min(ms), "mrays_s": prays / (mean * 1e-3) / 1e6}
+
+    per_pose = []
+    for origin, yaw in scenes.sweep_poses(11):
+        per_pose.append(pose_record(scenes.camera_from_pose(W, H, origin, yaw), [round(v, 3) for v in origin]))
+    line["sweep"] = {"what": "11 way points of the reference's benchmark fly-through (Benchmark.zig:141-173)", "poses": per_pose,
+                     "mean_mrays_s": sum(p["mrays_s"] for p in per_pose) / len(per_pose),
+                     "total_mrays_s": sum(p["rays"] for p in per_pose) / sum(p["ms"] * 1e-3 for p in per_pose) / 1e6,
+                     "mean_ms": sum(p["ms"] for p in per_pose) / len(per_pose)}
+    line["pose_survey"] = pose_record(scenes.camera(W, H, **POSE_SURVEY), "SURVEY 8(d) pose 0: origin (0,-8,0), yaw 0")
+    cctx.close()
+    ctx.trace(cam, sun)
+
+    # ---- the reference application's default configuration (main.zig:77-81,122-135; Sun.zig:4-11): general shading path
+    R = scenes.REF_DEFAULT
+    rgrid = scenes.build_ref_default_grid()
+    rcam = scenes.camera(R["width"], R["height"], spp=R["spp"], max_bounce=R["max_bounce"], origin=(0.0, -5.0, 14.0), euler_deg=(25.0, 0.0, 0.0))
+    rsun = scenes.sun(True, R["sun_radius"])
+    rc = ffi.Context(R["width"], R["height"], len(rgrid.brick_indices), device=rig.local_rank, flags=ffi.VRT_FLAG_AOV)
+    rc.upload_grid(rgrid, mats)
+    rc.trace(rcam, rsun)
+    rrays = rc.counters()["rays"]
+    rc.close()
+    rctx = ffi.Context(R["width"], R["height"], len(rgrid.brick_indices), device=rig.local_rank)
+    rctx.set_stream(stream.cuda_stream)
+    rctx.upload_grid(rgrid, mats)
+    rctx.set_schedule(ffi.VRT_SCHED_LPT, 8)
+    rms = trace_ms(rctx, rcam, rsun, n=24, warm=9)
+    # the same frame restricted to what the simple path covers (1 sample, no bounce, point sun), for the per-ray comparison
+    scam = scenes.camera(R["width"], R["height"], spp=1, max_bounce=0, origin=(0.0, -5.0, 14.0), euler_deg=(25.0, 0.0, 0.0))
+    sms = trace_ms(rctx, scam, scenes.sun(True, 0.0), n=24, warm=9)
+    sc = ffi.Context(R["width"], R["height"], len(rgrid.brick_indices), device=rig.local_rank, flags=ffi.VRT_FLAG_AOV | ffi.VRT_FLAG_BASELINE)
+    sc.upload_grid(rgrid, mats)
+    sc.trace(scam, scenes.sun(True, 0.0))
+    srays = sc.counters()["rays"]
+    sc.close()
+    rctx.close()
+    rmean, smean = sum(rms) / len(rms), sum(sms) / len(sms)
+    line["ref_default"] = {"workload": "reference default (main.zig:77-81,122-135): 128x64x128 bricks of 4^3 @0.5, 1024x576, spp 2, max_bounce 2, sun disc radius 5",
+                           "rays_per_step": rrays, "ms_per_step": rmean, "mrays_s": rrays / (rmean * 1e-3) / 1e6, "ns_per_ray": rmean * 1e6 / rrays,
+                           "simple_path_same_view": {"rays": srays, "ms": smean, "ns_per_ray": smean * 1e6 / srays},
+                           "general_over_simple_per_ray": (rmean / rrays) / (smean / srays)}
+
+    # ---- the step after the path: the reference's present pass (image.frag) over the traced frame, same resolution
+    dn = []
+    for i in range(3 + 20):
+        flush.fill_(i & 0xFF)
+        ctx._check(ctx._l.vrt_denoise(ctx.handle, ffi.DenoiseParams.default(), W, H, 0))
+        if i >= 3:
+            dn.append(ctx.last_denoise_ms())
+    dn_ms = sum(dn) / len(dn)
+    line["denoise"] = {"ms_per_frame": dn_ms, "mpixels_s": n_pixels / (dn_ms * 1e-3) / 1e6, "params": "samples 20, bias 0.6, multiplier 1.5, tolerance 20 (GraphicsPipeline.zig:34-39)",
+                       "algorithmic_gb_s": 8 * n_pixels / (dn_ms * 1e-3) / 1e9, "bound": "ALU/FMA issue (21 samples x 2 pow per pixel), not HBM"}
+
+    # ---- explicit-ray mode (vrt_trace_rays): this camera's primary rays as a 32 B/ray device buffer in, 32 B/ray hit records out
+    jj, ii = np.meshgrid(np.arange(H, dtype=np.float32), np.arange(W, dtype=np.float32), indexing="ij")
+    u, v = (ii / np.float32(W - 1))[..., None], (jj / np.float32(H - 1))[..., None]
+    hor, ver, llc, org = (np.array(list(getattr(cam, f)), dtype=np.float32) for f in ("horizontal", "vertical", "lower_left_corner", "origin"))
+    d = (hor * u + llc) + (ver * v - org)
+    d = d / np.linalg.norm(d, axis=-1, keepdims=True)
+    if H % 4 == 0 and W % 8 == 0:  # 8x4-pixel tiles, tile after tile: 32 consecutive rays = one coherent tile (the caller chooses the order)
+        d = d.reshape(H // 4, 4, W // 8, 8, 3).transpose(0, 2, 1, 3, 4)[::-1]  # ground tiles first, like the pixel kernel
+    rays_np = np.zeros(n_pixels, dtype=ffi.RAY_DTYPE)
+    rays_np["origin"], rays_np["direction"] = org, d.reshape(-1, 3)
+    d_rays = torch.from_numpy(rays_np.view(np.uint8).reshape(-1)).to(dev)
+    d_hits = torch.zeros(n_pixels * 32, dtype=torch.uint8, device=dev)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(3 + 20)]
+    for i, (a, b) in enumerate(ev):
+        flush.fill_(i & 0xFF)
+        a.record(stream)
+        ctx.trace_rays_device(d_rays.data_ptr(), d_hits.data_ptr(), n_pixels)
+        b.record(stream)
+    torch.cuda.synchronize(dev)
+    er_ms = sum(a.elapsed_time(b) for a, b in ev[3:]) / 20
+    line["explicit_rays"] = {"rays": n_pixels, "ms": er_ms, "mrays_s": n_pixels / (er_ms * 1e-3) / 1e6, "ray_io_gb_s": 64 * n_pixels / (er_ms * 1e-3) / 1e9,
+                             "note": "primary rays only, ordered in 8x4-pixel tiles; 32 B ray in + 32 B hit record out per ray, 128-bit loads / stores"}
+
+    # ---- scene edits between frames (VoxelRT.updateGridDelta, VoxelRT.zig:107-172): insert on the host grid, ship the five dirty
+    # ranges through the staging ring, trace.  Timed: vrt_trace's own events (rebuild of the derived structures + trace).
+    def ship_delta():
+        up = [ctx.upload_brick_statuses, ctx.upload_brick_indices, ctx.upload_brick_occupancy, ctx.upload_brick_start_indices, ctx.upload_material_indices]
+        arr = [grid.statuses, grid.brick_indices, grid.occupancy, grid.start_indices, grid.material_indices]
+        for which in range(5):
+            active, lo, hi = grid.delta(which)
+            if active:
+                up[which](lo, arr[which][lo:hi])
+                grid.delta_reset(which)
+
+    for which in range(5):
+        grid.delta_reset(which)
+    n = wl.n_voxels
+    rng = np.random.default_rng(1)
+    fresh = [(int(rng.integers(8, n - 8)), n - 8 - 4 * (k % 3), int(rng.integers(8, n - 8))) for k in range(12)]  # floating high above the terrain: empty bricks
+    t_in, t_new = [], []
+    for k in range(12):
+        flush.fill_(k)
+        x, y, z = fresh[k]
+        grid.insert(x, y, z, 7)  # a new brick: status bit + brick index change -> distance planes rebuilt
+        ship_delta()
+        ctx.trace(cam, sun)
+        t_new.append(ctx.last_trace_ms())
+        flush.fill_(k)
+        grid.insert(x, y, z - 1 if z % 4 else z + 1, 7)  # its neighbour voxel in the same brick: occupancy only
+        ship_delta()
+        ctx.trace(cam, sun)
+        t_in.append(ctx.last_trace_ms())
+    base = trace_ms(ctx, cam, sun, n=12, warm=2)
+    line["edit_frame_ms"] = {"no_edit": sum(base) / len(base), "voxel_in_loaded_brick": sum(t_in[2:]) / len(t_in[2:]), "voxel_in_new_brick": sum(t_new[2:]) / len(t_new[2:]),
+                             "what": "Grid.insert on the host, the five dirty ranges through the pinned staging ring, vrt_trace (rebuild of derived structures + trace kernel)"}
 
 
 if __name__ == "__main__":

@@ -238,8 +238,29 @@ int vrt_get_counters(vrt_ctx* ctx, vrt_counters* out);
 
 /* Milliseconds the device spent in the last vrt_trace (kernels + exchange), CUDA events on ctx's stream. */
 int vrt_last_trace_ms(vrt_ctx* ctx, float* out_ms);
+/* The part of it before the exchange: (derived-structure rebuild +) the trace kernel alone.  exchange = total - this. */
+int vrt_last_trace_kernel_ms(vrt_ctx* ctx, float* out_ms);
 /* Number of kernels the last vrt_trace launched. */
 int vrt_last_trace_launches(vrt_ctx* ctx, uint32_t* out);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Tile schedule (extension; the reference leaves workgroup order to the Vulkan driver, ComputePipeline.zig:547-550).
+ * The trace kernel's persistent warps pull 8x4-pixel tiles from a queue.  STATIC: bottom-up image order.  LPT: every tile
+ * reports what it cost and every `interval` frames the costs are sorted into the next frames' order, most expensive first
+ * (longest-processing-time-first list scheduling: the launch no longer ends on a 50 us tile that happened to start last).
+ * DEAL (contexts created with VRT_FLAG_INTERLEAVE): the sorted list of ALL tiles of the image is dealt round-robin to the
+ * part_world ranks instead of giving each rank fixed strips — every GPU gets the same mix of cheap and expensive tiles; needs
+ * a peer-store exchange mode when part_world > 1 GPUs really share the frame (a rank's tiles are scattered over the image),
+ * and every rank must call it with the same arguments.  The image is the same whatever the schedule.
+ * ------------------------------------------------------------------------------------------------- */
+#define VRT_SCHED_STATIC 0u
+#define VRT_SCHED_LPT 1u
+#define VRT_SCHED_DEAL 2u
+int vrt_set_schedule(vrt_ctx* ctx, uint32_t mode, uint32_t interval /* frames between sorts; 0 = 8 */);
+/* Debug / tests: read the per-tile costs of the last frame (clock ticks / 32, 0 = never traced), or install costs and sort them
+ * into the order right away.  count <= tiles of the image = ceil(width/8) * ceil(height/4). */
+int vrt_sched_get_costs(vrt_ctx* ctx, uint16_t* costs_host, size_t count);
+int vrt_sched_set_costs(vrt_ctx* ctx, const uint16_t* costs_host, size_t count);
 
 /* ---------------------------------------------------------------------------------------------------
  * Scene edits on the device: BrickGrid.insert (brick/Grid.zig:129-194) for a batch of voxels, the step in front of the

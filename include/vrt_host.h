@@ -150,6 +150,8 @@ uint32_t vrt_scene_terrain_materials(vrt_material* out, uint32_t capacity);
  * emit aborts and is returned.  vrt_scene_synthetic_fill is the common case emit = vrt_grid_insert. */
 typedef int (*vrt_emit_fn)(void* user, uint32_t x, uint32_t y, uint32_t z, uint8_t material);
 int vrt_scene_synthetic(uint32_t n_voxels, uint32_t seed, vrt_emit_fn emit, void* user);
+/* The same scene in an nx x ny x nz voxel box (heights scale with ny as in terrain.zig:81); nx = ny = nz is vrt_scene_synthetic. */
+int vrt_scene_synthetic_box(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t seed, vrt_emit_fn emit, void* user);
 int vrt_scene_synthetic_fill(vrt_grid* g, uint32_t seed);
 
 /* ------------------------------------------------------------------ MagicaVoxel .vox reader

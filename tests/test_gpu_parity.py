@@ -287,16 +287,17 @@ def test_attach_framebuffer_and_stream_interop(materials):
     ctx.close()
 
 
-@pytest.mark.parametrize("name", ["C2", "C3"])
+@pytest.mark.parametrize("name", ["C2", "C3", "C4", "C5"])
 def test_full_size_properties(materials, name):
-    """BASELINE sizes (1920x1080 over 256^3 / 512^3): the oracle is too slow to run per test at this size on every
+    """BASELINE sizes (1920x1080 over 256^3 / 512^3 / 1024^3 as 16^3 bricks; 3840x2160 over 512^3): the oracle is too slow to run per test at this size on every
     pixel, so check size-independent properties: tuned == reference-shape kernel pixel for pixel and record for record;
     traced rays = pixels + primary hits; every hit record is self-consistent with the uploaded grid (status bit set, occupancy
     bit set, material index equal to material_indices[...]); a 1/16 sample of rows equals the oracle."""
     wl = scenes.WORKLOADS[name]
-    grid = scenes.build_grid(wl.n_voxels, wl.brick_dim)
+    grid = scenes.build_grid(wl.n_voxels, wl.brick_dim, brick_alloc=scenes.count_bricks(wl.n_voxels, wl.brick_dim) if wl.n_voxels >= 1024 else 0)
     cam = scenes.camera(wl.width, wl.height, **POSE0)
     sun = scenes.sun(wl.sun)
+    brick_bytes = wl.brick_dim ** 3 // 8
     img_t, aov_t, cnt_t = trace(grid, materials, cam, sun, ffi.VRT_FLAG_AOV)
     img_b, aov_b, cnt_b = trace(grid, materials, cam, sun, ffi.VRT_FLAG_AOV | ffi.VRT_FLAG_BASELINE)
     assert_same(img_t, aov_t, img_b, aov_b)
@@ -310,9 +311,20 @@ def test_full_size_properties(materials, name):
     gi, vi = aov_b["grid_index"][hit].astype(np.int64), aov_b["voxel_index"][hit].astype(np.int64)
     assert ((grid.statuses[gi // 32] >> (gi % 32).astype(np.uint32)) & 1).all()
     bi = grid.brick_indices[gi].astype(np.int64)
-    assert ((grid.occupancy[bi * 8 + vi // 8] >> (vi % 8).astype(np.uint8)) & 1).all()
+    assert ((grid.occupancy[bi * brick_bytes + vi // 8] >> (vi % 8).astype(np.uint8)) & 1).all()
     assert np.array_equal(grid.material_indices[(grid.start_indices[bi] & 0x7FFFFFFF).astype(np.int64) + vi], aov_b["material"][hit].astype(np.uint8))
     assert (aov_b["material"][~hit] == 0xFFFFFFFF).all()
+    # the tile schedules change the order the tiles are traced in, never the frame
+    for mode in (ffi.VRT_SCHED_LPT, ffi.VRT_SCHED_DEAL):
+        ctx = ffi.Context(wl.width, wl.height, len(grid.brick_indices), brick_dim=wl.brick_dim, n_brick_alloc=grid.brick_alloc, part=(0, 1) if mode == ffi.VRT_SCHED_DEAL else None)
+        ctx.upload_grid(grid, materials)
+        ctx.set_schedule(mode, 2)
+        for _ in range(4):  # default order, then orders sorted from measured costs
+            ctx.trace(cam, sun)
+            assert np.array_equal(ctx.read_framebuffer(), img_b)
+        costs = ctx.sched_costs()
+        assert (costs > 0).all() and costs.max() > 4 * np.median(costs)  # every tile reported; the spread LPT exists for
+        ctx.close()
     # oracle on a 1/16 sample of the rows (row blocks of 8 every 128 rows)
     sc = orc.OracleScene.from_grid(grid, materials)
     for r0 in range(0, wl.height, 128):
@@ -322,6 +334,97 @@ def test_full_size_properties(materials, name):
         for f in EXACT:
             assert np.array_equal(ref_aov[f][r0:r1], aov_t[f][r0:r1]), f
         assert np.array_equal(ref_aov["t"][r0:r1].view(np.uint32), aov_t["t"][r0:r1].view(np.uint32))
+
+
+@pytest.mark.parametrize("bd,per_axis,scale,min_point", [(4, 20, 0.3, (-3.0, -3.0, -3.0)), (8, 10, 60.0 / 10, (-30.0, -30.0, -30.0)), (4, 24, 1.7, (-20.4, -20.4, -20.4)),
+                                                         (16, 6, 10.0, (-30.0, -30.0, -30.0))])
+def test_non_power_of_two_scales(materials, bd, per_axis, scale, min_point):
+    """Brick scales that are NOT powers of two: (p - min) / scale must be a true IEEE division in the tuned kernel (div_scale's
+    reciprocal shortcut is only exact for 2^k); tuned, reference-shape kernel and oracle agree bit for bit."""
+    g = ffi.Grid((per_axis,) * 3, brick_dim=bd, min_point=min_point, scale=scale)
+    assert g.fill_synthetic(scenes.SEED) == 0
+    ext = per_axis * scale
+    for pose in (dict(origin=(0.1 * ext, -0.35 * ext, 0.45 * ext), euler_deg=(25.0, 10.0, 0.0)), dict(origin=(0.05 * ext, 0.02 * ext, -0.1 * ext), euler_deg=(-15.0, 200.0, 0.0))):
+        cam = scenes.camera(200, 120, **pose)
+        for sun in (scenes.sun(True), scenes.sun(False)):
+            ref_img, ref_aov, _ = orc.OracleScene.from_grid(g, materials).render(cam, sun, aov=True)
+            assert 0.05 < ((ref_aov["flags"] & 1) != 0).mean() < 0.99
+            for flags in (ffi.VRT_FLAG_AOV, ffi.VRT_FLAG_AOV | ffi.VRT_FLAG_BASELINE):
+                img, aov, _ = trace(g, materials, cam, sun, flags)
+                assert_same(img, aov, ref_img, ref_aov)
+            img, _, _ = trace(g, materials, cam, sun, 0)
+            assert np.array_equal(img, ref_img)
+
+
+def test_tile_schedules_trace_the_same_frame(materials):
+    """STATIC / LPT / DEAL with arbitrary (random, constant, adversarial) costs: the schedule only permutes the order the tiles are
+    pulled in.  DEAL on one GPU traces this part's share only: the shares of all parts are disjoint and add up to the oracle's frame."""
+    grid = scenes.build_grid(64)
+    W, H = 203, 90  # ragged: partial tiles right and bottom
+    cam = scenes.camera(W, H, **POSE0)
+    sun = scenes.sun(True)
+    ref_img, _, _ = orc.OracleScene.from_grid(grid, materials).render(cam, sun)
+    rng = np.random.default_rng(5)
+    n_tiles = ((W + 7) // 8) * ((H + 3) // 4)
+    cost_sets = [rng.integers(0, 65536, n_tiles).astype(np.uint16), np.full(n_tiles, 7, np.uint16), np.arange(n_tiles).astype(np.uint16),
+                 np.where(np.arange(n_tiles) % 3 == 0, 65535, 0).astype(np.uint16)]
+    ctx = ffi.Context(W, H, len(grid.brick_indices))
+    ctx.upload_grid(grid, materials)
+    ctx.set_schedule(ffi.VRT_SCHED_LPT, 3)
+    for costs in cost_sets:
+        ctx.sched_set_costs(costs)
+        for _ in range(4):
+            assert np.array_equal(ctx.trace_to_host(cam, sun), ref_img)
+    got = ctx.sched_costs()
+    assert got.shape[0] == n_tiles and (got > 0).all()
+    ctx.set_schedule(ffi.VRT_SCHED_STATIC)
+    assert np.array_equal(ctx.trace_to_host(cam, sun), ref_img)
+    ctx.close()
+    for world in (2, 3, 8):
+        total = np.zeros((H, W, 4), dtype=np.uint32)
+        covered = np.zeros((H, W), dtype=np.int32)
+        for costs in cost_sets[:2]:
+            total[:], covered[:] = 0, 0
+            for r in range(world):
+                ctx = ffi.Context(W, H, len(grid.brick_indices), part=(r, world))
+                ctx.upload_grid(grid, materials)
+                ctx.set_schedule(ffi.VRT_SCHED_DEAL, 2)
+                ctx.sched_set_costs(costs)
+                ctx.trace(cam, sun)
+                ctx.trace(cam, sun)  # (only this part's tiles report costs here; real multi-GPU runs exchange them)
+                img = ctx.read_framebuffer()
+                covered += (img[..., 3] == 255)
+                total += img
+                ctx.close()
+            assert (covered == 1).all()
+            assert np.array_equal(total.astype(np.uint8), ref_img)
+
+
+def test_blocking_and_pipelined_frames_mix(materials):
+    """vrt_trace / vrt_trace_to_host right after vrt_trace_to_host_async frames: the blocking frame must wait for the copy still
+    reading its slot, and vrt_denoise / vrt_read_framebuffer must see the frame traced last."""
+    import torch
+
+    grid = scenes.build_grid(64)
+    sun = scenes.sun(True)
+    cams = [scenes.camera_from_pose(160, 96, o, q) for o, q in scenes.sweep_poses(7)]
+    sc = orc.OracleScene.from_grid(grid, materials)
+    refs = [sc.render(c, sun)[0] for c in cams]
+    ctx = ffi.Context(160, 96, len(grid.brick_indices))
+    ctx.upload_grid(grid, materials)
+    bufs = [torch.zeros(96, 160, 4, dtype=torch.uint8).pin_memory() for _ in cams]
+    for rep in range(3):
+        ctx.trace_to_host_async(cams[0], sun, bufs[0].data_ptr())
+        ctx.trace_to_host_async(cams[1], sun, bufs[1].data_ptr())
+        ctx.trace(cams[2], sun)  # blocking-style frame into a slot an async copy may still be reading
+        assert np.array_equal(ctx.read_framebuffer(), refs[2])
+        ctx.trace_to_host_async(cams[3], sun, bufs[3].data_ptr())
+        assert np.array_equal(ctx.denoise(None, 160, 96, 0), orc.denoise(refs[3]))  # the frame traced last, not a stale slot
+        assert np.array_equal(ctx.trace_to_host(cams[4], sun), refs[4])
+        ctx.sync()
+        for i in (0, 1, 3):
+            assert np.array_equal(bufs[i].numpy(), refs[i]), (rep, i)
+    ctx.close()
 
 
 def test_c4_brickmap_extension(materials):

@@ -1,8 +1,10 @@
-"""-m gpu, needs >= 2 CUDA devices (skipped otherwise): one process per GPU, every exchange mode x partition, blocking
-and pipelined frames; every rank must end with the oracle's full frame."""
+"""-m gpu, needs >= 2 CUDA devices (skipped otherwise): one process per GPU, every exchange mode x partition x tile schedule,
+blocking frames of a moving camera WITHOUT any host-side barrier, pipelined frames, and the two mixed; every rank must end
+every frame with the oracle's full frame.  Logs of the 2- / 4- / 8-GPU runs are kept under profiles/."""
 import os
 import socket
 import sys
+import time
 
 import numpy as np
 import pytest
@@ -29,56 +31,68 @@ def _worker(rank, world, port, out_dir):
     from zig_vulkan_b200 import ffi, scenes
     from oracle import orc
 
-    W, H = 256, 144  # 36 strips: divisible by 2 and 4, not by 8
+    W, H = 256, 144  # 36 strips: divisible by 2 and 4, not by 8 (ranks own 4 or 5 strips then)
     grid = scenes.build_grid(64)
     mats = zv.terrain_materials()
     sun = scenes.sun(True)
-    cams = [scenes.camera_from_pose(W, H, o, q) for o, q in scenes.sweep_poses(5)]
+    cams = [scenes.camera_from_pose(W, H, o, q) for o, q in scenes.sweep_poses(7)]
     sc = orc.OracleScene.from_grid(grid, mats)
     refs = [sc.render(c, sun)[0] for c in cams]
     failures = []
-    for partition in ("interleave", "slab"):
-        for exchange in ("allgather", "peer", "peerflags"):
-            if partition == "slab":
-                h = H // world
-                ctx = ffi.Context(W, H, len(grid.brick_indices), device=rank, rows=(rank * h, (rank + 1) * h))
-            else:
-                ctx = ffi.Context(W, H, len(grid.brick_indices), device=rank, part=(rank, world))
-            ctx.upload_grid(grid, mats)
-            ids = [ffi.Context.comm_unique_id() if rank == 0 else None]
-            dist.broadcast_object_list(ids, 0)
-            ctx.comm_init(rank, world, ids[0])
-            if exchange != "allgather":
-                handles = [None] * world
-                dist.all_gather_object(handles, ctx.comm_ipc_handle())
-                ctx.comm_open_peers(rank, world, b"".join(handles))
-                ctx.comm_set_exchange(ffi.VRT_EXCHANGE_PEER_STORE if exchange == "peer" else ffi.VRT_EXCHANGE_PEER_FLAGS)
-            # blocking frames
-            for cam, ref in zip(cams, refs):
+    S, L, D = ffi.VRT_SCHED_STATIC, ffi.VRT_SCHED_LPT, ffi.VRT_SCHED_DEAL
+    modes = [("interleave", "allgather", S), ("interleave", "allgather", L), ("interleave", "peer", S), ("interleave", "peer", D), ("interleave", "peerflags", L),
+             ("interleave", "peerflags", D), ("slab", "allgather", S), ("slab", "peer", L), ("slab", "peerflags", S)]
+    for partition, exchange, sched in modes:
+        tag = f"{partition}/{exchange}/sched{sched}"
+        if partition == "slab":
+            h = H // world
+            ctx = ffi.Context(W, H, len(grid.brick_indices), device=rank, rows=(rank * h, (rank + 1) * h))
+        else:
+            ctx = ffi.Context(W, H, len(grid.brick_indices), device=rank, part=(rank, world))
+        ctx.upload_grid(grid, mats)
+        ids = [ffi.Context.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, 0)
+        ctx.comm_init(rank, world, ids[0])
+        if exchange != "allgather":
+            handles = [None] * world
+            dist.all_gather_object(handles, ctx.comm_ipc_handle())
+            ctx.comm_open_peers(rank, world, b"".join(handles))
+            ctx.comm_set_exchange(ffi.VRT_EXCHANGE_PEER_STORE if exchange == "peer" else ffi.VRT_EXCHANGE_PEER_FLAGS)
+        ctx.set_schedule(sched, 2)
+        # blocking frames of a MOVING camera, no host-side barrier anywhere: a fast rank's next frame must not tear the frame a
+        # slow rank is still reading (the ranks are skewed on purpose)
+        for rep in range(3):
+            for i, (cam, ref) in enumerate(zip(cams, refs)):
                 ctx.trace(cam, sun)
-                ctx.sync()
-                dist.barrier()
-                if not np.array_equal(ctx.read_framebuffer(), ref):
-                    failures.append(f"{partition}/{exchange}: blocking frame differs on rank {rank}")
-                dist.barrier()
-            # pipelined frames, every rank copies to its own pinned buffers
-            bufs = [torch.zeros(H, W, 4, dtype=torch.uint8).pin_memory() for _ in cams]
-            for cam, buf in zip(cams, bufs):
-                ctx.trace_to_host_async(cam, sun, buf.data_ptr() if rank % 2 == 0 else None)
-            ctx.sync()
-            dist.barrier()
-            if rank % 2 == 0:
-                for buf, ref in zip(bufs, refs):
-                    if not np.array_equal(buf.numpy(), ref):
-                        failures.append(f"{partition}/{exchange}: pipelined frame differs on rank {rank}")
-            dist.barrier()
-            ctx.close()
+                img = ctx.read_framebuffer()
+                if (i + rep) % world == rank:
+                    time.sleep(0.003)
+                if not np.array_equal(img, ref):
+                    failures.append(f"{tag}: blocking frame {rep}.{i} differs on rank {rank} in {(img != ref).any(axis=2).sum()} pixels")
+            for i, (cam, ref) in enumerate(zip(cams, refs)):
+                img = ctx.trace_to_host(cam, sun)
+                if not np.array_equal(img, ref):
+                    failures.append(f"{tag}: trace_to_host frame {rep}.{i} differs on rank {rank}")
+        # pipelined frames, some ranks copy to their own pinned buffers, mixed with a blocking frame
+        bufs = [torch.zeros(H, W, 4, dtype=torch.uint8).pin_memory() for _ in cams]
+        for cam, buf in zip(cams, bufs):
+            ctx.trace_to_host_async(cam, sun, buf.data_ptr() if rank % 2 == 0 else None)
+        ctx.trace(cams[2], sun)
+        if not np.array_equal(ctx.read_framebuffer(), refs[2]):
+            failures.append(f"{tag}: blocking frame after pipelined frames differs on rank {rank}")
+        ctx.sync()
+        if rank % 2 == 0:
+            for i, (buf, ref) in enumerate(zip(bufs, refs)):
+                if not np.array_equal(buf.numpy(), ref):
+                    failures.append(f"{tag}: pipelined frame {i} differs on rank {rank}")
+        dist.barrier()
+        ctx.close()
     with open(os.path.join(out_dir, f"rank{rank}.txt"), "w") as f:
         f.write("\n".join(failures))
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_every_rank_ends_with_the_full_frame(tmp_path, world):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")

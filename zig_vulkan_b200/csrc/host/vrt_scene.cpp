@@ -77,14 +77,18 @@ uint32_t vrt_scene_terrain_materials(vrt_material* out, uint32_t capacity) {
     return 8;
 }
 
-int vrt_scene_synthetic(uint32_t n, uint32_t seed, vrt_emit_fn emit, void* user) {
-    if (!emit || n < 16 || n > 4096) return -1;
-    const uint32_t terrain_max = n / 2;  // terrain.zig:81: voxel_dim_y * 0.5
-    const uint32_t floor_h = n / 16;
-    const uint32_t ocean = n / 8;        // main.zig:120 passes ocean_level 20 of 256 (~1/12); 1/8 here so lakes are visible
-    const uint32_t p1 = n / 4 > 4 ? n / 4 : 4, p2 = n / 16 > 2 ? n / 16 : 2;
-    for (uint32_t x = 0; x < n; x++) {
-        for (uint32_t z = 0; z < n; z++) {
+int vrt_scene_synthetic(uint32_t n, uint32_t seed, vrt_emit_fn emit, void* user) { return vrt_scene_synthetic_box(n, n, n, seed, emit, user); }
+
+// The same scene in an nx x ny x nz voxel box (the reference's default grid is 512 x 256 x 512, main.zig:77-81): heights scale with
+// ny (terrain.zig:81 takes them from voxel_dim_y), lattice periods with nx.  nx = ny = nz gives vrt_scene_synthetic's scene exactly.
+int vrt_scene_synthetic_box(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t seed, vrt_emit_fn emit, void* user) {
+    if (!emit || nx < 16 || nx > 4096 || ny < 16 || ny > 4096 || nz < 16 || nz > 4096) return -1;
+    const uint32_t terrain_max = ny / 2;  // terrain.zig:81: voxel_dim_y * 0.5
+    const uint32_t floor_h = ny / 16;
+    const uint32_t ocean = ny / 8;        // main.zig:120 passes ocean_level 20 of 256 (~1/12); 1/8 here so lakes are visible
+    const uint32_t p1 = nx / 4 > 4 ? nx / 4 : 4, p2 = nx / 16 > 2 ? nx / 16 : 2;
+    for (uint32_t x = 0; x < nx; x++) {
+        for (uint32_t z = 0; z < nz; z++) {
             const uint32_t v = (3u * lattice_noise(x, z, p1, seed) + lattice_noise(x, z, p2, seed ^ 0x5bd1e995u)) >> 2;  // [0, 65535]
             const uint32_t height = floor_h + (uint32_t)(((uint64_t)v * (terrain_max - floor_h)) >> 16);
             uint32_t y = height / 2;  // terrain.zig:97
@@ -104,19 +108,19 @@ int vrt_scene_synthetic(uint32_t n, uint32_t seed, vrt_emit_fn emit, void* user)
         }
     }
     // K solid iron spheres floating above the terrain (below the pose-0 camera height of 0.625 n)
-    const uint32_t k_spheres = n / 32 > 1 ? n / 32 : 1;
+    const uint32_t k_spheres = nx / 32 > 1 ? nx / 32 : 1;
     for (uint32_t k = 0; k < k_spheres; k++) {
         Sphere s;
-        s.cx = hash3(k, 1, 0, seed) % n;
-        s.cz = hash3(k, 2, 0, seed) % n;
-        s.cy = n / 4 + hash3(k, 3, 0, seed) % (n / 4);
-        s.r = n / 32 + hash3(k, 4, 0, seed) % (n / 32 + 1);
+        s.cx = hash3(k, 1, 0, seed) % nx;
+        s.cz = hash3(k, 2, 0, seed) % nz;
+        s.cy = ny / 4 + hash3(k, 3, 0, seed) % (ny / 4);
+        s.r = ny / 32 + hash3(k, 4, 0, seed) % (ny / 32 + 1);
         for (int64_t x = s.cx - s.r; x <= s.cx + s.r; x++) {
-            if (x < 0 || x >= (int64_t)n) continue;
+            if (x < 0 || x >= (int64_t)nx) continue;
             for (int64_t z = s.cz - s.r; z <= s.cz + s.r; z++) {
-                if (z < 0 || z >= (int64_t)n) continue;
+                if (z < 0 || z >= (int64_t)nz) continue;
                 for (int64_t y = s.cy - s.r; y <= s.cy + s.r; y++) {
-                    if (y < 0 || y >= (int64_t)n) continue;
+                    if (y < 0 || y >= (int64_t)ny) continue;
                     const int64_t dx = x - s.cx, dy = y - s.cy, dz = z - s.cz;
                     if (dx * dx + dy * dy + dz * dz > s.r * s.r) continue;
                     const int rc = emit(user, (uint32_t)x, (uint32_t)y, (uint32_t)z, 7);
@@ -131,8 +135,7 @@ int vrt_scene_synthetic(uint32_t n, uint32_t seed, vrt_emit_fn emit, void* user)
 int vrt_scene_synthetic_fill(vrt_grid* g, uint32_t seed) {
     if (!g) return -1;
     const vrt_grid_state& s = g->state;
-    if (s.voxel_dim_x != s.voxel_dim_y || s.voxel_dim_x != s.voxel_dim_z) return -1;
-    return vrt_scene_synthetic(s.voxel_dim_x, seed, emit_to_grid, g);
+    return vrt_scene_synthetic_box(s.voxel_dim_x, s.voxel_dim_y, s.voxel_dim_z, seed, emit_to_grid, g);
 }
 
 // Benchmark.Configuration (Benchmark.zig:141-173) evaluated the way Benchmark.update does (:50-66), with

@@ -264,8 +264,17 @@ struct TraceParams {
     uint32_t dist_log_px, dist_log_pz;    // row / plane strides of `dist` are powers of two: x + (z << log_px) + (y << (log_px+log_pz))
     uint32_t scale_pow2, voxel_scale_pow2;  // brick / voxel scale is a power of two -> divide by multiplying with the exact inverse
     float inv_scale, inv_voxel_scale;
-    unsigned long long* tile_counter;     // persistent-kernel work counter (monotonic across frames)
-    unsigned long long tile_base;         // value of *tile_counter when this launch starts
+    // persistent-kernel work queue: counter[0] = next ticket, counter[1] = warps that have left the queue; the last warp to
+    // leave resets both, so every launch starts from 0 with identical parameters (frames can be replayed from a CUDA graph)
+    unsigned long long* tile_counter;
+    // Tile schedule (vrt_sched.cu).  order: a permutation of this launch's tile space, most expensive tile first (longest-
+    // processing-time-first keeps the tail of the launch short); ticket i traces tile order[order_offset + i * order_stride].
+    // NULL: bottom-up (ground rows first, sky tiles fill the tail).  cost: clock ticks / 32 each tile took, written by whoever
+    // traces it (and into every peer's copy when the tiles of one frame are dealt across GPUs), the sort key of the next order.
+    const uint32_t* tile_order;
+    uint32_t order_offset, order_stride;
+    uint16_t* tile_cost;
+    uint16_t* peer_cost[8];
     uint32_t vec_store_ok;                // framebuffer rows are 16-B aligned -> 128-bit stores
     // fused peer-store exchange (multi-GPU): framebuffers of every rank, this rank included
     uint32_t* peer_fb[8];

@@ -38,6 +38,18 @@ constexpr uint32_t kTileW = 8, kTileH = 4;
 
 // 3 CTAs of 256 threads per SM (80 registers): measured 10 % faster than 2 (102 registers, no spills) and equal to 4 (64, spills).
 // SIMPLE: the configuration shade_pixel_warp_simple covers (chosen per launch by launch_trace_tuned).
+// A warp leaves the work queue: the last one out resets the ticket counter for the next launch (see TraceParams::tile_counter).
+VRT_DI void leave_queue(const TraceParams& P, uint32_t lane) {
+    if (lane == 0) {
+        const unsigned long long warps = (unsigned long long)gridDim.x * (blockDim.x >> 5);
+        __threadfence();
+        if (atomicAdd(P.tile_counter + 1, 1ull) == warps - 1ull) {
+            P.tile_counter[0] = 0ull;
+            P.tile_counter[1] = 0ull;
+        }
+    }
+}
+
 template <int BD, bool AOV, bool SIMPLE>
 __global__ void __launch_bounds__(kTunedThreads, 3) trace_warp_kernel(const __grid_constant__ TraceParams P, const uint32_t tiles_x, const uint32_t tiles_total) {
     const uint32_t lane = threadIdx.x & 31u;
@@ -47,12 +59,13 @@ __global__ void __launch_bounds__(kTunedThreads, 3) trace_warp_kernel(const __gr
 
     for (;;) {
         unsigned long long t = 0ull;
-        if (lane == 0) t = atomicAdd(P.tile_counter, 1ull) - P.tile_base;
+        if (lane == 0) t = atomicAdd(P.tile_counter, 1ull);
         t = __shfl_sync(kFullMask, t, 0);
         if (t >= (unsigned long long)tiles_total) break;
-        // bottom-up: in the reference's convention image row 0 is up (sky); starting with the ground rows leaves the cheap sky
-        // tiles to fill the tail of the launch
-        const uint32_t tile = tiles_total - 1u - (uint32_t)t;
+        // Scheduled: the most expensive tiles of the previous frames first (vrt_sched.cu).  Otherwise bottom-up: in the reference's
+        // convention image row 0 is up (sky); starting with the ground rows leaves the cheap sky tiles to fill the tail of the launch.
+        const uint32_t tile = P.tile_order ? __ldg(P.tile_order + P.order_offset + (uint32_t)t * P.order_stride) : tiles_total - 1u - (uint32_t)t;
+        const long long tick0 = P.tile_cost ? clock64() : 0ll;
         const uint32_t px = (tile % tiles_x) * kTileW + lx;
         const uint32_t strip = tile / tiles_x;  // this launch's k-th strip of kTileH rows
         const uint32_t py = P.il_world ? (strip * P.il_world + P.il_rank) * kTileH + ly : P.row_begin + strip * kTileH + ly;
@@ -75,8 +88,23 @@ __global__ void __launch_bounds__(kTunedThreads, 3) trace_warp_kernel(const __gr
             P.fb[(size_t)out_row * width + px] = texel;
             for (uint32_t p = 0; p < P.n_peers; p++) P.peer_fb[p][(size_t)out_row * width + px] = texel;
         }
+        if (P.tile_cost) {  // what this tile cost: the sort key of the next frames' order (lane p also tells peer p)
+            const long long ticks = (clock64() - tick0) >> 5;
+            const uint16_t c = (uint16_t)(ticks > 65535ll ? 65535ll : (ticks < 1ll ? 1ll : ticks));
+            if (lane == 0) P.tile_cost[tile] = c;
+            if (lane < P.n_peers && P.peer_cost[lane]) P.peer_cost[lane][tile] = c;
+        }
     }
+    leave_queue(P, lane);
     if (AOV) flush_counters(P, pc);
+}
+
+uint32_t trace_tile_space(const TraceParams& P) {
+    const uint32_t rows = P.row_end - P.row_begin;
+    const uint32_t tiles_x = (P.cam.image_width + kTileW - 1) / kTileW;
+    uint32_t tiles_y = (rows + kTileH - 1) / kTileH;
+    if (P.il_world) tiles_y = (tiles_y + P.il_world - 1 - P.il_rank) / P.il_world;  // strips t = k * world + rank < tiles_y
+    return tiles_x * tiles_y;
 }
 
 template <int BD, bool AOV, bool SIMPLE>
@@ -85,21 +113,17 @@ cudaError_t launch_warp_kernel(const TraceParams& P, int num_sms, cudaStream_t s
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, trace_warp_kernel<BD, AOV, SIMPLE>, kTunedThreads, 0);
     if (e != cudaSuccess) return e;
     if (blocks_per_sm < 1) return cudaErrorLaunchOutOfResources;
-    const uint32_t rows = P.row_end - P.row_begin;
     const uint32_t tiles_x = (P.cam.image_width + kTileW - 1) / kTileW;
-    uint32_t tiles_y = (rows + kTileH - 1) / kTileH;
-    if (P.il_world) tiles_y = (tiles_y + P.il_world - 1 - P.il_rank) / P.il_world;  // strips t = k * world + rank < tiles_y
-    const uint32_t tiles_total = tiles_x * tiles_y;
+    uint32_t tiles_total = trace_tile_space(P);
+    if (P.tile_order && P.order_stride > 1u)  // this launch's share of a schedule dealt across ranks: tickets i with offset + i * stride < all tiles
+        tiles_total = P.order_offset < tiles_total ? (tiles_total - P.order_offset + P.order_stride - 1u) / P.order_stride : 0u;
     if (tiles_total == 0) return cudaSuccess;
     const uint32_t warps_per_block = kTunedThreads / 32;
     uint32_t grid = (uint32_t)(num_sms * blocks_per_sm);  // one resident wave: a multiple of the SM count
     const uint32_t needed = (tiles_total + warps_per_block - 1) / warps_per_block;
     if (grid > needed) grid = needed;
     trace_warp_kernel<BD, AOV, SIMPLE><<<grid, kTunedThreads, 0, stream>>>(P, tiles_x, tiles_total);
-    if (info) {
-        info->launches++;
-        info->counter_advance = (unsigned long long)tiles_total + (unsigned long long)grid * warps_per_block;  // every warp overshoots once
-    }
+    if (info) info->launches++;
     return cudaGetLastError();
 }
 
@@ -133,7 +157,7 @@ __global__ void __launch_bounds__(kTunedThreads, 3) trace_rays_kernel(const __gr
     const unsigned long long blocks = (count + 31ull) / 32ull;
     for (;;) {  // blocks of 32 rays from the same work counter as the pixel kernel: rays differ in cost by orders of magnitude
         unsigned long long t = 0ull;
-        if (lane == 0) t = atomicAdd(P.tile_counter, 1ull) - P.tile_base;
+        if (lane == 0) t = atomicAdd(P.tile_counter, 1ull);
         t = __shfl_sync(kFullMask, t, 0);
         if (t >= blocks) break;
         const unsigned long long base = t * 32ull;
@@ -152,6 +176,7 @@ __global__ void __launch_bounds__(kTunedThreads, 3) trace_rays_kernel(const __gr
             hits[2 * i + 1] = make_uint4(__float_as_uint(got ? hit.t : 0.0f), __float_as_uint(hit.normal.x), __float_as_uint(hit.normal.y), __float_as_uint(hit.normal.z));
         }
     }
+    leave_queue(P, lane);
 }
 
 cudaError_t launch_trace_rays(const TraceParams& P, const vrt_ray* rays, vrt_ray_hit* hits, size_t count, cudaStream_t stream, LaunchInfo* info) {
@@ -166,10 +191,7 @@ cudaError_t launch_trace_rays(const TraceParams& P, const vrt_ray* rays, vrt_ray
     if (grid > blocks_needed) grid = (unsigned)blocks_needed;
     if (P.brick_dim == 4) trace_rays_kernel<4><<<grid, kTunedThreads, 0, stream>>>(P, reinterpret_cast<const float4*>(rays), reinterpret_cast<uint4*>(hits), count);
     else trace_rays_kernel<0><<<grid, kTunedThreads, 0, stream>>>(P, reinterpret_cast<const float4*>(rays), reinterpret_cast<uint4*>(hits), count);
-    if (info) {
-        info->launches++;
-        info->counter_advance = warps_needed + (unsigned long long)grid * (kTunedThreads / 32);  // every warp overshoots once
-    }
+    if (info) info->launches++;
     return cudaGetLastError();
 }
 
@@ -244,13 +266,14 @@ __global__ void __launch_bounds__(128) dist_scan_kernel(const __grid_constant__ 
 }
 
 // tmp: 6 * n_bricks bytes of scratch.  The border bytes of `dist` (255) are written once when it is allocated.
-cudaError_t launch_build_accel(const TraceParams& P, unsigned long long* occ_dense, uint8_t* dist, uint8_t* tmp, size_t n_bricks, cudaStream_t stream,
-                               LaunchInfo* info) {
+cudaError_t launch_build_accel(const TraceParams& P, unsigned long long* occ_dense, uint8_t* dist, uint8_t* tmp, size_t n_bricks, bool occ_only,
+                               cudaStream_t stream, LaunchInfo* info) {
     const unsigned blocks = (unsigned)((n_bricks + 255) / 256);
     if (occ_dense) {
         build_occ_dense_kernel<<<blocks, 256, 0, stream>>>(P, occ_dense, n_bricks);
         if (info) info->launches++;
     }
+    if (occ_only) return cudaGetLastError();
     uint8_t* tmp_x = tmp;                 // [2][n]
     uint8_t* tmp_z = tmp + 2 * n_bricks;  // [4][n]
     const size_t dx = P.grid.dim_x, dy = P.grid.dim_y, dz = P.grid.dim_z;

@@ -14,16 +14,21 @@ constexpr uint32_t kDistBorder = 255u;  // dist byte of the one-cell border arou
 constexpr uint32_t kDistFree = 0x80u;   // dist bit: no loaded brick anywhere in this cell's octant (low 7 bits: distance, <= 126)
 
 struct LaunchInfo {
-    uint32_t launches;                 // kernels enqueued
-    unsigned long long counter_advance;  // how far the launch moves *tile_counter (tuned kernel)
+    uint32_t launches;  // kernels enqueued
 };
 
 // Enqueue the kernels that trace rows [P.row_begin, P.row_end) into P.fb.
 cudaError_t launch_trace(const TraceParams& P, TraceKernel which, bool aov, cudaStream_t stream, LaunchInfo* info);
 
-// Rebuild the derived structures (occ_dense, dist) from the reference-format buffers.  tmp: 6 * n_bricks bytes.
-cudaError_t launch_build_accel(const TraceParams& P, unsigned long long* occ_dense, uint8_t* dist, uint8_t* tmp, size_t n_bricks, cudaStream_t stream,
-                               LaunchInfo* info);
+// Rebuild the derived structures (occ_dense; dist unless occ_only) from the reference-format buffers.  tmp: 6 * n_bricks bytes.
+cudaError_t launch_build_accel(const TraceParams& P, unsigned long long* occ_dense, uint8_t* dist, uint8_t* tmp, size_t n_bricks, bool occ_only,
+                               cudaStream_t stream, LaunchInfo* info);
+// Tiles (8x4 pixels) of the launch launch_trace_tuned would make for P with no schedule attached: the tile space an order for it permutes.
+uint32_t trace_tile_space(const TraceParams& P);
+// Tile schedule (vrt_sched.cu): order[i] = n - 1 - i and zeroed costs; stable sort of the tiles by cost, most expensive first.
+size_t sched_scratch_words(uint32_t n_tiles);
+cudaError_t launch_sched_init(uint32_t* order, uint16_t* cost0, uint16_t* cost1, uint32_t n_tiles, cudaStream_t stream, LaunchInfo* info);
+cudaError_t launch_sched_sort(const uint16_t* cost, uint32_t n_tiles, uint32_t* order, uint32_t* scratch, cudaStream_t stream, LaunchInfo* info);
 // Explicit-ray mode: GridHit on caller-supplied rays (device pointers).
 cudaError_t launch_trace_rays(const TraceParams& P, const vrt_ray* rays, vrt_ray_hit* hits, size_t count, cudaStream_t stream, LaunchInfo* info);
 // After the all-gather of an interleaved partition: rank-major strips -> row-major frame (width % 4 == 0).

@@ -105,8 +105,7 @@ struct vrt_ctx {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_traced[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
     bool slot_used[2] = {false, false};
-    cudaEvent_t barrier_after_copy = nullptr;  // peer-store: the frame barrier must not pass before this copy has finished
-    uint64_t async_frames = 0;
+    uint64_t ring_seq = 0;  // frames that went through the two-slot ring (async frames; every frame in the peer-store modes)
 
     // post-process output (vrt_denoise)
     uint32_t* d_denoised = nullptr;
@@ -126,11 +125,28 @@ struct vrt_ctx {
     size_t dist_plane = 0;          // bytes per octant
     uint32_t dist_log_px = 0, dist_log_pz = 0;
     uint32_t accel_dim[3] = {0, 0, 0};
-    bool accel_dirty = true;
+    bool accel_dirty = true;   // statuses / brick indices changed: occ_dense and the distance planes are stale
+    bool occ_dirty = true;     // only occupancy bytes changed: occ_dense is stale, the distance planes are not
 
-    // persistent-kernel work counter
+    // persistent-kernel work queue {next ticket, warps that left}; the kernel resets it itself
     unsigned long long* d_tile_counter = nullptr;
-    unsigned long long tile_base = 0;
+
+    // tile schedule (vrt_sched.cu): costs live behind the frame ring + flags in the IPC allocation so that peers can write them
+    uint32_t sched_mode = VRT_SCHED_STATIC, sched_interval = 8;
+    uint32_t* d_order = nullptr;
+    uint32_t* d_sched_scratch = nullptr;
+    uint16_t* d_cost[2] = {nullptr, nullptr};
+    uint32_t tiles_global = 0;      // 8x4-pixel tiles of the whole image
+    uint32_t sched_tiles = 0;       // tile space the current order covers (0: order not initialised)
+    uint64_t sched_frames = 0;      // frames traced under the current schedule
+    cudaEvent_t ev_kernel_end = nullptr;  // after the trace kernel, before the exchange
+
+    // pinned staging ring of the uploads (render/StagingRamp.zig:98-175: N host-visible buffers filled round-robin)
+    uint8_t* h_stage = nullptr;
+    cudaEvent_t ev_stage[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool stage_used[4] = {false, false, false, false};
+    int stage_next = 0;
+    size_t stage_off = 0;  // fill level of buffer stage_next
 
     // multi-GPU
     int rank = 0, world = 1;
@@ -163,6 +179,44 @@ int fail(vrt_ctx* ctx, int code, const char* fmt, ...) {
         }                                                                                                     \
     } while (0)
 
+// Uploads go through a ring of pinned staging buffers, like the reference's StagingRamp (render/StagingRamp.zig:98-175,318-360):
+// the caller's bytes are copied into the next free buffer and DMA'd from there on the ctx stream, so the call returns as soon
+// as the bytes are staged — whatever memory `src` is (pageable, pinned, mapped) the caller may overwrite it immediately and is
+// never blocked by the transfer itself; a buffer is reused only after the copy that read it has finished.
+constexpr size_t kStageChunk = 16u << 20;
+constexpr int kStageBuffers = 4;
+int stage_upload(vrt_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (!ctx->h_stage) {
+        if (cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_stage), kStageChunk * kStageBuffers, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            ctx->h_stage = nullptr;
+            return fail(ctx, VRT_E_OOM, "cannot allocate the %zu-byte pinned staging ring", kStageChunk * kStageBuffers);
+        }
+        for (int i = 0; i < kStageBuffers; i++) VRT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_stage[i], cudaEventDisableTiming));
+    }
+    const uint8_t* s = static_cast<const uint8_t*>(src);
+    uint8_t* d = static_cast<uint8_t*>(dst);
+    while (bytes) {
+        if (ctx->stage_off >= kStageChunk) {  // this buffer is full: on to the next one, once the copies that read it are done
+            ctx->stage_next = (ctx->stage_next + 1) % kStageBuffers;
+            ctx->stage_off = 0;
+            if (ctx->stage_used[ctx->stage_next]) VRT_CUDA(ctx, cudaEventSynchronize(ctx->ev_stage[ctx->stage_next]));
+            ctx->stage_used[ctx->stage_next] = false;
+        }
+        const int b = ctx->stage_next;
+        const size_t room = kStageChunk - ctx->stage_off;
+        const size_t n = bytes < room ? bytes : room;
+        uint8_t* stage = ctx->h_stage + (size_t)b * kStageChunk + ctx->stage_off;
+        std::memcpy(stage, s, n);
+        VRT_CUDA(ctx, cudaMemcpyAsync(d, stage, n, cudaMemcpyHostToDevice, ctx->stream));
+        VRT_CUDA(ctx, cudaEventRecord(ctx->ev_stage[b], ctx->stream));  // = the latest copy out of buffer b
+        ctx->stage_used[b] = true;
+        ctx->stage_off += (n + 255u) & ~(size_t)255u;
+        s += n, d += n, bytes -= n;
+    }
+    return VRT_OK;
+}
+
 template <class T>
 int upload_range(vrt_ctx* ctx, T* dst, size_t capacity, size_t offset, const T* data, size_t count, const char* what) {
     if (!ctx) return VRT_E_INVALID;
@@ -171,11 +225,10 @@ int upload_range(vrt_ctx* ctx, T* dst, size_t capacity, size_t offset, const T* 
     if (offset > capacity || count > capacity - offset)
         return fail(ctx, VRT_E_RANGE, "%s: [%zu, %zu) outside capacity %zu", what, offset, offset + count, capacity);
     VRT_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
-    // Pageable source: the runtime stages it before returning, so the caller may reuse `data` immediately
-    // (stricter than the reference's deferred path, render/StagingRamp.zig:105-111).
-    VRT_CUDA(ctx, cudaMemcpyAsync(dst + offset, data, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
-    return VRT_OK;
+    return stage_upload(ctx, dst + offset, data, count * sizeof(T));
 }
+
+size_t cost_bytes(const vrt_ctx* c) { return ((size_t)c->tiles_global * sizeof(uint16_t) + 255u) & ~(size_t)255u; }
 
 void fill_params(const vrt_ctx* c, const vrt_camera* cam, const vrt_sun* sun, TraceParams& P) {
     std::memset(&P, 0, sizeof(P));
@@ -217,7 +270,6 @@ void fill_params(const vrt_ctx* c, const vrt_camera* cam, const vrt_sun* sun, Tr
     P.inv_scale = P.scale_pow2 ? 1.0f / scale : 0.0f;
     P.inv_voxel_scale = P.voxel_scale_pow2 ? 1.0f / voxel_scale : 0.0f;
     P.tile_counter = c->d_tile_counter;
-    P.tile_base = c->tile_base;
     P.vec_store_ok = (cam->image_width % 4 == 0) && ((reinterpret_cast<uintptr_t>(c->d_fb) & 15u) == 0);
     P.n_peers = 0;
     P.one = 1u;
@@ -225,6 +277,22 @@ void fill_params(const vrt_ctx* c, const vrt_camera* cam, const vrt_sun* sun, Tr
         const size_t slot_words = (c->d_fb == c->d_fb_ring1) ? c->fb_bytes / 4 : 0;  // same ring slot on every rank
         for (int r = 0; r < c->world; r++)
             if (r != c->rank) P.peer_fb[P.n_peers++] = static_cast<uint32_t*>(c->peer_fb[r]) + slot_words;
+    }
+    // tile schedule (tuned kernel, not the counting / AOV variant)
+    if (c->sched_mode != VRT_SCHED_STATIC && !(c->cfg.flags & (VRT_FLAG_AOV | VRT_FLAG_BASELINE))) {
+        const int parity = (int)(c->sched_frames & 1u);
+        P.tile_order = c->d_order;
+        P.tile_cost = c->d_cost[parity];
+        P.order_offset = 0u, P.order_stride = 1u;
+        if (c->sched_mode == VRT_SCHED_DEAL) {  // the whole image is one tile space, this rank takes every part_world-th entry of the order
+            P.order_offset = c->part_rank, P.order_stride = c->part_world;
+            P.il_world = 0u, P.il_gather = 0u;
+            P.row_begin = 0u, P.row_end = c->cfg.height;
+            const size_t cost_off = 2 * c->fb_bytes + kPeerFlagBytes + (size_t)parity * cost_bytes(c);
+            uint32_t p = 0;
+            for (int r = 0; r < c->world && P.n_peers; r++)
+                if (r != c->rank) P.peer_cost[p++] = reinterpret_cast<uint16_t*>(static_cast<uint8_t*>(c->peer_fb[r]) + cost_off);
+        }
     }
 }
 
@@ -306,6 +374,7 @@ int vrt_init(vrt_ctx** out_ctx, const vrt_config* cfg) {
     ctx->n_start_indices = ctx->cfg.n_brick_alloc;                    // Grid.zig:57
     ctx->n_material_indices = ctx->cfg.n_brick_alloc * (size_t)bits;  // Grid.zig:61-62
     ctx->fb_bytes = (size_t)cfg->width * cfg->height * 4;
+    ctx->tiles_global = ((cfg->width + 7u) / 8u) * ((cfg->height + kStripRows - 1u) / kStripRows);
 
 #define INIT_CUDA(call)                                                                                          \
     do {                                                                                                         \
@@ -329,9 +398,16 @@ int vrt_init(vrt_ctx** out_ctx, const vrt_config* cfg) {
     INIT_CUDA(cudaMalloc(&ctx->d_occupancy, ctx->n_occupancy));
     INIT_CUDA(cudaMalloc(&ctx->d_start_indices, ctx->n_start_indices * 4));
     INIT_CUDA(cudaMalloc(&ctx->d_material_indices, ctx->n_material_indices));
-    INIT_CUDA(cudaMalloc(&ctx->d_fb_own, 2 * ctx->fb_bytes + kPeerFlagBytes));  // slot 0 + slot 1 of the frame ring + barrier flags, one allocation = one IPC handle
+    // slot 0 + slot 1 of the frame ring + barrier flags + the two tile-cost arrays: one allocation = one IPC handle
+    const size_t shared_bytes = 2 * ctx->fb_bytes + kPeerFlagBytes + 2 * cost_bytes(ctx);
+    INIT_CUDA(cudaMalloc(&ctx->d_fb_own, shared_bytes));
     ctx->d_fb_ring1 = ctx->d_fb_own + ctx->fb_bytes / 4;
-    INIT_CUDA(cudaMalloc(&ctx->d_tile_counter, 8));
+    ctx->d_cost[0] = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(ctx->d_fb_own) + 2 * ctx->fb_bytes + kPeerFlagBytes);
+    ctx->d_cost[1] = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(ctx->d_cost[0]) + cost_bytes(ctx));
+    INIT_CUDA(cudaMalloc(&ctx->d_order, (size_t)ctx->tiles_global * 4));
+    INIT_CUDA(cudaMalloc(&ctx->d_sched_scratch, sched_scratch_words(ctx->tiles_global) * 4));
+    INIT_CUDA(cudaEventCreate(&ctx->ev_kernel_end));
+    INIT_CUDA(cudaMalloc(&ctx->d_tile_counter, 16));
     ctx->d_fb = ctx->d_fb_own;
     ctx->h_materials = new (std::nothrow) vrt_material[ctx->n_materials]();
     if (!ctx->h_materials) {
@@ -346,8 +422,8 @@ int vrt_init(vrt_ctx** out_ctx, const vrt_config* cfg) {
     INIT_CUDA(cudaMemsetAsync(ctx->d_occupancy, 0, ctx->n_occupancy, ctx->stream));
     INIT_CUDA(cudaMemsetAsync(ctx->d_start_indices, 0xff, ctx->n_start_indices * 4, ctx->stream));
     INIT_CUDA(cudaMemsetAsync(ctx->d_material_indices, 0, ctx->n_material_indices, ctx->stream));
-    INIT_CUDA(cudaMemsetAsync(ctx->d_fb_own, 0, 2 * ctx->fb_bytes + kPeerFlagBytes, ctx->stream));
-    INIT_CUDA(cudaMemsetAsync(ctx->d_tile_counter, 0, 8, ctx->stream));
+    INIT_CUDA(cudaMemsetAsync(ctx->d_fb_own, 0, shared_bytes, ctx->stream));
+    INIT_CUDA(cudaMemsetAsync(ctx->d_tile_counter, 0, 16, ctx->stream));
     if (cfg->brick_dim == 4) INIT_CUDA(cudaMalloc(&ctx->d_occ_dense, cfg->n_bricks * 8));
     if (cfg->flags & VRT_FLAG_AOV) {
         INIT_CUDA(cudaMalloc(&ctx->d_aov, (size_t)cfg->width * cfg->height * sizeof(vrt_aov)));
@@ -373,6 +449,11 @@ void vrt_deinit(vrt_ctx* ctx) {
     cudaFree(ctx->d_materials), cudaFree(ctx->d_statuses), cudaFree(ctx->d_brick_indices), cudaFree(ctx->d_occupancy);
     cudaFree(ctx->d_start_indices), cudaFree(ctx->d_material_indices), cudaFree(ctx->d_fb_own), cudaFree(ctx->d_aov);
     cudaFree(ctx->d_counters), cudaFree(ctx->d_occ_dense), cudaFree(ctx->d_dist), cudaFree(ctx->d_dist_tmp);
+    cudaFree(ctx->d_order), cudaFree(ctx->d_sched_scratch);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    for (int i = 0; i < 4; i++)
+        if (ctx->ev_stage[i]) cudaEventDestroy(ctx->ev_stage[i]);
+    if (ctx->ev_kernel_end) cudaEventDestroy(ctx->ev_kernel_end);
     cudaFree(ctx->d_tile_counter), cudaFree(ctx->d_gather), cudaFree(ctx->d_barrier), cudaFree(ctx->d_denoised), cudaFree(ctx->d_dn_decoded);
     if (ctx->h_barrier_error) cudaFreeHost(ctx->h_barrier_error);
     if (ctx->ev_dn_begin) cudaEventDestroy(ctx->ev_dn_begin);
@@ -422,7 +503,7 @@ int vrt_upload_brick_indices(vrt_ctx* ctx, size_t offset, const uint32_t* data, 
 }
 int vrt_upload_brick_occupancy(vrt_ctx* ctx, size_t offset, const uint8_t* data, size_t count) {
     const int rc = upload_range(ctx, ctx ? ctx->d_occupancy : nullptr, ctx ? ctx->n_occupancy : 0, offset, data, count, "vrt_upload_brick_occupancy");
-    if (rc == VRT_OK && count) ctx->accel_dirty = true;
+    if (rc == VRT_OK && count) ctx->occ_dirty = true;  // voxels inside bricks: the distance planes (brick level) are unaffected
     return rc;
 }
 int vrt_upload_brick_start_indices(vrt_ctx* ctx, size_t offset, const uint32_t* data, size_t count) {
@@ -432,42 +513,105 @@ int vrt_upload_material_indices(vrt_ctx* ctx, size_t offset, const uint8_t* data
     return upload_range(ctx, ctx ? ctx->d_material_indices : nullptr, ctx ? ctx->n_material_indices : 0, offset, data, count, "vrt_upload_material_indices");
 }
 
-int vrt_trace(vrt_ctx* ctx, const vrt_camera* camera, const vrt_sun* sun) {
-    if (!ctx) return VRT_E_INVALID;
+namespace {
+
+bool peer_mode(const vrt_ctx* c) {
+    return c->world > 1 && c->peers_open && (c->exchange_mode == VRT_EXCHANGE_PEER_STORE || c->exchange_mode == VRT_EXCHANGE_PEER_FLAGS);
+}
+bool owns_fb(const vrt_ctx* c) { return c->d_fb == c->d_fb_own || c->d_fb == c->d_fb_ring1; }
+
+int ensure_ring(vrt_ctx* ctx) {  // copy stream + per-slot events of the two-slot frame ring
+    if (ctx->copy_stream) return VRT_OK;
+    VRT_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        VRT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_traced[i], cudaEventDisableTiming));
+        VRT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
+    }
+    return VRT_OK;
+}
+
+// The frame about to be traced goes into slot `slot` of the ring (or stays in the attached image): make the stream wait until the
+// slot's previous contents have reached the host (an earlier vrt_trace_to_host_async may still be copying them).
+int claim_slot(vrt_ctx* ctx, int slot) {
+    if (ctx->slot_used[slot]) {
+        VRT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[slot], 0));
+        ctx->slot_used[slot] = false;
+    }
+    ctx->d_fb = slot ? ctx->d_fb_ring1 : ctx->d_fb_own;
+    return VRT_OK;
+}
+
+// One frame: (derived structures) -> trace kernel -> exchange -> (schedule).  `ring`: this frame uses the ring slot ring_seq & 1.
+int trace_frame(vrt_ctx* ctx, const vrt_camera* camera, const vrt_sun* sun, bool ring) {
     if (!camera || !sun) return fail(ctx, VRT_E_INVALID, "vrt_trace: camera or sun is NULL");
     if (!ctx->have_grid) return fail(ctx, VRT_E_STATE, "vrt_trace: vrt_upload_grid_state has not been called");
     if (camera->image_width != ctx->cfg.width || camera->image_height != ctx->cfg.height)
         return fail(ctx, VRT_E_INVALID, "vrt_trace: camera image %ux%u != target image %ux%u", camera->image_width, camera->image_height,
                     ctx->cfg.width, ctx->cfg.height);
     if (camera->samples_per_pixel < 1) return fail(ctx, VRT_E_INVALID, "vrt_trace: samples_per_pixel < 1");
+    const bool gather = ctx->world > 1 && ctx->exchange_mode == VRT_EXCHANGE_ALLGATHER;
+    if (ctx->world > 1 && !ctx->comm && ctx->exchange_mode != VRT_EXCHANGE_PEER_FLAGS)  // the flag barrier needs no communicator
+        return fail(ctx, VRT_E_STATE, "vrt_trace: world > 1 but vrt_comm_init has not been called");
+    if (ctx->sched_mode == VRT_SCHED_DEAL && ctx->world > 1 && !peer_mode(ctx))
+        return fail(ctx, VRT_E_STATE, "vrt_trace: VRT_SCHED_DEAL scatters a rank's tiles over the image and needs a peer-store exchange mode");
     VRT_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+
+    // Frame ring.  Async frames always use it.  In the peer-store modes EVERY frame does: a peer's frame k+1 stores straight into this
+    // rank's framebuffer, and the frame barrier only orders them after this rank's TRACE of frame k — with one buffer they could land
+    // while the host is still reading frame k.  With two slots, frame k+1 goes to the other slot and frame k+2 cannot start on any rank
+    // before this rank has traced k+1, which its host does after it has finished with frame k.
+    if (ring || (peer_mode(ctx) && owns_fb(ctx))) {
+        const int rc = ensure_ring(ctx);
+        if (rc != VRT_OK) return rc;
+        const int slot = (int)(ctx->ring_seq & 1u);
+        const int rc2 = claim_slot(ctx, slot);
+        if (rc2 != VRT_OK) return rc2;
+        ring = true;
+    } else if (owns_fb(ctx) && ctx->copy_stream) {  // a blocking frame after async ones: same hazard on whatever slot d_fb points at
+        const int rc = claim_slot(ctx, ctx->d_fb == ctx->d_fb_ring1 ? 1 : 0);
+        if (rc != VRT_OK) return rc;
+    }
 
     TraceParams P;
     fill_params(ctx, camera, sun, P);
-    LaunchInfo info = {0u, 0ull};
+    LaunchInfo info = {0u};
     const bool aov = (ctx->cfg.flags & VRT_FLAG_AOV) != 0;
     const TraceKernel which = (ctx->cfg.flags & VRT_FLAG_BASELINE) ? KERNEL_REF : KERNEL_TUNED;
 
     VRT_CUDA(ctx, cudaEventRecord(ctx->ev_begin, ctx->stream));
-    if (which == KERNEL_TUNED && ctx->accel_dirty) {  // (vrt_trace_rays does the same)
-        // Uploads changed statuses / indices / occupancy: rebuild the derived structures before tracing.  Stream order
-        // gives upload -> build -> trace, where the reference has no barrier at all between its staging
-        // copy and the next dispatch (edits land one frame late, Pipeline.zig:540).
+    if (which == KERNEL_TUNED && (ctx->accel_dirty || ctx->occ_dirty)) {  // (vrt_trace_rays does the same)
+        // Uploads changed statuses / indices / occupancy: rebuild the derived structures before tracing.  Stream order gives
+        // upload -> build -> trace, where the reference has no barrier at all between its staging copy and the next dispatch
+        // (edits land one frame late, Pipeline.zig:540).  Occupancy-only edits (voxels inside loaded bricks — most of
+        // Grid.insert's traffic) leave the brick-level distance planes alone.
         const size_t n_cells = (size_t)ctx->grid.dim_x * ctx->grid.dim_y * ctx->grid.dim_z;
-        VRT_CUDA(ctx, launch_build_accel(P, ctx->d_occ_dense, ctx->d_dist, ctx->d_dist_tmp, n_cells, ctx->stream, &info));
-        ctx->accel_dirty = false;
+        VRT_CUDA(ctx, launch_build_accel(P, ctx->d_occ_dense, ctx->d_dist, ctx->d_dist_tmp, n_cells, !ctx->accel_dirty, ctx->stream, &info));
+        ctx->accel_dirty = ctx->occ_dirty = false;
     }
     if (aov) VRT_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
-    const bool gather = ctx->world > 1 && ctx->exchange_mode == VRT_EXCHANGE_ALLGATHER;
-    if (ctx->world > 1 && !ctx->comm && ctx->exchange_mode != VRT_EXCHANGE_PEER_FLAGS)  // the flag barrier needs no communicator
-        return fail(ctx, VRT_E_STATE, "vrt_trace: world > 1 but vrt_comm_init has not been called");
     if (gather && ctx->interleave) {  // trace straight into this rank's slice of the rank-major gather buffer
         P.fb = ctx->d_gather;
         P.il_gather = 1u;
         P.vec_store_ok = (camera->image_width % 4 == 0) ? 1u : 0u;
     }
+    if (P.tile_order) {  // a schedule is attached: (re)initialise it when the tile space it permutes has changed
+        TraceParams Q = P;
+        Q.tile_order = nullptr;
+        const uint32_t space = trace_tile_space(Q);
+        if (space != ctx->sched_tiles) {
+            VRT_CUDA(ctx, launch_sched_init(ctx->d_order, ctx->d_cost[0], ctx->d_cost[1], space, ctx->stream, &info));
+            ctx->sched_tiles = space, ctx->sched_frames = 0;
+            P.tile_cost = ctx->d_cost[0];
+            if (ctx->sched_mode == VRT_SCHED_DEAL && P.n_peers) {  // parity 0 again
+                const size_t cost_off = 2 * ctx->fb_bytes + kPeerFlagBytes;
+                uint32_t p = 0;
+                for (int r = 0; r < ctx->world; r++)
+                    if (r != ctx->rank) P.peer_cost[p++] = reinterpret_cast<uint16_t*>(static_cast<uint8_t*>(ctx->peer_fb[r]) + cost_off);
+            }
+        }
+    }
     VRT_CUDA(ctx, launch_trace(P, which, aov, ctx->stream, &info));
-    ctx->tile_base += info.counter_advance;
+    VRT_CUDA(ctx, cudaEventRecord(ctx->ev_kernel_end, ctx->stream));
 
     if (gather) {
         // in place: the kernel already wrote this rank's pixels at their offset in the gathered buffer
@@ -484,11 +628,11 @@ int vrt_trace(vrt_ctx* ctx, const vrt_camera* camera, const vrt_sun* sun) {
             if (r != ncclSuccess) return fail(ctx, VRT_E_NCCL, "ncclAllGather failed: %s", g_nccl.GetErrorString(r));
         }
     } else if (ctx->world > 1) {
-        // peer-store: the pixels are already in every rank's framebuffer; a 4-byte all-reduce makes "every rank has finished
-        // frame k" visible in stream order, so frame k+1's remote stores cannot overtake a peer still reading frame k
-        // (pipelined frames: the NEXT frame's remote stores land in the other ring slot of every peer, so this barrier also
-        // waits until this rank has copied that slot's previous frame to its host)
-        if (ctx->barrier_after_copy) VRT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->barrier_after_copy, 0));
+        // peer-store: the pixels are already in every rank's framebuffer; the frame barrier makes "every rank has finished
+        // frame k" visible in stream order.  The NEXT frame's remote stores land in the other ring slot of every peer, so the
+        // barrier also waits until this rank has copied that slot's previous frame to its host (pipelined frames).
+        const int other = (int)((ctx->ring_seq + 1u) & 1u);
+        if (ring && ctx->slot_used[other]) VRT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[other], 0));
         if (ctx->exchange_mode == VRT_EXCHANGE_PEER_FLAGS) {
             uint32_t* flags[8] = {nullptr};
             for (int r = 0; r < ctx->world; r++) flags[r] = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(ctx->peer_fb[r]) + 2 * ctx->fb_bytes);
@@ -498,10 +642,32 @@ int vrt_trace(vrt_ctx* ctx, const vrt_camera* camera, const vrt_sun* sun) {
             if (r != ncclSuccess) return fail(ctx, VRT_E_NCCL, "ncclAllReduce failed: %s", g_nccl.GetErrorString(r));
         }
     }
+    if (P.tile_order) {
+        // every `interval` frames (and after the first): sort the costs this frame reported into the next frames' order.  Dealt
+        // schedules sort AFTER the frame barrier, when every rank's costs of this frame have arrived: all ranks sort the same array.
+        if (ctx->sched_frames % ctx->sched_interval == 0)
+            VRT_CUDA(ctx, launch_sched_sort(P.tile_cost, ctx->sched_tiles, ctx->d_order, ctx->d_sched_scratch, ctx->stream, &info));
+        ctx->sched_frames++;
+    }
     VRT_CUDA(ctx, cudaEventRecord(ctx->ev_end, ctx->stream));
     ctx->timing_valid = true;
     ctx->last_launches = info.launches;
+    if (ring) ctx->ring_seq++;
     return VRT_OK;
+}
+
+// device -> host copy of what this context holds of the frame in d_fb: its own rows, or the whole image after an exchange
+void host_span(const vrt_ctx* ctx, size_t* from, size_t* n) {
+    const bool whole = ctx->world > 1 || ctx->interleave || ctx->sched_mode == VRT_SCHED_DEAL;
+    *from = whole ? 0 : (size_t)ctx->row_begin * ctx->cfg.width * 4;
+    *n = whole ? ctx->fb_bytes : (size_t)(ctx->row_end - ctx->row_begin) * ctx->cfg.width * 4;
+}
+
+}  // namespace
+
+int vrt_trace(vrt_ctx* ctx, const vrt_camera* camera, const vrt_sun* sun) {
+    if (!ctx) return VRT_E_INVALID;
+    return trace_frame(ctx, camera, sun, false);
 }
 
 int vrt_sync(vrt_ctx* ctx) {
@@ -517,38 +683,18 @@ int vrt_sync(vrt_ctx* ctx) {
 int vrt_trace_to_host_async(vrt_ctx* ctx, const vrt_camera* camera, const vrt_sun* sun, uint8_t* rgba8_host, size_t bytes) {
     if (!ctx) return VRT_E_INVALID;
     if (rgba8_host && bytes != ctx->fb_bytes) return fail(ctx, VRT_E_INVALID, "vrt_trace_to_host_async: need a %zu-byte buffer", ctx->fb_bytes);
-    if (ctx->d_fb != ctx->d_fb_own && ctx->d_fb != ctx->d_fb_ring1)
-        return fail(ctx, VRT_E_STATE, "vrt_trace_to_host_async: not available while a caller-owned framebuffer is attached");
-    VRT_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
-    if (!ctx->copy_stream) {  // first use: second framebuffer, copy stream, events
-        VRT_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; i++) {
-            VRT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_traced[i], cudaEventDisableTiming));
-            VRT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
-        }
-    }
-    const int slot = (int)(ctx->async_frames & 1u);
-    uint32_t* const fb = slot ? ctx->d_fb_ring1 : ctx->d_fb_own;
-    // the trace may not overwrite this slot before its previous contents (frame k-2) have reached the host
-    if (ctx->slot_used[slot]) VRT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[slot], 0));
-    uint32_t* const saved = ctx->d_fb;
-    ctx->d_fb = fb;
-    ctx->barrier_after_copy = ctx->slot_used[slot ^ 1] ? ctx->ev_copied[slot ^ 1] : nullptr;
-    const int rc = vrt_trace(ctx, camera, sun);
-    ctx->barrier_after_copy = nullptr;
-    ctx->d_fb = saved;
+    if (!owns_fb(ctx)) return fail(ctx, VRT_E_STATE, "vrt_trace_to_host_async: not available while a caller-owned framebuffer is attached");
+    const int slot = (int)(ctx->ring_seq & 1u);
+    const int rc = trace_frame(ctx, camera, sun, true);
     if (rc != VRT_OK) return rc;
     VRT_CUDA(ctx, cudaEventRecord(ctx->ev_traced[slot], ctx->stream));
     VRT_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_traced[slot], 0));
-    const size_t off = (size_t)ctx->row_begin * ctx->cfg.width * 4;
-    const bool whole = ctx->world > 1 || ctx->interleave;
-    const size_t n = whole ? ctx->fb_bytes : (size_t)(ctx->row_end - ctx->row_begin) * ctx->cfg.width * 4;
-    const size_t from = whole ? 0 : off;
+    size_t from, n;
+    host_span(ctx, &from, &n);
     if (rgba8_host)  // NULL: take part in the frame ring (multi-GPU ranks that do not need the pixels on their host) without a copy
-        VRT_CUDA(ctx, cudaMemcpyAsync(rgba8_host + from, reinterpret_cast<const uint8_t*>(fb) + from, n, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        VRT_CUDA(ctx, cudaMemcpyAsync(rgba8_host + from, reinterpret_cast<const uint8_t*>(ctx->d_fb) + from, n, cudaMemcpyDeviceToHost, ctx->copy_stream));
     VRT_CUDA(ctx, cudaEventRecord(ctx->ev_copied[slot], ctx->copy_stream));
     ctx->slot_used[slot] = true;
-    ctx->async_frames++;
     return VRT_OK;
 }
 
@@ -564,12 +710,10 @@ int vrt_read_framebuffer(vrt_ctx* ctx, uint8_t* rgba8_host, size_t bytes) {
 int vrt_trace_to_host(vrt_ctx* ctx, const vrt_camera* camera, const vrt_sun* sun, uint8_t* rgba8_host, size_t bytes) {
     if (!ctx) return VRT_E_INVALID;
     if (!rgba8_host || bytes != ctx->fb_bytes) return fail(ctx, VRT_E_INVALID, "vrt_trace_to_host: need a %zu-byte buffer", ctx->fb_bytes);
-    const int rc = vrt_trace(ctx, camera, sun);
+    const int rc = trace_frame(ctx, camera, sun, false);
     if (rc != VRT_OK) return rc;
-    const size_t off = (size_t)ctx->row_begin * ctx->cfg.width * 4;
-    const bool whole = ctx->world > 1 || ctx->interleave;
-    const size_t n = whole ? ctx->fb_bytes : (size_t)(ctx->row_end - ctx->row_begin) * ctx->cfg.width * 4;
-    const size_t from = whole ? 0 : off;
+    size_t from, n;
+    host_span(ctx, &from, &n);
     VRT_CUDA(ctx, cudaMemcpyAsync(rgba8_host + from, reinterpret_cast<const uint8_t*>(ctx->d_fb) + from, n, cudaMemcpyDeviceToHost, ctx->stream));
     VRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return VRT_OK;
@@ -608,7 +752,7 @@ int vrt_insert_voxels(vrt_ctx* ctx, const uint32_t* xyzm_host, size_t count, uin
     uint32_t* last_writer = nullptr;
     int rc = VRT_OK;
     unsigned long long totals[4] = {0, 0, 0, 0};
-    LaunchInfo info = {0u, 0ull};
+    LaunchInfo info = {0u};
     auto cuda_ok = [&](cudaError_t e) {
         if (e == cudaSuccess) return true;
         rc = fail(ctx, VRT_E_CUDA, "vrt_insert_voxels: %s", cudaGetErrorString(e));
@@ -693,7 +837,7 @@ int vrt_denoise(vrt_ctx* ctx, const vrt_denoise_params* params, uint32_t out_wid
         VRT_CUDA(ctx, cudaEventCreate(&ctx->ev_dn_begin));
         VRT_CUDA(ctx, cudaEventCreate(&ctx->ev_dn_end));
     }
-    LaunchInfo info = {0u, 0ull};
+    LaunchInfo info = {0u};
     VRT_CUDA(ctx, cudaEventRecord(ctx->ev_dn_begin, ctx->stream));
     VRT_CUDA(ctx, launch_denoise(ctx->d_fb, ctx->d_dn_decoded, ctx->cfg.width, ctx->cfg.height, *params, ctx->d_denoised, out_width, out_height, (flags & VRT_DENOISE_BGRA) != 0u,
                                  ctx->stream, &info));
@@ -743,14 +887,13 @@ int vrt_trace_rays(vrt_ctx* ctx, const vrt_ray* rays_device, vrt_ray_hit* hits_d
     std::memset(&sun, 0, sizeof(sun));
     TraceParams P;
     fill_params(ctx, &cam, &sun, P);
-    LaunchInfo info = {0u, 0ull};
-    if (ctx->accel_dirty) {
+    LaunchInfo info = {0u};
+    if (ctx->accel_dirty || ctx->occ_dirty) {
         const size_t n_cells = (size_t)ctx->grid.dim_x * ctx->grid.dim_y * ctx->grid.dim_z;
-        VRT_CUDA(ctx, launch_build_accel(P, ctx->d_occ_dense, ctx->d_dist, ctx->d_dist_tmp, n_cells, ctx->stream, &info));
-        ctx->accel_dirty = false;
+        VRT_CUDA(ctx, launch_build_accel(P, ctx->d_occ_dense, ctx->d_dist, ctx->d_dist_tmp, n_cells, !ctx->accel_dirty, ctx->stream, &info));
+        ctx->accel_dirty = ctx->occ_dirty = false;
     }
     VRT_CUDA(ctx, launch_trace_rays(P, rays_device, hits_device, count, ctx->stream, &info));
-    ctx->tile_base += info.counter_advance;
     ctx->last_launches = info.launches;
     return VRT_OK;
 }
@@ -838,6 +981,56 @@ int vrt_framebuffer_device_ptr(vrt_ctx* ctx, void** out_device_ptr) {
     return VRT_OK;
 }
 
+int vrt_last_trace_kernel_ms(vrt_ctx* ctx, float* out_ms) {
+    if (!ctx) return VRT_E_INVALID;
+    if (!out_ms) return fail(ctx, VRT_E_INVALID, "vrt_last_trace_kernel_ms: out is NULL");
+    if (!ctx->timing_valid) return fail(ctx, VRT_E_STATE, "vrt_last_trace_kernel_ms: no trace yet");
+    VRT_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    VRT_CUDA(ctx, cudaEventSynchronize(ctx->ev_kernel_end));
+    VRT_CUDA(ctx, cudaEventElapsedTime(out_ms, ctx->ev_begin, ctx->ev_kernel_end));
+    return VRT_OK;
+}
+
+int vrt_set_schedule(vrt_ctx* ctx, uint32_t mode, uint32_t interval) {
+    if (!ctx) return VRT_E_INVALID;
+    if (mode > VRT_SCHED_DEAL) return fail(ctx, VRT_E_INVALID, "vrt_set_schedule: unknown mode %u", mode);
+    if (mode == VRT_SCHED_DEAL) {
+        if (!ctx->interleave) return fail(ctx, VRT_E_STATE, "vrt_set_schedule: VRT_SCHED_DEAL needs a context created with VRT_FLAG_INTERLEAVE (part_rank / part_world)");
+        if (!ctx->d_fb_own || !owns_fb(ctx)) return fail(ctx, VRT_E_STATE, "vrt_set_schedule: VRT_SCHED_DEAL needs the context-owned framebuffer");
+    }
+    if (mode != ctx->sched_mode) ctx->sched_tiles = 0;  // another tile space / another set of tiles per rank: start from the default order
+    ctx->sched_mode = mode;
+    ctx->sched_interval = interval ? interval : 8u;
+    return VRT_OK;
+}
+
+int vrt_sched_get_costs(vrt_ctx* ctx, uint16_t* costs_host, size_t count) {
+    if (!ctx) return VRT_E_INVALID;
+    if (!costs_host || count > ctx->tiles_global) return fail(ctx, VRT_E_INVALID, "vrt_sched_get_costs: at most %u tiles", ctx->tiles_global);
+    VRT_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    // the array the most recent frame wrote (frames alternate between two, so that a fast peer's next frame cannot disturb a sort)
+    const int parity = ctx->sched_frames ? (int)((ctx->sched_frames - 1u) & 1u) : 0;
+    VRT_CUDA(ctx, cudaMemcpyAsync(costs_host, ctx->d_cost[parity], count * sizeof(uint16_t), cudaMemcpyDeviceToHost, ctx->stream));
+    VRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VRT_OK;
+}
+
+int vrt_sched_set_costs(vrt_ctx* ctx, const uint16_t* costs_host, size_t count) {
+    if (!ctx) return VRT_E_INVALID;
+    if (!costs_host || count == 0 || count > ctx->tiles_global) return fail(ctx, VRT_E_INVALID, "vrt_sched_set_costs: 1 .. %u tiles", ctx->tiles_global);
+    if (ctx->sched_mode == VRT_SCHED_STATIC) return fail(ctx, VRT_E_STATE, "vrt_sched_set_costs: no schedule selected (vrt_set_schedule)");
+    VRT_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    for (int i = 0; i < 2; i++) {
+        const int rc = stage_upload(ctx, ctx->d_cost[i], costs_host, count * sizeof(uint16_t));
+        if (rc != VRT_OK) return rc;
+    }
+    LaunchInfo info = {0u};
+    VRT_CUDA(ctx, launch_sched_sort(ctx->d_cost[0], (uint32_t)count, ctx->d_order, ctx->d_sched_scratch, ctx->stream, &info));
+    ctx->sched_tiles = (uint32_t)count;
+    ctx->sched_frames = 1;  // the order is in place: no re-initialisation, next sort at the next multiple of the interval
+    return VRT_OK;
+}
+
 int vrt_comm_get_unique_id(uint8_t id_out[VRT_NCCL_ID_BYTES]) {
     static_assert(sizeof(ncclUniqueId) == VRT_NCCL_ID_BYTES, "ncclUniqueId size");
     if (!id_out) return fail(nullptr, VRT_E_INVALID, "vrt_comm_get_unique_id: out is NULL");
@@ -875,6 +1068,23 @@ int vrt_comm_init(vrt_ctx* ctx, int rank, int world, const uint8_t id[VRT_NCCL_I
     }
     if (world > 1 && ctx->interleave && !ctx->d_gather)
         VRT_CUDA(ctx, cudaMalloc(&ctx->d_gather, (size_t)world * ctx->strips_max * kStripRows * ctx->cfg.width * 4));
+    if (world > 1) {
+        // NCCL connects its channels lazily, inside the first collective of each kind: pay for that here (every rank calls
+        // vrt_comm_init), not inside the first frames a caller times.
+        ncclResult_t r = g_nccl.AllReduce(ctx->d_barrier, ctx->d_barrier, 1, ncclInt32, ncclSum, ctx->comm, ctx->stream);
+        if (r == ncclSuccess) {
+            if (ctx->interleave) {
+                const size_t slab_bytes = (size_t)ctx->strips_max * kStripRows * ctx->cfg.width * 4;
+                r = g_nccl.AllGather(reinterpret_cast<const uint8_t*>(ctx->d_gather) + (size_t)rank * slab_bytes, ctx->d_gather, slab_bytes, ncclUint8, ctx->comm, ctx->stream);
+            } else {
+                const size_t slab_bytes = (size_t)rows * ctx->cfg.width * 4;
+                r = g_nccl.AllGather(reinterpret_cast<const uint8_t*>(ctx->d_fb_own) + (size_t)ctx->row_begin * ctx->cfg.width * 4, ctx->d_fb_own, slab_bytes, ncclUint8, ctx->comm, ctx->stream);
+            }
+        }
+        if (r != ncclSuccess) return fail(ctx, VRT_E_NCCL, "vrt_comm_init: warm-up collective failed: %s", g_nccl.GetErrorString(r));
+        VRT_CUDA(ctx, cudaMemsetAsync(ctx->d_barrier, 0, 4, ctx->stream));
+        VRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
     return VRT_OK;
 }
 
@@ -882,7 +1092,7 @@ int vrt_comm_get_ipc_handle(vrt_ctx* ctx, uint8_t handle_out[VRT_IPC_HANDLE_BYTE
     static_assert(sizeof(cudaIpcMemHandle_t) == VRT_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
     if (!ctx) return VRT_E_INVALID;
     if (!handle_out) return fail(ctx, VRT_E_INVALID, "vrt_comm_get_ipc_handle: out is NULL");
-    if (ctx->d_fb != ctx->d_fb_own) return fail(ctx, VRT_E_STATE, "vrt_comm_get_ipc_handle: only the context-owned framebuffer can be shared");
+    if (!owns_fb(ctx)) return fail(ctx, VRT_E_STATE, "vrt_comm_get_ipc_handle: only the context-owned framebuffer can be shared");
     VRT_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
     cudaIpcMemHandle_t h;
     VRT_CUDA(ctx, cudaIpcGetMemHandle(&h, ctx->d_fb_own));
@@ -919,6 +1129,15 @@ int vrt_comm_set_exchange(vrt_ctx* ctx, uint32_t mode) {
         *ctx->h_barrier_error = 0;
     }
     ctx->exchange_mode = mode;
+    if (mode == VRT_EXCHANGE_PEER_FLAGS && ctx->world > 1) {
+        // one round of the flag barrier now (every rank makes this call): the first touch of each peer mapping happens here, and
+        // all ranks leave set-up together
+        uint32_t* flags[8] = {nullptr};
+        for (int r = 0; r < ctx->world; r++) flags[r] = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(ctx->peer_fb[r]) + 2 * ctx->fb_bytes);
+        VRT_CUDA(ctx, launch_peer_barrier(flags, (uint32_t)ctx->rank, (uint32_t)ctx->world, ++ctx->barrier_frame, ctx->h_barrier_error, ctx->stream, nullptr));
+        VRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (*reinterpret_cast<volatile int*>(ctx->h_barrier_error) != 0) return fail(ctx, VRT_E_STATE, "vrt_comm_set_exchange: a rank did not join the flag barrier");
+    }
     return VRT_OK;
 }
 

@@ -19,6 +19,7 @@ VRT_FLAG_INTERLEAVE = 4
 VRT_EXCHANGE_ALLGATHER = 0
 VRT_EXCHANGE_PEER_STORE = 1
 VRT_EXCHANGE_PEER_FLAGS = 2
+VRT_SCHED_STATIC, VRT_SCHED_LPT, VRT_SCHED_DEAL = 0, 1, 2
 VRT_NCCL_ID_BYTES = 128
 VRT_IPC_HANDLE_BYTES = 64
 
@@ -164,7 +165,11 @@ VRT_SYMBOLS = {
     "vrt_read_aov": (C.c_int, [_P, _P, _SZ]),
     "vrt_get_counters": (C.c_int, [_P, C.POINTER(Counters)]),
     "vrt_last_trace_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
+    "vrt_last_trace_kernel_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "vrt_last_trace_launches": (C.c_int, [_P, C.POINTER(C.c_uint32)]),
+    "vrt_set_schedule": (C.c_int, [_P, C.c_uint32, C.c_uint32]),
+    "vrt_sched_get_costs": (C.c_int, [_P, _P, _SZ]),
+    "vrt_sched_set_costs": (C.c_int, [_P, _P, _SZ]),
     "vrt_set_stream": (C.c_int, [_P, _P]),
     "vrt_insert_voxels": (C.c_int, [_P, _P, _SZ, C.POINTER(C.c_uint32)]),
     "vrt_download_buffer": (C.c_int, [_P, C.c_uint32, _SZ, _P, _SZ]),
@@ -232,6 +237,7 @@ VRT_HOST_SYMBOLS = {
     "vrt_renderer_present_to_host": (C.c_int, [_P, C.POINTER(DenoiseParams), C.c_uint32, C.c_uint32, C.c_uint32, _P, _SZ]),
     "vrt_scene_terrain_materials": (C.c_uint32, [_P, C.c_uint32]),
     "vrt_scene_synthetic": (C.c_int, [C.c_uint32, C.c_uint32, _P, _P]),
+    "vrt_scene_synthetic_box": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _P, _P]),
     "vrt_scene_synthetic_fill": (C.c_int, [_P, C.c_uint32]),
     "vrt_vox_validate_header": (C.c_int, [_P, _SZ]),
     "vrt_vox_parse": (C.c_int, [C.POINTER(_P), _P, _SZ, C.c_int]),
@@ -731,6 +737,28 @@ class Context:
         ms = C.c_float()
         self._check(self._l.vrt_last_trace_ms(self.handle, C.byref(ms)))
         return ms.value
+
+    def last_trace_kernel_ms(self) -> float:
+        """The part of last_trace_ms() before the exchange: (rebuild +) trace kernel."""
+        ms = C.c_float()
+        self._check(self._l.vrt_last_trace_kernel_ms(self.handle, C.byref(ms)))
+        return ms.value
+
+    def set_schedule(self, mode: int, interval: int = 0):
+        self._check(self._l.vrt_set_schedule(self.handle, mode, interval))
+
+    @property
+    def n_tiles(self) -> int:
+        return ((self.width + 7) // 8) * ((self.height + 3) // 4)
+
+    def sched_costs(self, count: int | None = None) -> np.ndarray:
+        out = np.zeros(count or self.n_tiles, dtype=np.uint16)
+        self._check(self._l.vrt_sched_get_costs(self.handle, _ptr(out), out.shape[0]))
+        return out
+
+    def sched_set_costs(self, costs: np.ndarray):
+        a = np.ascontiguousarray(costs, dtype=np.uint16)
+        self._check(self._l.vrt_sched_set_costs(self.handle, _ptr(a), a.shape[0]))
 
     def last_trace_launches(self) -> int:
         n = C.c_uint32()

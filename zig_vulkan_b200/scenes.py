@@ -43,6 +43,19 @@ WORKLOADS = {
     "C5": Workload("C5", 512, 4, 3840, 2160, True, "512^3 voxel grid, 3840x2160, primary + 1 shadow ray, rows tiled across GPUs"),
 }
 
+# The reference application's own default configuration (src/main.zig:23,71,77-81,122-135, Sun.zig:4-11): 128 x 64 x 128 bricks of 4^3 at
+# scale 0.5 with min corner (-32,-16,-32), internal resolution 1024x576, 2 samples per pixel, max_bounce 2 (device value 3), sun
+# enabled with a disc of radius 5.  Every pixel takes the general shading path (jittered samples, scatter functions, sin-hash RNG).
+REF_DEFAULT = dict(dim=(128, 64, 128), brick_dim=4, min_point=(-32.0, -16.0, -32.0), scale=0.5, width=1024, height=576, spp=2, max_bounce=2, sun_radius=5.0)
+
+
+def build_ref_default_grid(seed: int = SEED) -> ffi.Grid:
+    g = ffi.Grid(REF_DEFAULT["dim"], brick_dim=4, min_point=REF_DEFAULT["min_point"], scale=REF_DEFAULT["scale"])
+    rc = g.fill_synthetic(seed)
+    if rc != 0:
+        raise ffi.VrtError(rc, "vrt_scene_synthetic_fill failed for the reference default grid")
+    return g
+
 
 def build_grid(n_voxels: int, brick_dim: int = 4, seed: int = SEED, brick_alloc: int = 0) -> ffi.Grid:
     """Cubic BrickGrid of world extent 64 filled with the synthetic terrain."""
