@@ -178,6 +178,30 @@ def test_sun():
     assert list(still.device.position) == [0.0, -1000.0, 0.0]
 
 
+def test_sun_cycle_takes_the_short_arc():
+    """Sun.update slerps through three orientations 120 degrees apart about z (Sun.zig:36-40,72).  The third segment (240 degrees
+    back to the identity) has a negative quaternion dot product: zalgebra's slerp negates one operand and keeps going the short
+    way (another 120 degrees), so the sun circles the grid at a steady pace — 12 degrees per update at speed 0.1 and dt 1 —
+    instead of swinging 240 degrees backwards."""
+    s = ffi.HostSun()
+    pos = []
+    for _ in range(61):  # two full cycles of 3 segments x 10 updates
+        s.update(1.0)
+        pos.append(np.array(list(s.device.position), dtype=np.float64))
+    steps = [np.degrees(np.arccos(np.clip(np.dot(a, b) / (np.linalg.norm(a) * np.linalg.norm(b)), -1, 1))) for a, b in zip(pos, pos[1:])]
+    assert max(steps) < 16.0 and min(steps) > 8.0, (min(steps), max(steps))
+    # the winding about z is monotonic: one full turn per 30 updates
+    ang = np.unwrap([np.arctan2(p[0], -p[1]) for p in pos])
+    assert np.all(np.diff(ang) > 0) or np.all(np.diff(ang) < 0)
+    assert abs(abs(ang[30] - ang[0]) - 2 * np.pi) < 0.15
+    # mid third segment: rotation by 300 degrees about z of (0,-1000,0)
+    s2 = ffi.HostSun()
+    for _ in range(26):
+        s2.update(1.0)
+    p = np.array(list(s2.device.position))
+    assert p[0] < -700 and p[1] < -300 and abs(p[2]) < 120, p
+
+
 def test_bench_path():
     o, q = zv.bench_path_pose(0.0)
     assert o == [0, 0, 0] and q == [1, 0, 0, 0]                      # Benchmark.zig:146,160

@@ -72,14 +72,24 @@ inline Quat qnorm(Quat q) {
     return {q.w / l, q.x / l, q.y / l, q.z / l};
 }
 inline Quat qlerp(Quat l, Quat r, float t) { return {lerp(l.w, r.w, t), lerp(l.x, r.x, t), lerp(l.y, r.y, t), lerp(l.z, r.z, t)}; }
+// zalgebra (kooparse/zalgebra@7cf3b90, build.zig.zon:20-23) is an un-vendored dependency: its source is not in the reference
+// tree, so this is a restatement of its published Quaternion.slerp from the algorithm, not from the text: the dot product's
+// absolute value is used (q and -q are the same rotation, so the right operand is negated when the dot is negative and the
+// interpolation takes the SHORTEST arc), nearly parallel operands fall back to a normalised lerp, otherwise
+// sin((1-t)a)/sin(a) * l + sin(t a)/sin(a) * r.  Call sites: Sun.zig:72 (three orientations 120 degrees apart about z: the third
+// segment, 240 degrees -> 0, has dot -0.5 and would sweep the long way round without the negation), Benchmark.zig:62.
+// Host-side convenience only — the device path takes finished vrt_camera / vrt_sun structs.
 inline Quat qslerp(Quat l, Quat r, float t) {
     const float threshold = 0.9995f;
-    const float cos_theta = qdot(l, r);
+    float cos_theta = qdot(l, r);
+    if (cos_theta < 0.0f) {
+        cos_theta = -cos_theta;
+        r = qscale(r, -1.0f);
+    }
     if (cos_theta > threshold) return qnorm(qlerp(l, r, t));
-    const float clamped = cos_theta < -1.0f ? -1.0f : (cos_theta > 1.0f ? 1.0f : cos_theta);
-    const float thetap = std::acos(clamped) * t;
-    const Quat qperp = qnorm(qsub(r, qscale(l, cos_theta)));
-    return qadd(qscale(l, std::cos(thetap)), qscale(qperp, std::sin(thetap)));
+    const float angle = std::acos(cos_theta > 1.0f ? 1.0f : cos_theta);
+    const float s = std::sin(angle);
+    return qadd(qscale(l, std::sin((1.0f - t) * angle) / s), qscale(r, std::sin(t * angle) / s));
 }
 inline Vec3 rotate(Quat q_in, Vec3 v) {
     const Quat q = qnorm(q_in);

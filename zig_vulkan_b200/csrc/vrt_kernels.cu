@@ -33,7 +33,13 @@ __global__ void __launch_bounds__(256) trace_ref_kernel(const __grid_constant__ 
 // (vrt_trav_warp.cuh).  The tile is written as eight 128-bit stores (4 texels each, gathered by shfl); in the
 // fused multi-GPU exchange the same stores also go to every peer's framebuffer over NVLink.
 // ----------------------------------------------------------------------------------------------------
-constexpr int kTunedThreads = 256;
+#ifndef VRT_TUNED_THREADS
+#define VRT_TUNED_THREADS 256
+#endif
+#ifndef VRT_TUNED_BLOCKS
+#define VRT_TUNED_BLOCKS 3
+#endif
+constexpr int kTunedThreads = VRT_TUNED_THREADS;
 constexpr uint32_t kTileW = 8, kTileH = 4;
 
 // 3 CTAs of 256 threads per SM (80 registers): measured 10 % faster than 2 (102 registers, no spills) and equal to 4 (64, spills).
@@ -51,11 +57,14 @@ VRT_DI void leave_queue(const TraceParams& P, uint32_t lane) {
 }
 
 template <int BD, bool AOV, bool SIMPLE>
-__global__ void __launch_bounds__(kTunedThreads, 3) trace_warp_kernel(const __grid_constant__ TraceParams P, const uint32_t tiles_x, const uint32_t tiles_total) {
+__global__ void __launch_bounds__(kTunedThreads, VRT_TUNED_BLOCKS) trace_warp_kernel(const __grid_constant__ TraceParams P, const uint32_t tiles_x, const uint32_t tiles_total) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t lx = lane & (kTileW - 1u), ly = lane >> 3;
     const uint32_t width = P.cam.image_width;
     PixelCounters pc = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+#if VRT_TMA_MASKS
+    if (BD != 4 && P.brick_dim == 16) brick_stage_init();
+#endif
 
     for (;;) {
         unsigned long long t = 0ull;
@@ -150,11 +159,14 @@ cudaError_t launch_trace_tuned(const TraceParams& P, bool aov, cudaStream_t stre
 // 32-byte hit records (two 128-bit stores each).  Persistent warps pull blocks of 32 rays from the work counter.
 // ----------------------------------------------------------------------------------------------------
 template <int BD>
-__global__ void __launch_bounds__(kTunedThreads, 3) trace_rays_kernel(const __grid_constant__ TraceParams P, const float4* __restrict__ rays,
+__global__ void __launch_bounds__(kTunedThreads, VRT_TUNED_BLOCKS) trace_rays_kernel(const __grid_constant__ TraceParams P, const float4* __restrict__ rays,
                                                                      uint4* __restrict__ hits, const unsigned long long count) {
     const uint32_t lane = threadIdx.x & 31u;
     const bool ignore_test = P.materials_have_none != 0u;  // CreateRay's ignore type is MAT_NONE (:182)
     const unsigned long long blocks = (count + 31ull) / 32ull;
+#if VRT_TMA_MASKS
+    if (BD != 4 && P.brick_dim == 16) brick_stage_init();
+#endif
     for (;;) {  // blocks of 32 rays from the same work counter as the pixel kernel: rays differ in cost by orders of magnitude
         unsigned long long t = 0ull;
         if (lane == 0) t = atomicAdd(P.tile_counter, 1ull);
@@ -186,7 +198,7 @@ cudaError_t launch_trace_rays(const TraceParams& P, const vrt_ray* rays, vrt_ray
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
     if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
     const unsigned long long warps_needed = (count + 31) / 32;
-    unsigned grid = (unsigned)(sms * 3);
+    unsigned grid = (unsigned)(sms * VRT_TUNED_BLOCKS);
     const unsigned long long blocks_needed = (warps_needed + kTunedThreads / 32 - 1) / (kTunedThreads / 32);
     if (grid > blocks_needed) grid = (unsigned)blocks_needed;
     if (P.brick_dim == 4) trace_rays_kernel<4><<<grid, kTunedThreads, 0, stream>>>(P, reinterpret_cast<const float4*>(rays), reinterpret_cast<uint4*>(hits), count);

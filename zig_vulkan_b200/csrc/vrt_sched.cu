@@ -18,7 +18,7 @@ namespace vrt {
 
 namespace {
 
-constexpr int kSortThreads = 256;
+constexpr int kSortThreads = 1024;  // tiles per block: 64 blocks for a 1080p frame, 254 for 4K -> a 16 K / 65 K-entry scan
 constexpr int kBins = 256;
 
 // monotonic 8-bit key of a 16-bit cost; bin 0 = most expensive
@@ -33,7 +33,7 @@ __device__ __forceinline__ uint32_t cost_bin(uint32_t c) {
     return 255u - q;
 }
 
-__global__ void __launch_bounds__(kSortThreads) sched_init_kernel(uint32_t* __restrict__ order, uint16_t* __restrict__ cost0, uint16_t* __restrict__ cost1, uint32_t n) {
+__global__ void __launch_bounds__(256) sched_init_kernel(uint32_t* __restrict__ order, uint16_t* __restrict__ cost0, uint16_t* __restrict__ cost1, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     order[i] = n - 1u - i;  // bottom-up: ground rows first (vrt_kernels.cu)
@@ -44,22 +44,20 @@ __global__ void __launch_bounds__(kSortThreads) sched_init_kernel(uint32_t* __re
 // hist[bin * nblk + blk] = tiles of block blk in bin
 __global__ void __launch_bounds__(kSortThreads) sched_hist_kernel(const uint16_t* __restrict__ cost, uint32_t n, uint32_t* __restrict__ hist) {
     __shared__ uint32_t sh[kBins];
-    sh[threadIdx.x] = 0u;
+    if (threadIdx.x < kBins) sh[threadIdx.x] = 0u;
     __syncthreads();
     const uint32_t i = blockIdx.x * kSortThreads + threadIdx.x;
     if (i < n) atomicAdd(&sh[cost_bin(cost[i])], 1u);
     __syncthreads();
-    hist[threadIdx.x * gridDim.x + blockIdx.x] = sh[threadIdx.x];
+    if (threadIdx.x < kBins) hist[threadIdx.x * gridDim.x + blockIdx.x] = sh[threadIdx.x];
 }
 
-// exclusive scan of m words in place, one CTA
-__global__ void __launch_bounds__(1024) sched_scan_kernel(uint32_t* __restrict__ data, uint32_t m) {
-    __shared__ uint32_t warp_sums[32];
-    const uint32_t per = (m + 1023u) / 1024u;
-    const uint32_t begin = threadIdx.x * per, end = min(begin + per, m);
+// exclusive scan of cnt words of shared memory in place (+ the running carry of earlier chunks), all 1024 threads
+__device__ __forceinline__ void scan_chunk(uint32_t* stage, uint32_t cnt, uint32_t* warp_sums, uint32_t& carry) {
+    const uint32_t per = (cnt + 1023u) / 1024u;
+    const uint32_t begin = min(threadIdx.x * per, cnt), end = min(begin + per, cnt);
     uint32_t sum = 0u;
-    for (uint32_t i = begin; i < end; i++) sum += data[i];
-    // block-wide exclusive scan of the 1024 partial sums
+    for (uint32_t i = begin; i < end; i++) sum += stage[i];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     uint32_t incl = sum;
     for (int d = 1; d < 32; d <<= 1) {
@@ -77,19 +75,40 @@ __global__ void __launch_bounds__(1024) sched_scan_kernel(uint32_t* __restrict__
         warp_sums[lane] = w;  // inclusive over warps
     }
     __syncthreads();
-    uint32_t run = incl - sum + (warp ? warp_sums[warp - 1u] : 0u);
+    uint32_t run = carry + incl - sum + (warp ? warp_sums[warp - 1u] : 0u);
     for (uint32_t i = begin; i < end; i++) {
-        const uint32_t v = data[i];
-        data[i] = run;
+        const uint32_t v = stage[i];
+        stage[i] = run;
         run += v;
     }
+    __syncthreads();
+    if (threadIdx.x == 1023u) carry = run;  // the last thread's running total = everything so far
 }
 
+// exclusive scan of m words in place, one CTA; m <= 64 * 1024 words are staged through shared memory so that the global
+// loads / stores are coalesced (a thread's serial chunk of `per` words is strided in global memory)
+constexpr uint32_t kScanSmemWords = 8192;
+__global__ void __launch_bounds__(1024) sched_scan_kernel(uint32_t* __restrict__ data, uint32_t m) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t stage[kScanSmemWords];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0u;
+    for (uint32_t base = 0; base < m; base += kScanSmemWords) {  // 2 trips for a 1080p frame, 8 for 4K
+        const uint32_t cnt = min(kScanSmemWords, m - base);
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < cnt; i += 1024u) stage[i] = data[base + i];
+        __syncthreads();
+        scan_chunk(stage, cnt, warp_sums, carry);
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < cnt; i += 1024u) data[base + i] = stage[i];
+    }
+}
 // order[base(bin, blk) + rank of this tile among the block's tiles of the same bin, in tile order] = tile   (stable)
 __global__ void __launch_bounds__(kSortThreads) sched_scatter_kernel(const uint16_t* __restrict__ cost, uint32_t n, const uint32_t* __restrict__ base,
                                                                      uint32_t* __restrict__ order) {
     __shared__ uint16_t warp_count[kSortThreads / 32][kBins];
-    for (int w = 0; w < kSortThreads / 32; w++) warp_count[w][threadIdx.x] = 0;
+    if (threadIdx.x < kBins)
+        for (int w = 0; w < kSortThreads / 32; w++) warp_count[w][threadIdx.x] = 0;
     __syncthreads();
     const uint32_t i = blockIdx.x * kSortThreads + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -99,7 +118,7 @@ __global__ void __launch_bounds__(kSortThreads) sched_scatter_kernel(const uint1
     const uint32_t rank_in_warp = (uint32_t)__popc(same & ((1u << lane) - 1u));
     if (valid && rank_in_warp == 0u) warp_count[warp][bin] = (uint16_t)__popc(same);
     __syncthreads();
-    {  // per bin (one thread each): exclusive prefix over the warps
+    if (threadIdx.x < kBins) {  // per bin (one thread each): exclusive prefix over the warps
         uint32_t acc = 0u;
         for (int w = 0; w < kSortThreads / 32; w++) {
             const uint32_t c = warp_count[w][threadIdx.x];
@@ -117,7 +136,7 @@ size_t sched_scratch_words(uint32_t n_tiles) { return (size_t)kBins * ((n_tiles 
 
 cudaError_t launch_sched_init(uint32_t* order, uint16_t* cost0, uint16_t* cost1, uint32_t n_tiles, cudaStream_t stream, LaunchInfo* info) {
     if (n_tiles == 0) return cudaSuccess;
-    sched_init_kernel<<<(n_tiles + kSortThreads - 1) / kSortThreads, kSortThreads, 0, stream>>>(order, cost0, cost1, n_tiles);
+    sched_init_kernel<<<(n_tiles + 255) / 256, 256, 0, stream>>>(order, cost0, cost1, n_tiles);
     if (info) info->launches++;
     return cudaGetLastError();
 }

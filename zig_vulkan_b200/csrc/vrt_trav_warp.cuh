@@ -143,6 +143,87 @@ VRT_DI int brick_hit_warp4(const TraceParams& P, const Ray& r, bool ignore_test,
     return found;
 }
 
+#ifndef VRT_TMA_MASKS
+#define VRT_TMA_MASKS 0
+#endif
+#if VRT_TMA_MASKS
+// ---- TMA staging of 16^3 brick masks (brick_dim 16, BASELINE config 4) — MEASURED AND LEFT OFF (build with -DVRT_TMA_MASKS=1) -----
+// The north star names "brick mask staged through TMA into shared memory".  This is that, where it has its best case; it is
+// bit-exact and 14 % slower than the register-cached mask word (profiles/README.md "TMA staging", ncu captures of both builds
+// under profiles/): the bulk copy + mbarrier wait sit in front of every brick test, while the word cache already removes most
+// loads.  For 4^3 bricks the whole mask is one 8-byte load — there is nothing to stage.
+// A 16^3 brick's occupancy mask is 512 bytes = four cache lines, and a voxel DDA touches them one word at a time along a
+// dependent chain.  The rays a warp parks in one phase sit on few distinct bricks (a 16^3 brick covers many pixels), so phase B
+// first copies the masks of up to kStageSlots distinct bricks into shared memory with one bulk-async copy each
+// (cp.async.bulk, SASS UBLKCP; completion on a per-warp mbarrier) and the DDA then reads words with LDS.  Lanes whose brick
+// did not get a slot read global memory as before.
+constexpr int kStageSlots = 2;
+constexpr int kStageWords = 128;  // 512 bytes
+struct BrickStage {
+    alignas(128) uint32_t mask[8][kStageSlots][kStageWords];  // [warp of the CTA][slot][word]
+    alignas(8) unsigned long long bar[8];
+    uint32_t phase[8];
+};
+VRT_DI BrickStage& brick_stage() {
+    __shared__ BrickStage s;
+    return s;
+}
+VRT_DI uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// every thread of the CTA, once, before the first traversal (kernels with brick_dim == 16 only)
+VRT_DI void brick_stage_init() {
+    BrickStage& s = brick_stage();
+    if ((threadIdx.x & 31u) == 0u) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s.bar[threadIdx.x >> 5])) : "memory");
+        s.phase[threadIdx.x >> 5] = 0u;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+}
+// Called by the parked lanes of a warp (mask `lanes`) with their brick's mask offset; returns this lane's slot or -1.
+VRT_DI int brick_stage_masks(const TraceParams& P, unsigned lanes, uint32_t brick_index, unsigned long long mask_base) {
+    BrickStage& s = brick_stage();
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const bool in_bounds = mask_base + 4ull * kStageWords <= P.n_occupancy;
+    const unsigned peers = __match_any_sync(lanes, brick_index);
+    const int leader = __ffs(peers) - 1;
+    const bool is_leader = (int)lane == leader && in_bounds;
+    const unsigned leaders = __ballot_sync(lanes, is_leader);
+    const int my_rank = __popc(leaders & ((1u << lane) - 1u));
+    const int leader_rank = __shfl_sync(lanes, my_rank, leader);
+    int slot = (((leaders >> leader) & 1u) && leader_rank < kStageSlots) ? leader_rank : -1;
+    const int n_staged = min(__popc(leaders), kStageSlots);
+    if (n_staged == 0) return -1;  // uniform over `lanes`
+    const uint32_t bar = smem_u32(&s.bar[warp]);
+    const uint32_t phase = s.phase[warp];
+    __syncwarp(lanes);
+    if ((int)lane == __ffs(lanes) - 1) {
+        // the slots were last read through the generic proxy (previous phase B): order those reads before the async writes
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(n_staged * 4 * kStageWords)) : "memory");
+        s.phase[warp] = phase ^ 1u;
+    }
+    __syncwarp(lanes);
+    if (is_leader && my_rank < kStageSlots) {
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(&s.mask[warp][my_rank][0])),
+                     "l"(P.occupancy + mask_base), "r"((uint32_t)(4 * kStageWords)), "r"(bar)
+                     : "memory");
+    }
+    uint32_t done = 0u;
+    for (int tries = 0; tries < (1 << 22) && !done; tries++) {  // bounded: a copy that never lands must not hang the GPU
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(done)
+            : "r"(bar), "r"(phase)
+            : "memory");
+    }
+    return done ? slot : -1;
+}
+#endif  // VRT_TMA_MASKS
+
 // The same for 8^3 and 16^3 bricks (brick_dim is a specialization constant upstream, State.zig:5; 16 is this repo's documented
 // extension).  State layout: 6-bit fields (x+bd) | (z+bd) << 6 | (y+bd) << 12 — inside iff bit log2(bd) of every field is set — and
 // voxel_index in bits 18+.  The brick's mask lives in the occupancy buffer (:415); the 32-bit word holding the current voxel's
@@ -166,6 +247,10 @@ VRT_DI int brick_hit_warp_n(const TraceParams& P, const Ray& r, bool ignore_test
     const int stx = ray_step.x * (1 + (1 << 18)), stz = ray_step.z * ((1 << 6) + (bd << 18)), sty = ray_step.y * ((1 << 12) + ((bd * bd) << 18));
     const uint32_t brick_index = grid_index < P.n_brick_indices ? __ldg(P.brick_indices + grid_index) : 0u;  // :337
     const unsigned long long mask_base = (unsigned long long)brick_index * P.brick_bytes;                    // :390
+#if VRT_TMA_MASKS
+    const int slot = bd == 16 ? brick_stage_masks(P, lanes, brick_index, mask_base) : -1;                     // 16^3: mask staged in shared memory
+    const uint32_t* staged = slot >= 0 ? brick_stage().mask[threadIdx.x >> 5][slot] : nullptr;
+#endif
     int word_at = -1;
     uint32_t word = 0u;
     int prev = state;
@@ -176,6 +261,10 @@ VRT_DI int brick_hit_warp_n(const TraceParams& P, const Ray& r, bool ignore_test
         if ((voxel_index >> 5) != word_at) {
             word_at = voxel_index >> 5;
             const unsigned long long at = mask_base + 4ull * (unsigned long long)word_at;
+#if VRT_TMA_MASKS
+            if (staged) word = staged[word_at];
+            else
+#endif
             word = at < P.n_occupancy ? __ldg(reinterpret_cast<const uint32_t*>(P.occupancy + at)) : 0u;  // bytes :415 reads one at a time
         }
         if ((word >> (voxel_index & 31)) & 1u) {  // :415-417
