@@ -410,7 +410,77 @@ def measure(rig, grid, mats, W, H, brick_dim, cam, sun, steps, warmup, with_e2e=
     e2e_s = rig.reduce([time.perf_counter() - t0])[0]
     res["e2e_s"], res["latency_ms"] = e2e_s, lat_s / n_lat * 1e3
     res["e2e_frame_ok"] = bool(np.array_equal(host_frames[(steps - 1) & 1].numpy().reshape(H, W, 4), img)) if rank == 0 else None
+    if world > 1 and ctx.interleaved:
+        res["e2e_host"] = e2e_host_assembled(rig, ctx, cam, sun, W, H, steps, img)
     return res
+
+
+def e2e_host_assembled(rig, ctx, cam, sun, W, H, steps, want_img):
+    """N > 1 with the host as the consumer: no device-side exchange (VRT_EXCHANGE_HOST) — every rank DMAs its own strips straight into
+    ONE frame in shared pinned host memory (POSIX shm, cudaHostRegister'ed by each process), N PCIe links at once.  Two frames in
+    flight per rank; the timed region ends when every rank's last copy has landed (vrt_sync + barrier)."""
+    import numpy as np
+    from multiprocessing import shared_memory
+    from zig_vulkan_b200 import ffi
+
+    torch, dist = rig.torch, rig.dist
+    fb = W * H * 4
+    name = [f"vrt_bench_{os.getpid()}" if rig.rank == 0 else None]
+    dist.broadcast_object_list(name, 0)
+    shm = shared_memory.SharedMemory(name=name[0], create=True, size=2 * fb) if rig.rank == 0 else None
+    dist.barrier()
+    if shm is None:
+        shm = shared_memory.SharedMemory(name=name[0])
+    frames = np.frombuffer(shm.buf, dtype=np.uint8, count=2 * fb)
+    ptr = frames.ctypes.data
+    rt = torch.cuda.cudart()
+    registered = int(rt.cudaHostRegister(ptr, 2 * fb, 0)) == 0
+    out = None
+    try:
+        ctx.comm_set_exchange(ffi.VRT_EXCHANGE_HOST)
+        ctx.set_schedule(ffi.VRT_SCHED_LPT, 8)
+        if rig.rank == 0:
+            frames[:] = 0
+        for i in range(9):  # warm-up: the first sort of the new (local) tile space is in here
+            ctx.trace_to_host_async(cam, sun, ptr + (i & 1) * fb)
+        ctx.sync()
+        rig.barrier()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            rig.flush.fill_(i & 0xFF)
+            ctx.trace_to_host_async(cam, sun, ptr + (i & 1) * fb)
+        ctx.sync()
+        rig.barrier()
+        secs = rig.reduce([time.perf_counter() - t0])[0]
+        ok = bool(np.array_equal(frames[((steps - 1) & 1) * fb:][:fb].reshape(H, W, 4), want_img)) if rig.rank == 0 else None
+        out = {"seconds": secs, "frame_ok": ok, "pinned": registered, "d2h_bytes_per_step_per_rank": fb // rig.world}
+    finally:
+        rig.barrier()
+        if registered:
+            rt.cudaHostUnregister(ptr)
+        del frames
+        shm.close()
+        if rig.rank == 0:
+            shm.unlink()
+    return out
+
+
+def e2e_record(m, rays, steps, n_pixels, world):
+    """The headline: frames through the C ABI with host buffers.  N = 1: vrt_trace_to_host_async into pinned memory.  N > 1: the
+    host-assembled exchange (every rank's strips over its own PCIe link into one shared pinned frame); the variant that first
+    assembles the frame on every GPU over NVLink and then ships it through rank 0's link alone is reported beside it."""
+    funnel = {"value": rays * steps / m["e2e_s"] / 1e6, "ms_per_step": m["e2e_s"] / steps * 1e3, "frame_latency_ms": m["latency_ms"], "frame_ok": m["e2e_frame_ok"]}
+    how = ("vrt_trace_to_host_async per frame (camera+sun host structs in, RGBA8 frame into pinned host memory, 2 frames in flight), "
+           "L2 flush enqueued between frames inside the timed region; frame_latency_ms = blocking vrt_trace_to_host")
+    h = m.get("e2e_host")
+    if h:
+        return {"value": rays * steps / h["seconds"] / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 128 * world, "d2h_bytes_per_step": n_pixels * 4,
+                "ms_per_step": h["seconds"] / steps * 1e3, "frame_ok": h["frame_ok"], "pinned": h["pinned"],
+                "how": "VRT_EXCHANGE_HOST: no device-side exchange; " + how.split(";")[0] + f"; each of the {world} ranks copies its own 4-row strips into ONE "
+                       "frame in shared pinned host memory over its own PCIe link; timed until every rank's last copy has landed",
+                "via_rank0_after_device_exchange": funnel}
+    funnel.update({"unit": "Mrays/s", "h2d_bytes_per_step": 128, "d2h_bytes_per_step": n_pixels * 4, "how": how})
+    return funnel
 
 
 def main():
@@ -495,10 +565,7 @@ def main():
                          "traffic_source": prof.get("source"), "peak_kind": peak_kind, "algorithmic_bytes_per_launch": int(alg_bytes // world), "kernel_ms": kernel_ms,
                          "note": "request-byte model of the reference algorithm (DESIGN.md); DRAM is ~0.3 % busy — the kernel is issue-bound, see `issue`",
                          "issue": issue},
-            "e2e": {"value": rays * args.steps / m["e2e_s"] / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 128, "d2h_bytes_per_step": n_pixels * 4,
-                    "ms_per_step": m["e2e_s"] / args.steps * 1e3, "frame_latency_ms": m["latency_ms"], "frame_ok": m["e2e_frame_ok"],
-                    "how": "vrt_trace_to_host_async per frame (camera+sun host structs in, RGBA8 frame into pinned host memory, 2 frames in flight), "
-                           "L2 flush enqueued between frames inside the timed region; frame_latency_ms = blocking vrt_trace_to_host"},
+            "e2e": e2e_record(m, rays, args.steps, n_pixels, world),
             "gpu_launches": m["launches_per_step"] * args.steps, "wall_ms": m["wall_ms"], "clocks": clocks,
             "frame_crc": m["crc"],
         }
@@ -518,8 +585,7 @@ def main():
             line["c5"] = {"workload": scenes.WORKLOADS["C5"].description, "rays_per_step": c5["rays"], "ms_per_step": ms5, "value": c5["rays"] / (ms5 * 1e-3) / 1e6,
                           "unit": "Mrays/s", "step_ms": stats(m5["step_max"]), "exchange": m5["exchange"], "schedule": m5["schedule"], "mode_candidates_ms": m5["candidates_ms"],
                           "per_rank_kernel_ms": {"max": m5["kernel_ms_max"], "min": m5["kernel_ms_min"]}, "exchange_ms": m5["exchange_ms"], "frame_crc": m5["crc"],
-                          "e2e": {"value": c5["rays"] * max(20, args.steps // 4) / m5["e2e_s"] / 1e6, "ms_per_step": m5["e2e_s"] / max(20, args.steps // 4) * 1e3,
-                                  "d2h_bytes_per_step": 3840 * 2160 * 4, "frame_ok": m5["e2e_frame_ok"]}}
+                          "e2e": e2e_record(m5, c5["rays"], max(20, args.steps // 4), 3840 * 2160, rig.world)}
         m5["ctx"].close()
         ctx = None
     if rank == 0 and world == 1 and extras:
@@ -654,14 +720,7 @@ def single_gpu_extras(rig, line, ctx, wl, grid, mats, cam, sun):
 
     # ---- scene edits between frames (VoxelRT.updateGridDelta, VoxelRT.zig:107-172): insert on the host grid, ship the five dirty
     # ranges through the staging ring, trace.  Timed: vrt_trace's own events (rebuild of the derived structures + trace).
-    def ship_delta():
-        up = [ctx.upload_brick_statuses, ctx.upload_brick_indices, ctx.upload_brick_occupancy, ctx.upload_brick_start_indices, ctx.upload_material_indices]
-        arr = [grid.statuses, grid.brick_indices, grid.occupancy, grid.start_indices, grid.material_indices]
-        for which in range(5):
-            active, lo, hi = grid.delta(which)
-            if active:
-                up[which](lo, arr[which][lo:hi])
-                grid.delta_reset(which)
+    ship_delta = lambda: ctx.upload_grid_delta(grid)
 
     for which in range(5):
         grid.delta_reset(which)

@@ -281,6 +281,10 @@ int vrt_insert_voxels(vrt_ctx* ctx, const uint32_t* xyzm_host, size_t count, uin
 #define VRT_BUFFER_OCCUPANCY 5u        /* uint8  */
 #define VRT_BUFFER_START_INDICES 6u    /* uint32 */
 #define VRT_BUFFER_MATERIAL_INDICES 7u /* uint8  */
+#define VRT_BUFFER_DEBUG_DIST 100u     /* debug / tests: the derived distance planes (uint8, 8 octants x padded grid), after
+                                          bringing them up to date with the uploads made so far */
+/* Debug / tests: the next trace rebuilds the distance planes from scratch instead of patching them for the bricks added since. */
+int vrt_debug_force_accel_rebuild(vrt_ctx* ctx);
 /* Copy `count` elements starting at element `offset` of a grid buffer to the host (the inverse of vrt_upload_*).  Blocks. */
 int vrt_download_buffer(vrt_ctx* ctx, uint32_t which, size_t offset, void* host, size_t count);
 
@@ -337,6 +341,11 @@ int vrt_framebuffer_device_ptr(vrt_ctx* ctx, void** out_device_ptr);
 #define VRT_EXCHANGE_ALLGATHER 0u
 #define VRT_EXCHANGE_PEER_STORE 1u
 #define VRT_EXCHANGE_PEER_FLAGS 2u
+#define VRT_EXCHANGE_HOST 3u /* no device-side exchange at all: the consumer is the host.  vrt_trace_to_host(_async) copies only this
+                                rank's own rows / 4-row strips into their place of the full-image host buffer, so N ranks given the same
+                                (shared, pinned) buffer assemble the frame over N PCIe links at once instead of funnelling it through one
+                                GPU.  Needs no communicator and no peer mappings; the device framebuffers stay partial; the ranks'
+                                host code decides when a frame is complete (all ranks' vrt_sync / a host barrier).  Not with VRT_SCHED_DEAL. */
 
 int vrt_comm_get_unique_id(uint8_t id_out[VRT_NCCL_ID_BYTES]);
 int vrt_comm_init(vrt_ctx* ctx, int rank, int world, const uint8_t id[VRT_NCCL_ID_BYTES]);

@@ -400,6 +400,37 @@ def test_tile_schedules_trace_the_same_frame(materials):
             assert np.array_equal(total.astype(np.uint8), ref_img)
 
 
+def test_host_assembled_frame_from_strips(materials):
+    """VRT_EXCHANGE_HOST: every part copies exactly its own 4-row strips (ragged last strip included) into its place of one host
+    frame; the parts of all ranks put together are the oracle's frame.  Needs no communicator: one GPU plays every rank in turn."""
+    import torch
+
+    grid = scenes.build_grid(64)
+    W, H = 200, 90  # 22 full strips + one of 2 rows
+    cam, sun = scenes.camera(W, H, **POSE0), scenes.sun(True)
+    ref_img, _, _ = orc.OracleScene.from_grid(grid, materials).render(cam, sun)
+    for world in (1, 2, 3, 5):
+        frame = torch.full((H, W, 4), 7, dtype=torch.uint8).pin_memory()
+        for r in range(world):
+            ctx = ffi.Context(W, H, len(grid.brick_indices), part=(r, world))
+            ctx.upload_grid(grid, materials)
+            ctx.comm_set_exchange(ffi.VRT_EXCHANGE_HOST)
+            ctx.set_schedule(ffi.VRT_SCHED_LPT, 2)
+            before = frame.numpy().copy()
+            ctx.trace_to_host_async(cam, sun, frame.data_ptr())
+            ctx.sync()
+            mine = np.zeros(H, dtype=bool)
+            for t in range(r, (H + 3) // 4, world):
+                mine[t * 4:t * 4 + 4] = True
+            assert np.array_equal(frame.numpy()[~mine], before[~mine])  # nobody else's rows touched
+            assert np.array_equal(frame.numpy()[mine], ref_img[mine])
+            blocking = np.full((H, W, 4), 9, dtype=np.uint8)
+            ctx.trace_to_host(cam, sun, out=blocking)
+            assert np.array_equal(blocking[mine], ref_img[mine]) and (blocking[~mine] == 9).all()
+            ctx.close()
+        assert np.array_equal(frame.numpy(), ref_img)
+
+
 def test_blocking_and_pipelined_frames_mix(materials):
     """vrt_trace / vrt_trace_to_host right after vrt_trace_to_host_async frames: the blocking frame must wait for the copy still
     reading its slot, and vrt_denoise / vrt_read_framebuffer must see the frame traced last."""

@@ -86,6 +86,27 @@ def _worker(rank, world, port, out_dir):
                 if not np.array_equal(buf.numpy(), ref):
                     failures.append(f"{tag}: pipelined frame {i} differs on rank {rank}")
         dist.barrier()
+        # the host as the consumer (VRT_EXCHANGE_HOST): no device exchange, each rank copies exactly its own rows / strips
+        if sched != D:
+            ctx.comm_set_exchange(ffi.VRT_EXCHANGE_HOST)
+            mine = np.zeros(H, dtype=bool)
+            if partition == "slab":
+                mine[rank * (H // world):(rank + 1) * (H // world)] = True
+            else:
+                for t in range(rank, (H + 3) // 4, world):
+                    mine[t * 4:t * 4 + 4] = True
+            for i in (1, 4):
+                buf = torch.full((H, W, 4), 7, dtype=torch.uint8).pin_memory()
+                ctx.trace_to_host_async(cams[i], sun, buf.data_ptr())
+                ctx.sync()
+                got = buf.numpy()
+                if not (np.array_equal(got[mine], refs[i][mine]) and (got[~mine] == 7).all()):
+                    failures.append(f"{tag}: host-assembled frame {i} wrong on rank {rank}")
+                got2 = np.full((H, W, 4), 7, dtype=np.uint8)
+                ctx.trace_to_host(cams[i], sun, out=got2)
+                if not (np.array_equal(got2[mine], refs[i][mine]) and (got2[~mine] == 7).all()):
+                    failures.append(f"{tag}: host-assembled blocking frame {i} wrong on rank {rank}")
+        dist.barrier()
         ctx.close()
     with open(os.path.join(out_dir, f"rank{rank}.txt"), "w") as f:
         f.write("\n".join(failures))

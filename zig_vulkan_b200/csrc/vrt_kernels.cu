@@ -242,7 +242,8 @@ __global__ void __launch_bounds__(256) build_occ_dense_kernel(const __grid_const
 constexpr uint32_t kDistCap = 126u;
 
 __global__ void __launch_bounds__(128) dist_scan_kernel(const __grid_constant__ TraceParams P, const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
-                                                        size_t n_bricks, int axis) {
+                                                        size_t n_bricks, int axis, const AccelDelta* __restrict__ delta) {
+    if (delta && !(delta->force_full || delta->n_new > kAccelMaxNew)) return;  // nothing changed, or dist_patch_kernel has done it
     const size_t dim_x = P.grid.dim_x, dim_y = P.grid.dim_y, dim_z = P.grid.dim_z;
     const size_t lines = axis == 0 ? dim_z * dim_y : (axis == 1 ? dim_x * dim_y : dim_x * dim_z);
     const size_t line = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -277,9 +278,79 @@ __global__ void __launch_bounds__(128) dist_scan_kernel(const __grid_constant__ 
     }
 }
 
+// Status words that were uploaded again: copy them over the live ones and note which bits changed.  Grid.insert re-registers the
+// status word of every voxel it touches (brick/Grid.zig:188-189), so most uploaded words are identical to what is there.
+__global__ void __launch_bounds__(256) status_merge_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ staged, size_t count, size_t first_word,
+                                                           uint32_t dim_x, uint32_t dim_z, uint64_t n_cells, AccelDelta* __restrict__ delta) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const uint32_t was = dst[i], now = staged[i];
+    if (was == now) return;
+    dst[i] = now;
+    if (was & ~now) delta->force_full = 1u;
+    uint32_t added = now & ~was;
+    while (added) {
+        const uint32_t bit = (uint32_t)__ffs((int)added) - 1u;
+        added &= added - 1u;
+        const uint64_t g = (uint64_t)(first_word + i) * 32u + bit;
+        if (g >= n_cells) continue;  // padding bits of the last word
+        const uint32_t slot = atomicAdd(&delta->n_new, 1u);
+        if (slot < kAccelMaxNew) {
+            delta->cell[slot] = (uint32_t)g;
+            const uint32_t x = (uint32_t)(g % dim_x), z = (uint32_t)((g / dim_x) % dim_z), y = (uint32_t)(g / ((uint64_t)dim_x * dim_z));
+            atomicMin(&delta->lo[0], x), atomicMin(&delta->lo[1], y), atomicMin(&delta->lo[2], z);
+            atomicMax(&delta->hi[0], x), atomicMax(&delta->hi[1], y), atomicMax(&delta->hi[2], z);
+        }
+    }
+}
+
+cudaError_t launch_status_merge(uint32_t* dst, const uint32_t* staged, size_t count, size_t first_word, const vrt_grid_state& grid, AccelDelta* delta,
+                                cudaStream_t stream, LaunchInfo* info) {
+    if (count == 0) return cudaSuccess;
+    status_merge_kernel<<<(unsigned)((count + 255) / 256), 256, 0, stream>>>(dst, staged, count, first_word, grid.dim_x, grid.dim_z,
+                                                                             (uint64_t)grid.dim_x * grid.dim_y * grid.dim_z, delta);
+    if (info) info->launches++;
+    return cudaGetLastError();
+}
+
+// A few bricks were added (status bits 0 -> 1): patch the distance planes in place instead of rebuilding them.  A new brick q can
+// only LOWER values, and only for the cells p that have q in their closed octant: dist_o(p) = min(dist_o(p), |q - p|_1), and p's
+// octant is not free any more.  One thread per cell and octant; O(cells) bytes touched in the worst case, against the three
+// serial line scans of the full rebuild.  Same bytes as a rebuild from scratch (tests/test_accel_update.py).
+__global__ void __launch_bounds__(256) dist_patch_kernel(const __grid_constant__ TraceParams P, uint8_t* __restrict__ dist, const AccelDelta* __restrict__ delta) {
+    const uint32_t n = delta->n_new;
+    if (n == 0u || n > kAccelMaxNew || delta->force_full) return;
+    const uint32_t dim_x = P.grid.dim_x, dim_y = P.grid.dim_y, dim_z = P.grid.dim_z;
+    const size_t cell = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= (size_t)dim_x * dim_y * dim_z) return;
+    const int o = (int)blockIdx.y;  // bit0: x decreasing, bit1: y decreasing, bit2: z decreasing (dist_scan_kernel)
+    const int px = (int)(cell % dim_x), pz = (int)((cell / dim_x) % dim_z), py = (int)(cell / ((size_t)dim_x * dim_z));
+    // the octant of p must contain at least the extreme new cell
+    if ((o & 1) ? px < (int)delta->lo[0] : px > (int)delta->hi[0]) return;
+    if ((o & 2) ? py < (int)delta->lo[1] : py > (int)delta->hi[1]) return;
+    if ((o & 4) ? pz < (int)delta->lo[2] : pz > (int)delta->hi[2]) return;
+    uint32_t best = 0xffffu;
+    for (uint32_t j = 0; j < n; j++) {
+        const uint32_t g = delta->cell[j];
+        const int qx = (int)(g % dim_x), qz = (int)((g / dim_x) % dim_z), qy = (int)(g / (dim_x * dim_z));
+        const int dx = (o & 1) ? px - qx : qx - px, dy = (o & 2) ? py - qy : qy - py, dz = (o & 4) ? pz - qz : qz - pz;
+        if (dx >= 0 && dy >= 0 && dz >= 0) best = min(best, (uint32_t)(dx + dy + dz));
+    }
+    if (best == 0xffffu) return;
+    uint8_t* at = dist + (size_t)o * P.dist_plane + (size_t)(px + 1) + ((size_t)(pz + 1) << P.dist_log_px) + ((size_t)(py + 1) << (P.dist_log_px + P.dist_log_pz));
+    const uint32_t cur = *at;
+    const uint32_t d = min(min(cur & 0x7fu, best), kDistCap);
+    if (d != cur) *at = (uint8_t)d;  // free bit cleared
+}
+
+__global__ void accel_delta_reset_kernel(AccelDelta* delta) {
+    delta->n_new = 0u, delta->force_full = 0u;
+    for (int a = 0; a < 3; a++) delta->lo[a] = 0xffffffffu, delta->hi[a] = 0u;
+}
+
 // tmp: 6 * n_bricks bytes of scratch.  The border bytes of `dist` (255) are written once when it is allocated.
 cudaError_t launch_build_accel(const TraceParams& P, unsigned long long* occ_dense, uint8_t* dist, uint8_t* tmp, size_t n_bricks, bool occ_only,
-                               cudaStream_t stream, LaunchInfo* info) {
+                               AccelDelta* delta, cudaStream_t stream, LaunchInfo* info) {
     const unsigned blocks = (unsigned)((n_bricks + 255) / 256);
     if (occ_dense) {
         build_occ_dense_kernel<<<blocks, 256, 0, stream>>>(P, occ_dense, n_bricks);
@@ -289,10 +360,18 @@ cudaError_t launch_build_accel(const TraceParams& P, unsigned long long* occ_den
     uint8_t* tmp_x = tmp;                 // [2][n]
     uint8_t* tmp_z = tmp + 2 * n_bricks;  // [4][n]
     const size_t dx = P.grid.dim_x, dy = P.grid.dim_y, dz = P.grid.dim_z;
-    dist_scan_kernel<<<dim3((unsigned)((dz * dy + 127) / 128), 2), 128, 0, stream>>>(P, nullptr, tmp_x, n_bricks, 0);
-    dist_scan_kernel<<<dim3((unsigned)((dx * dy + 127) / 128), 4), 128, 0, stream>>>(P, tmp_x, tmp_z, n_bricks, 1);
-    dist_scan_kernel<<<dim3((unsigned)((dx * dz + 127) / 128), 8), 128, 0, stream>>>(P, tmp_z, dist, n_bricks, 2);
+    if (delta) {
+        dist_patch_kernel<<<dim3(blocks, 8), 256, 0, stream>>>(P, dist, delta);
+        if (info) info->launches++;
+    }
+    dist_scan_kernel<<<dim3((unsigned)((dz * dy + 127) / 128), 2), 128, 0, stream>>>(P, nullptr, tmp_x, n_bricks, 0, delta);
+    dist_scan_kernel<<<dim3((unsigned)((dx * dy + 127) / 128), 4), 128, 0, stream>>>(P, tmp_x, tmp_z, n_bricks, 1, delta);
+    dist_scan_kernel<<<dim3((unsigned)((dx * dz + 127) / 128), 8), 128, 0, stream>>>(P, tmp_z, dist, n_bricks, 2, delta);
     if (info) info->launches += 3;
+    if (delta) {
+        accel_delta_reset_kernel<<<1, 1, 0, stream>>>(delta);
+        if (info) info->launches++;
+    }
     return cudaGetLastError();
 }
 

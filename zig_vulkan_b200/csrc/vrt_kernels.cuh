@@ -20,9 +20,24 @@ struct LaunchInfo {
 // Enqueue the kernels that trace rows [P.row_begin, P.row_end) into P.fb.
 cudaError_t launch_trace(const TraceParams& P, TraceKernel which, bool aov, cudaStream_t stream, LaunchInfo* info);
 
-// Rebuild the derived structures (occ_dense; dist unless occ_only) from the reference-format buffers.  tmp: 6 * n_bricks bytes.
+// What the status uploads since the last rebuild changed, kept on the device so that no upload has to wait for an answer:
+// the cells whose status bit went 0 -> 1 (the only thing Grid.insert ever does to a status word, brick/Grid.zig:188), or "too many /
+// a bit was cleared / never built" = rebuild everything.
+constexpr uint32_t kAccelMaxNew = 32;
+struct AccelDelta {
+    uint32_t n_new;       // bits that went 0 -> 1 (may exceed kAccelMaxNew: then only the count is meaningful)
+    uint32_t force_full;  // a bit went 1 -> 0, or the distance planes were never built for this grid
+    uint32_t lo[3], hi[3];  // bounding box (cell coordinates) of the new cells
+    uint32_t cell[kAccelMaxNew];
+};
+// Write `count` freshly uploaded status words (staged at `staged`) over dst[0..count) and record what changed in *delta.
+cudaError_t launch_status_merge(uint32_t* dst, const uint32_t* staged, size_t count, size_t first_word, const vrt_grid_state& grid, AccelDelta* delta,
+                                cudaStream_t stream, LaunchInfo* info);
+// Rebuild the derived structures from the reference-format buffers: occ_dense always (brick_dim 4); the distance planes according
+// to *delta — untouched if no status bit changed, patched in place for a few new bricks, rebuilt by the three line scans otherwise;
+// *delta is cleared at the end.  occ_only: the distance planes are known to be current (host-side knowledge).  tmp: 6 * n_bricks bytes.
 cudaError_t launch_build_accel(const TraceParams& P, unsigned long long* occ_dense, uint8_t* dist, uint8_t* tmp, size_t n_bricks, bool occ_only,
-                               cudaStream_t stream, LaunchInfo* info);
+                               AccelDelta* delta, cudaStream_t stream, LaunchInfo* info);
 // Tiles (8x4 pixels) of the launch launch_trace_tuned would make for P with no schedule attached: the tile space an order for it permutes.
 uint32_t trace_tile_space(const TraceParams& P);
 // Tile schedule (vrt_sched.cu): order[i] = n - 1 - i and zeroed costs; stable sort of the tiles by cost, most expensive first.

@@ -125,8 +125,11 @@ struct vrt_ctx {
     size_t dist_plane = 0;          // bytes per octant
     uint32_t dist_log_px = 0, dist_log_pz = 0;
     uint32_t accel_dim[3] = {0, 0, 0};
-    bool accel_dirty = true;   // statuses / brick indices changed: occ_dense and the distance planes are stale
-    bool occ_dirty = true;     // only occupancy bytes changed: occ_dense is stale, the distance planes are not
+    bool accel_dirty = true;   // status words were uploaded: the distance planes MAY be stale (d_accel_delta knows)
+    bool occ_dirty = true;     // brick indices / occupancy bytes changed: occ_dense is stale, the distance planes are not
+    bool accel_force = true;   // the distance planes must be rebuilt from scratch (new grid, device-side insert)
+    AccelDelta* d_accel_delta = nullptr;  // which status bits the uploads since the last build changed
+    uint32_t* d_status_stage = nullptr;   // uploaded status words land here; status_merge_kernel compares them with the live ones
 
     // persistent-kernel work queue {next ticket, warps that left}; the kernel resets it itself
     unsigned long long* d_tile_counter = nullptr;
@@ -228,6 +231,18 @@ int upload_range(vrt_ctx* ctx, T* dst, size_t capacity, size_t offset, const T* 
     return stage_upload(ctx, dst + offset, data, count * sizeof(T));
 }
 
+// Bring occ_dense / the distance planes up to date with the uploads (stream-ordered, nothing waits).
+int rebuild_accel(vrt_ctx* ctx, const TraceParams& P, LaunchInfo* info) {
+    const size_t n_cells = (size_t)ctx->grid.dim_x * ctx->grid.dim_y * ctx->grid.dim_z;
+    if (ctx->accel_force) {
+        VRT_CUDA(ctx, cudaMemsetAsync(&ctx->d_accel_delta->force_full, 1, 1, ctx->stream));  // little-endian: the word becomes >= 1
+        ctx->accel_dirty = true;
+    }
+    VRT_CUDA(ctx, launch_build_accel(P, ctx->d_occ_dense, ctx->d_dist, ctx->d_dist_tmp, n_cells, !ctx->accel_dirty, ctx->d_accel_delta, ctx->stream, info));
+    ctx->accel_dirty = ctx->occ_dirty = ctx->accel_force = false;
+    return VRT_OK;
+}
+
 size_t cost_bytes(const vrt_ctx* c) { return ((size_t)c->tiles_global * sizeof(uint16_t) + 255u) & ~(size_t)255u; }
 
 void fill_params(const vrt_ctx* c, const vrt_camera* cam, const vrt_sun* sun, TraceParams& P) {
@@ -314,7 +329,7 @@ int ensure_accel(vrt_ctx* ctx) {
     VRT_CUDA(ctx, cudaMalloc(&ctx->d_dist_tmp, 6 * (size_t)dx * dy * dz));
     VRT_CUDA(ctx, cudaMemsetAsync(ctx->d_dist, 255, 8 * ctx->dist_plane, ctx->stream));  // the border; interiors are rewritten by every build
     ctx->accel_dim[0] = dx, ctx->accel_dim[1] = dy, ctx->accel_dim[2] = dz;
-    ctx->accel_dirty = true;
+    ctx->accel_dirty = ctx->accel_force = true;
     return VRT_OK;
 }
 
@@ -394,6 +409,9 @@ int vrt_init(vrt_ctx** out_ctx, const vrt_config* cfg) {
     INIT_CUDA(cudaEventCreate(&ctx->ev_end));
     INIT_CUDA(cudaMalloc(&ctx->d_materials, ctx->n_materials * sizeof(vrt_material)));
     INIT_CUDA(cudaMalloc(&ctx->d_statuses, ctx->n_statuses * 4));
+    INIT_CUDA(cudaMalloc(&ctx->d_status_stage, ctx->n_statuses * 4));
+    INIT_CUDA(cudaMalloc(&ctx->d_accel_delta, sizeof(AccelDelta)));
+    INIT_CUDA(cudaMemsetAsync(ctx->d_accel_delta, 0, sizeof(AccelDelta), ctx->stream));
     INIT_CUDA(cudaMalloc(&ctx->d_brick_indices, ctx->n_brick_indices * 4));
     INIT_CUDA(cudaMalloc(&ctx->d_occupancy, ctx->n_occupancy));
     INIT_CUDA(cudaMalloc(&ctx->d_start_indices, ctx->n_start_indices * 4));
@@ -449,7 +467,7 @@ void vrt_deinit(vrt_ctx* ctx) {
     cudaFree(ctx->d_materials), cudaFree(ctx->d_statuses), cudaFree(ctx->d_brick_indices), cudaFree(ctx->d_occupancy);
     cudaFree(ctx->d_start_indices), cudaFree(ctx->d_material_indices), cudaFree(ctx->d_fb_own), cudaFree(ctx->d_aov);
     cudaFree(ctx->d_counters), cudaFree(ctx->d_occ_dense), cudaFree(ctx->d_dist), cudaFree(ctx->d_dist_tmp);
-    cudaFree(ctx->d_order), cudaFree(ctx->d_sched_scratch);
+    cudaFree(ctx->d_order), cudaFree(ctx->d_sched_scratch), cudaFree(ctx->d_status_stage), cudaFree(ctx->d_accel_delta);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     for (int i = 0; i < 4; i++)
         if (ctx->ev_stage[i]) cudaEventDestroy(ctx->ev_stage[i]);
@@ -481,6 +499,7 @@ int vrt_upload_grid_state(vrt_ctx* ctx, const vrt_grid_state* state) {
     if (state->dim_x > 4096 || state->dim_y > 4096 || state->dim_z > 4096)
         return fail(ctx, VRT_E_INVALID, "vrt_upload_grid_state: grid dimension above 4096 bricks");
     VRT_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    if (ctx->have_grid && (state->dim_x != ctx->grid.dim_x || state->dim_y != ctx->grid.dim_y || state->dim_z != ctx->grid.dim_z)) ctx->accel_force = true;
     ctx->grid = *state;
     ctx->have_grid = true;
     return ensure_accel(ctx);
@@ -492,13 +511,25 @@ int vrt_upload_materials(vrt_ctx* ctx, size_t offset, const vrt_material* data, 
     return rc;
 }
 int vrt_upload_brick_statuses(vrt_ctx* ctx, size_t offset, const uint32_t* data, size_t count) {
-    const int rc = upload_range(ctx, ctx ? ctx->d_statuses : nullptr, ctx ? ctx->n_statuses : 0, offset, data, count, "vrt_upload_brick_statuses");
-    if (rc == VRT_OK && count) ctx->accel_dirty = true;
-    return rc;
+    if (!ctx) return VRT_E_INVALID;
+    if (!ctx->have_grid) {  // no grid dimensions yet to place the changed bits in: plain copy, full rebuild later
+        const int rc = upload_range(ctx, ctx->d_statuses, ctx->n_statuses, offset, data, count, "vrt_upload_brick_statuses");
+        if (rc == VRT_OK && count) ctx->accel_dirty = ctx->accel_force = true;
+        return rc;
+    }
+    // Grid.insert re-registers the status word of every voxel it touches (brick/Grid.zig:188-189), so the per-frame delta upload
+    // (VoxelRT.zig:112-123) mostly carries words that are already there.  The words go to a staging copy and a kernel merges
+    // them, recording which bits really changed: the next trace then leaves the distance planes alone, patches them for a few new
+    // bricks, or rebuilds them — decided on the device, the upload never waits for the answer.
+    const int rc = upload_range(ctx, ctx->d_status_stage, ctx->n_statuses, offset, data, count, "vrt_upload_brick_statuses");
+    if (rc != VRT_OK || count == 0) return rc;
+    VRT_CUDA(ctx, launch_status_merge(ctx->d_statuses + offset, ctx->d_status_stage + offset, count, offset, ctx->grid, ctx->d_accel_delta, ctx->stream, nullptr));
+    ctx->accel_dirty = true;
+    return VRT_OK;
 }
 int vrt_upload_brick_indices(vrt_ctx* ctx, size_t offset, const uint32_t* data, size_t count) {
     const int rc = upload_range(ctx, ctx ? ctx->d_brick_indices : nullptr, ctx ? ctx->n_brick_indices : 0, offset, data, count, "vrt_upload_brick_indices");
-    if (rc == VRT_OK && count) ctx->accel_dirty = true;
+    if (rc == VRT_OK && count) ctx->occ_dirty = true;  // occ_dense is indexed through brick_indices; the distance planes only read the status bits
     return rc;
 }
 int vrt_upload_brick_occupancy(vrt_ctx* ctx, size_t offset, const uint8_t* data, size_t count) {
@@ -550,7 +581,7 @@ int trace_frame(vrt_ctx* ctx, const vrt_camera* camera, const vrt_sun* sun, bool
                     ctx->cfg.width, ctx->cfg.height);
     if (camera->samples_per_pixel < 1) return fail(ctx, VRT_E_INVALID, "vrt_trace: samples_per_pixel < 1");
     const bool gather = ctx->world > 1 && ctx->exchange_mode == VRT_EXCHANGE_ALLGATHER;
-    if (ctx->world > 1 && !ctx->comm && ctx->exchange_mode != VRT_EXCHANGE_PEER_FLAGS)  // the flag barrier needs no communicator
+    if (ctx->world > 1 && !ctx->comm && ctx->exchange_mode != VRT_EXCHANGE_PEER_FLAGS && ctx->exchange_mode != VRT_EXCHANGE_HOST)  // neither needs a communicator
         return fail(ctx, VRT_E_STATE, "vrt_trace: world > 1 but vrt_comm_init has not been called");
     if (ctx->sched_mode == VRT_SCHED_DEAL && ctx->world > 1 && !peer_mode(ctx))
         return fail(ctx, VRT_E_STATE, "vrt_trace: VRT_SCHED_DEAL scatters a rank's tiles over the image and needs a peer-store exchange mode");
@@ -584,9 +615,8 @@ int trace_frame(vrt_ctx* ctx, const vrt_camera* camera, const vrt_sun* sun, bool
         // upload -> build -> trace, where the reference has no barrier at all between its staging copy and the next dispatch
         // (edits land one frame late, Pipeline.zig:540).  Occupancy-only edits (voxels inside loaded bricks — most of
         // Grid.insert's traffic) leave the brick-level distance planes alone.
-        const size_t n_cells = (size_t)ctx->grid.dim_x * ctx->grid.dim_y * ctx->grid.dim_z;
-        VRT_CUDA(ctx, launch_build_accel(P, ctx->d_occ_dense, ctx->d_dist, ctx->d_dist_tmp, n_cells, !ctx->accel_dirty, ctx->stream, &info));
-        ctx->accel_dirty = ctx->occ_dirty = false;
+        const int rcb = rebuild_accel(ctx, P, &info);
+        if (rcb != VRT_OK) return rcb;
     }
     if (aov) VRT_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
     if (gather && ctx->interleave) {  // trace straight into this rank's slice of the rank-major gather buffer
@@ -627,7 +657,7 @@ int trace_frame(vrt_ctx* ctx, const vrt_camera* camera, const vrt_sun* sun, bool
             const ncclResult_t r = g_nccl.AllGather(send, ctx->d_fb, slab_bytes, ncclUint8, ctx->comm, ctx->stream);
             if (r != ncclSuccess) return fail(ctx, VRT_E_NCCL, "ncclAllGather failed: %s", g_nccl.GetErrorString(r));
         }
-    } else if (ctx->world > 1) {
+    } else if (ctx->world > 1 && ctx->exchange_mode != VRT_EXCHANGE_HOST) {
         // peer-store: the pixels are already in every rank's framebuffer; the frame barrier makes "every rank has finished
         // frame k" visible in stream order.  The NEXT frame's remote stores land in the other ring slot of every peer, so the
         // barrier also waits until this rank has copied that slot's previous frame to its host (pipelined frames).
@@ -656,11 +686,35 @@ int trace_frame(vrt_ctx* ctx, const vrt_camera* camera, const vrt_sun* sun, bool
     return VRT_OK;
 }
 
-// device -> host copy of what this context holds of the frame in d_fb: its own rows, or the whole image after an exchange
-void host_span(const vrt_ctx* ctx, size_t* from, size_t* n) {
-    const bool whole = ctx->world > 1 || ctx->interleave || ctx->sched_mode == VRT_SCHED_DEAL;
-    *from = whole ? 0 : (size_t)ctx->row_begin * ctx->cfg.width * 4;
-    *n = whole ? ctx->fb_bytes : (size_t)(ctx->row_end - ctx->row_begin) * ctx->cfg.width * 4;
+// device -> host copy of what this context holds of the frame in d_fb, into the same place of a full-image host buffer: the whole
+// image after a device-side exchange; only this rank's own rows / strips when there is none (one row slab, or — VRT_EXCHANGE_HOST with
+// an interleaved partition — one strided copy of the 4-row strips k * world + rank).
+int copy_frame_to_host(vrt_ctx* ctx, uint8_t* host, cudaStream_t stream) {
+    const uint8_t* fb = reinterpret_cast<const uint8_t*>(ctx->d_fb);
+    const size_t row_bytes = (size_t)ctx->cfg.width * 4;
+    const bool host_mode = ctx->exchange_mode == VRT_EXCHANGE_HOST;
+    if (ctx->interleave && host_mode && ctx->sched_mode != VRT_SCHED_DEAL) {
+        const size_t chunk = kStripRows * row_bytes, pitch = (size_t)ctx->part_world * chunk, first = (size_t)ctx->part_rank * chunk;
+        const uint32_t strips = (ctx->cfg.height + kStripRows - 1) / kStripRows;
+        const uint32_t mine = strips > ctx->part_rank ? (strips - ctx->part_rank + ctx->part_world - 1) / ctx->part_world : 0u;
+        if (mine == 0) return VRT_OK;
+        const uint32_t last_strip = (mine - 1) * ctx->part_world + ctx->part_rank;
+        const uint32_t last_rows = (last_strip + 1) * kStripRows <= ctx->cfg.height ? kStripRows : ctx->cfg.height - last_strip * kStripRows;
+        const uint32_t full = last_rows == kStripRows ? mine : mine - 1;
+        if (full) VRT_CUDA(ctx, cudaMemcpy2DAsync(host + first, pitch, fb + first, pitch, chunk, full, cudaMemcpyDeviceToHost, stream));
+        if (full != mine) {
+            const size_t at = (size_t)last_strip * chunk;
+            VRT_CUDA(ctx, cudaMemcpyAsync(host + at, fb + at, last_rows * row_bytes, cudaMemcpyDeviceToHost, stream));
+        }
+        return VRT_OK;
+    }
+    const bool whole = !host_mode && (ctx->world > 1 || ctx->interleave || ctx->sched_mode == VRT_SCHED_DEAL);
+    const size_t from = whole ? 0 : (size_t)ctx->row_begin * row_bytes;
+    const size_t n = whole ? ctx->fb_bytes : (size_t)(ctx->row_end - ctx->row_begin) * row_bytes;
+    if (ctx->interleave && !whole && ctx->sched_mode == VRT_SCHED_DEAL)
+        return fail(ctx, VRT_E_STATE, "VRT_EXCHANGE_HOST cannot be combined with VRT_SCHED_DEAL (a rank's tiles are scattered over the image)");
+    VRT_CUDA(ctx, cudaMemcpyAsync(host + from, fb + from, n, cudaMemcpyDeviceToHost, stream));
+    return VRT_OK;
 }
 
 }  // namespace
@@ -689,10 +743,10 @@ int vrt_trace_to_host_async(vrt_ctx* ctx, const vrt_camera* camera, const vrt_su
     if (rc != VRT_OK) return rc;
     VRT_CUDA(ctx, cudaEventRecord(ctx->ev_traced[slot], ctx->stream));
     VRT_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_traced[slot], 0));
-    size_t from, n;
-    host_span(ctx, &from, &n);
-    if (rgba8_host)  // NULL: take part in the frame ring (multi-GPU ranks that do not need the pixels on their host) without a copy
-        VRT_CUDA(ctx, cudaMemcpyAsync(rgba8_host + from, reinterpret_cast<const uint8_t*>(ctx->d_fb) + from, n, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    if (rgba8_host) {  // NULL: take part in the frame ring (multi-GPU ranks that do not need the pixels on their host) without a copy
+        const int rcc = copy_frame_to_host(ctx, rgba8_host, ctx->copy_stream);
+        if (rcc != VRT_OK) return rcc;
+    }
     VRT_CUDA(ctx, cudaEventRecord(ctx->ev_copied[slot], ctx->copy_stream));
     ctx->slot_used[slot] = true;
     return VRT_OK;
@@ -712,9 +766,8 @@ int vrt_trace_to_host(vrt_ctx* ctx, const vrt_camera* camera, const vrt_sun* sun
     if (!rgba8_host || bytes != ctx->fb_bytes) return fail(ctx, VRT_E_INVALID, "vrt_trace_to_host: need a %zu-byte buffer", ctx->fb_bytes);
     const int rc = trace_frame(ctx, camera, sun, false);
     if (rc != VRT_OK) return rc;
-    size_t from, n;
-    host_span(ctx, &from, &n);
-    VRT_CUDA(ctx, cudaMemcpyAsync(rgba8_host + from, reinterpret_cast<const uint8_t*>(ctx->d_fb) + from, n, cudaMemcpyDeviceToHost, ctx->stream));
+    const int rcc = copy_frame_to_host(ctx, rgba8_host, ctx->stream);
+    if (rcc != VRT_OK) return rcc;
     VRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return VRT_OK;
 }
@@ -782,7 +835,7 @@ int vrt_insert_voxels(vrt_ctx* ctx, const uint32_t* xyzm_host, size_t count, uin
         if (!cuda_ok(launch_insert_commit(B, d_xyzm, count, *active_bricks, last_writer, ctx->stream, &info))) break;
         if (!cuda_ok(cudaStreamSynchronize(ctx->stream))) break;
         *active_bricks += new_bricks;
-        ctx->accel_dirty = true;
+        ctx->accel_dirty = ctx->accel_force = true;  // the status words changed on the device, behind the merge kernel's back
     } while (false);
     cudaFree(last_writer);
     cudaFree(scratch);
@@ -799,6 +852,22 @@ int vrt_download_buffer(vrt_ctx* ctx, uint32_t which, size_t offset, void* host,
         case VRT_BUFFER_OCCUPANCY: src = ctx->d_occupancy, capacity = ctx->n_occupancy, elem = 1; break;
         case VRT_BUFFER_START_INDICES: src = reinterpret_cast<const uint8_t*>(ctx->d_start_indices), capacity = ctx->n_start_indices; break;
         case VRT_BUFFER_MATERIAL_INDICES: src = ctx->d_material_indices, capacity = ctx->n_material_indices, elem = 1; break;
+        case VRT_BUFFER_DEBUG_DIST: {  // the derived distance planes, brought up to date first (what the next trace would use)
+            if (!ctx->have_grid || !ctx->d_dist) return fail(ctx, VRT_E_STATE, "vrt_download_buffer: no grid state yet");
+            VRT_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+            if (ctx->accel_dirty || ctx->occ_dirty || ctx->accel_force) {
+                vrt_camera cam;
+                vrt_sun sun;
+                std::memset(&cam, 0, sizeof(cam));
+                std::memset(&sun, 0, sizeof(sun));
+                TraceParams P;
+                fill_params(ctx, &cam, &sun, P);
+                const int rcb = rebuild_accel(ctx, P, nullptr);
+                if (rcb != VRT_OK) return rcb;
+            }
+            src = ctx->d_dist, capacity = 8 * ctx->dist_plane, elem = 1;
+            break;
+        }
         default: return fail(ctx, VRT_E_INVALID, "vrt_download_buffer: unknown buffer %u", which);
     }
     if (count == 0) return VRT_OK;
@@ -807,6 +876,12 @@ int vrt_download_buffer(vrt_ctx* ctx, uint32_t which, size_t offset, void* host,
     VRT_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
     VRT_CUDA(ctx, cudaMemcpyAsync(host, src + offset * elem, count * elem, cudaMemcpyDeviceToHost, ctx->stream));
     VRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VRT_OK;
+}
+
+int vrt_debug_force_accel_rebuild(vrt_ctx* ctx) {
+    if (!ctx) return VRT_E_INVALID;
+    ctx->accel_dirty = ctx->accel_force = true;
     return VRT_OK;
 }
 
@@ -889,9 +964,8 @@ int vrt_trace_rays(vrt_ctx* ctx, const vrt_ray* rays_device, vrt_ray_hit* hits_d
     fill_params(ctx, &cam, &sun, P);
     LaunchInfo info = {0u};
     if (ctx->accel_dirty || ctx->occ_dirty) {
-        const size_t n_cells = (size_t)ctx->grid.dim_x * ctx->grid.dim_y * ctx->grid.dim_z;
-        VRT_CUDA(ctx, launch_build_accel(P, ctx->d_occ_dense, ctx->d_dist, ctx->d_dist_tmp, n_cells, !ctx->accel_dirty, ctx->stream, &info));
-        ctx->accel_dirty = ctx->occ_dirty = false;
+        const int rcb = rebuild_accel(ctx, P, &info);
+        if (rcb != VRT_OK) return rcb;
     }
     VRT_CUDA(ctx, launch_trace_rays(P, rays_device, hits_device, count, ctx->stream, &info));
     ctx->last_launches = info.launches;
@@ -1120,9 +1194,10 @@ int vrt_comm_open_peers(vrt_ctx* ctx, int rank, int world, const uint8_t* handle
 
 int vrt_comm_set_exchange(vrt_ctx* ctx, uint32_t mode) {
     if (!ctx) return VRT_E_INVALID;
-    if (mode != VRT_EXCHANGE_ALLGATHER && mode != VRT_EXCHANGE_PEER_STORE && mode != VRT_EXCHANGE_PEER_FLAGS)
+    if (mode != VRT_EXCHANGE_ALLGATHER && mode != VRT_EXCHANGE_PEER_STORE && mode != VRT_EXCHANGE_PEER_FLAGS && mode != VRT_EXCHANGE_HOST)
         return fail(ctx, VRT_E_INVALID, "vrt_comm_set_exchange: unknown mode %u", mode);
-    if (mode != VRT_EXCHANGE_ALLGATHER && !ctx->peers_open) return fail(ctx, VRT_E_STATE, "vrt_comm_set_exchange: call vrt_comm_open_peers first");
+    if ((mode == VRT_EXCHANGE_PEER_STORE || mode == VRT_EXCHANGE_PEER_FLAGS) && !ctx->peers_open)
+        return fail(ctx, VRT_E_STATE, "vrt_comm_set_exchange: call vrt_comm_open_peers first");
     if (mode == VRT_EXCHANGE_PEER_FLAGS && !ctx->h_barrier_error) {
         VRT_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
         VRT_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_barrier_error), sizeof(int), cudaHostAllocMapped));

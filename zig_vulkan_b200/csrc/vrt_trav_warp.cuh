@@ -143,6 +143,12 @@ VRT_DI int brick_hit_warp4(const TraceParams& P, const Ray& r, bool ignore_test,
     return found;
 }
 
+#ifndef VRT_PREFETCH
+#define VRT_PREFETCH 0
+#endif
+#ifndef VRT_PREFETCH_K
+#define VRT_PREFETCH_K 3
+#endif
 #ifndef VRT_TMA_MASKS
 #define VRT_TMA_MASKS 0
 #endif
@@ -363,6 +369,12 @@ VRT_DI bool grid_hit_warp(const TraceParams& P, const Ray& r, bool active, bool 
     float fdx = marching ? dx : 0.0f, fdy = marching ? dy : 0.0f, fdz = marching ? dz : 0.0f;
     int fsx = stx, fsy = sty, fsz = stz;  // (stx.. are 0 when not marching)
 
+#if VRT_PREFETCH
+    bool near_rounds = false;  // warp-uniform: the previous round was at most VRT_PREFETCH_K steps long
+#if VRT_PREFETCH == 2
+    uint32_t pf_sink0, pf_sink1;
+#endif
+#endif
     while (__any_sync(kFullMask, mode != kDone)) {
         // ---- phase A (:313-373 without the per-cell tests): rounds of { every marching ray looks its cell up; all of
         // them take k = min over the warp of the distances found steps }.  k is warp-uniform, so the step loop has no
@@ -372,6 +384,20 @@ VRT_DI bool grid_hit_warp(const TraceParams& P, const Ray& r, bool active, bool 
             uint32_t d = kIdle;
             if (mode == kMarching) {
                 d = __ldg(dist + idx);
+#if VRT_PREFETCH
+                // Near a surface the rounds are one or two steps long and the next lookup lands on a neighbouring cell: the x
+                // neighbours share this cell's 128-byte line, the z / y neighbours are one row / one plane away.  Ask for those
+                // two lines now, so that the next round's lookup finds them in L1 instead of paying the L2 round trip.
+                if (near_rounds) {
+#if VRT_PREFETCH == 1
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(dist + idx + fsz));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(dist + idx + fsy));
+#else
+                    asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(pf_sink0) : "l"(dist + idx + fsz));
+                    asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(pf_sink1) : "l"(dist + idx + fsy));
+#endif
+                }
+#endif
                 // bit 7: left the grid (border byte 255, :313-315), or — exact shortcut — no loaded brick exists anywhere in
                 // the octant this DDA can reach, so the shader's loop would only step through empty cells until it
                 // leaves the grid.  (COUNT keeps marching through free octants so that its step counters equal the shader's.)
@@ -392,6 +418,9 @@ VRT_DI bool grid_hit_warp(const TraceParams& P, const Ray& r, bool active, bool 
             }
             const uint32_t k = __reduce_min_sync(kFullMask, d);
             if (k == kIdle) break;
+#if VRT_PREFETCH
+            near_rounds = k <= VRT_PREFETCH_K;
+#endif
             const bool on = d != kIdle;
             for (uint32_t i = 1; i < k; i++) {  // k-1 steps onto cells known to be empty and inside
                 march_step(sx, sy, sz, fdx, fdy, fdz, fsx, fsy, fsz, idx, one);

@@ -19,6 +19,7 @@ VRT_FLAG_INTERLEAVE = 4
 VRT_EXCHANGE_ALLGATHER = 0
 VRT_EXCHANGE_PEER_STORE = 1
 VRT_EXCHANGE_PEER_FLAGS = 2
+VRT_EXCHANGE_HOST = 3
 VRT_SCHED_STATIC, VRT_SCHED_LPT, VRT_SCHED_DEAL = 0, 1, 2
 VRT_NCCL_ID_BYTES = 128
 VRT_IPC_HANDLE_BYTES = 64
@@ -167,6 +168,7 @@ VRT_SYMBOLS = {
     "vrt_last_trace_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "vrt_last_trace_kernel_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "vrt_last_trace_launches": (C.c_int, [_P, C.POINTER(C.c_uint32)]),
+    "vrt_debug_force_accel_rebuild": (C.c_int, [_P]),
     "vrt_set_schedule": (C.c_int, [_P, C.c_uint32, C.c_uint32]),
     "vrt_sched_get_costs": (C.c_int, [_P, _P, _SZ]),
     "vrt_sched_set_costs": (C.c_int, [_P, _P, _SZ]),
@@ -616,6 +618,20 @@ class Context:
 
     def upload_grid_state(self, state: GridState):
         self._check(self._l.vrt_upload_grid_state(self.handle, C.byref(state)))
+        self._grid_dims = (state.dim_x, state.dim_y, state.dim_z)
+
+    def upload_grid_delta(self, grid: "Grid") -> int:
+        """VoxelRT.updateGridDelta (VoxelRT.zig:107-172): ship the five dirty ranges of the host grid.  Returns the bytes sent."""
+        up = [self.upload_brick_statuses, self.upload_brick_indices, self.upload_brick_occupancy, self.upload_brick_start_indices, self.upload_material_indices]
+        arr = [grid.statuses, grid.brick_indices, grid.occupancy, grid.start_indices, grid.material_indices]
+        sent = 0
+        for which in range(5):
+            active, lo, hi = grid.delta(which)
+            if active:
+                up[which](lo, arr[which][lo:hi])
+                sent += int(arr[which][lo:hi].nbytes)
+                grid.delta_reset(which)
+        return sent
 
     def _upload(self, fn, offset, data: np.ndarray, dtype):
         a = np.ascontiguousarray(data, dtype=dtype)
@@ -737,6 +753,25 @@ class Context:
         ms = C.c_float()
         self._check(self._l.vrt_last_trace_ms(self.handle, C.byref(ms)))
         return ms.value
+
+    def debug_dist_planes(self) -> np.ndarray:
+        """The derived distance planes (8 octants x padded grid bytes), up to date with the uploads so far.  Tests only."""
+        n = C.c_size_t(0)
+        # capacity is 8 * plane bytes: ask for everything by probing with the grid's padded size
+        g = self._grid_dims
+        lx = 1
+        while (1 << lx) < g[0] + 2:
+            lx += 1
+        lz = 1
+        while (1 << lz) < g[2] + 2:
+            lz += 1
+        count = 8 * ((g[1] + 2) << (lx + lz))
+        out = np.empty(count, dtype=np.uint8)
+        self._check(self._l.vrt_download_buffer(self.handle, 100, 0, _ptr(out), count))
+        return out.reshape(8, g[1] + 2, 1 << lz, 1 << lx)
+
+    def debug_force_accel_rebuild(self):
+        self._check(self._l.vrt_debug_force_accel_rebuild(self.handle))
 
     def last_trace_kernel_ms(self) -> float:
         """The part of last_trace_ms() before the exchange: (rebuild +) trace kernel."""
