@@ -44,7 +44,8 @@ ab: $(PKG)/libvrt.so
 	cp $(PKG)/libvrt.so build/ab/libvrt_base.so
 	for v in $(AB); do name=$${v%%:*}; defs=$$(echo $${v#*:} | tr ',' ' '); \
 	  $(NVCC) $(NVCCFLAGS) $$defs -c -o build/ab/kernels_$$name.o $(CSRC)/vrt_kernels.cu 2> build/ab/kernels_$$name.ptxas.log || exit 1; \
-	  $(NVCC) -gencode arch=compute_100a,code=sm_100a -shared -o build/ab/libvrt_$$name.so build/ab/kernels_$$name.o $(CSRC)/vrt_shim.o $(CSRC)/vrt_denoise.o $(CSRC)/vrt_build.o $(CSRC)/vrt_sched.o -ldl || exit 1; \
+	  $(NVCC) $(NVCCFLAGS) $$defs -c -o build/ab/shim_$$name.o $(CSRC)/vrt_shim.cu 2> /dev/null || exit 1; \
+	  $(NVCC) -gencode arch=compute_100a,code=sm_100a -shared -o build/ab/libvrt_$$name.so build/ab/kernels_$$name.o build/ab/shim_$$name.o $(CSRC)/vrt_denoise.o $(CSRC)/vrt_build.o $(CSRC)/vrt_sched.o -ldl || exit 1; \
 	  grep -A2 "trace_warp_kernelILi4ELb0ELb1E" build/ab/kernels_$$name.ptxas.log | grep -E "registers|spill" | tr '\n' ' '; echo " <- $$name"; done
 
 clean:

@@ -33,11 +33,20 @@ __global__ void __launch_bounds__(256) trace_ref_kernel(const __grid_constant__ 
 // (vrt_trav_warp.cuh).  The tile is written as eight 128-bit stores (4 texels each, gathered by shfl); in the
 // fused multi-GPU exchange the same stores also go to every peer's framebuffer over NVLink.
 // ----------------------------------------------------------------------------------------------------
+// 8 CTAs of 128 threads per SM = 32 warps at 64 registers (40 bytes of spills outside the march): measured 4.5 % faster than
+// 24 warps at 80 registers and no spills, 1 % faster than 36 warps at 56 (profiles/r02_ab_occupancy_prefetch_C3.txt).  The warps of a
+// CTA share nothing, so the CTA size only sets the granularity of the register file split.
 #ifndef VRT_TUNED_THREADS
-#define VRT_TUNED_THREADS 256
+#define VRT_TUNED_THREADS 128
 #endif
 #ifndef VRT_TUNED_BLOCKS
-#define VRT_TUNED_BLOCKS 3
+#define VRT_TUNED_BLOCKS 8
+#endif
+#ifndef VRT_GENERAL_BLOCKS
+#define VRT_GENERAL_BLOCKS 6  // the general shading path (scatter functions, RNG, sample loop) keeps 80 registers: at 64 it spills 470 bytes
+#endif
+#ifndef VRT_TICKET_PREFETCH
+#define VRT_TICKET_PREFETCH 0
 #endif
 constexpr int kTunedThreads = VRT_TUNED_THREADS;
 constexpr uint32_t kTileW = 8, kTileH = 4;
@@ -57,7 +66,7 @@ VRT_DI void leave_queue(const TraceParams& P, uint32_t lane) {
 }
 
 template <int BD, bool AOV, bool SIMPLE>
-__global__ void __launch_bounds__(kTunedThreads, VRT_TUNED_BLOCKS) trace_warp_kernel(const __grid_constant__ TraceParams P, const uint32_t tiles_x, const uint32_t tiles_total) {
+__global__ void __launch_bounds__(kTunedThreads, SIMPLE ? VRT_TUNED_BLOCKS : VRT_GENERAL_BLOCKS) trace_warp_kernel(const __grid_constant__ TraceParams P, const uint32_t tiles_x, const uint32_t tiles_total) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t lx = lane & (kTileW - 1u), ly = lane >> 3;
     const uint32_t width = P.cam.image_width;
@@ -66,11 +75,23 @@ __global__ void __launch_bounds__(kTunedThreads, VRT_TUNED_BLOCKS) trace_warp_ke
     if (BD != 4 && P.brick_dim == 16) brick_stage_init();
 #endif
 
+#if VRT_TICKET_PREFETCH
+    // the ticket of the NEXT tile is drawn while this one is traced: the atomic's round trip to L2 (4 % of the stall samples at the
+    // head of every tile) overlaps the tile instead of preceding it
+    unsigned long long t_next = 0ull;
+    if (lane == 0) t_next = atomicAdd(P.tile_counter, 1ull);
+#endif
     for (;;) {
         unsigned long long t = 0ull;
+#if VRT_TICKET_PREFETCH
+        t = __shfl_sync(kFullMask, t_next, 0);
+        if (t >= (unsigned long long)tiles_total) break;
+        if (lane == 0) t_next = atomicAdd(P.tile_counter, 1ull);
+#else
         if (lane == 0) t = atomicAdd(P.tile_counter, 1ull);
         t = __shfl_sync(kFullMask, t, 0);
         if (t >= (unsigned long long)tiles_total) break;
+#endif
         // Scheduled: the most expensive tiles of the previous frames first (vrt_sched.cu).  Otherwise bottom-up: in the reference's
         // convention image row 0 is up (sky); starting with the ground rows leaves the cheap sky tiles to fill the tail of the launch.
         const uint32_t tile = P.tile_order ? __ldg(P.tile_order + P.order_offset + (uint32_t)t * P.order_stride) : tiles_total - 1u - (uint32_t)t;
@@ -271,7 +292,8 @@ __global__ void __launch_bounds__(128) dist_scan_kernel(const __grid_constant__ 
         const uint32_t byte = d | fr;
         if (axis == 2) {
             const uint32_t x = (uint32_t)(g % dim_x), z = (uint32_t)((g / dim_x) % dim_z);
-            out[(size_t)v * P.dist_plane + (size_t)(x + 1) + ((size_t)(z + 1) << P.dist_log_px) + ((size_t)(c + 1) << (P.dist_log_px + P.dist_log_pz))] = (uint8_t)byte;
+            const uint32_t cell = (x + 1u) + ((z + 1u) << P.dist_log_px) + ((uint32_t)(c + 1) << (P.dist_log_px + P.dist_log_pz));
+            out[(size_t)v * P.dist_plane + dist_addr(cell, P.dist_xhi_mask, P.dist_zlo_mask, P.dist_wx)] = (uint8_t)byte;
         } else {
             out[(size_t)v * n_bricks + g] = (uint8_t)byte;
         }
@@ -337,7 +359,8 @@ __global__ void __launch_bounds__(256) dist_patch_kernel(const __grid_constant__
         if (dx >= 0 && dy >= 0 && dz >= 0) best = min(best, (uint32_t)(dx + dy + dz));
     }
     if (best == 0xffffu) return;
-    uint8_t* at = dist + (size_t)o * P.dist_plane + (size_t)(px + 1) + ((size_t)(pz + 1) << P.dist_log_px) + ((size_t)(py + 1) << (P.dist_log_px + P.dist_log_pz));
+    const uint32_t padded = (uint32_t)(px + 1) + ((uint32_t)(pz + 1) << P.dist_log_px) + ((uint32_t)(py + 1) << (P.dist_log_px + P.dist_log_pz));
+    uint8_t* at = dist + (size_t)o * P.dist_plane + dist_addr(padded, P.dist_xhi_mask, P.dist_zlo_mask, P.dist_wx);
     const uint32_t cur = *at;
     const uint32_t d = min(min(cur & 0x7fu, best), kDistCap);
     if (d != cur) *at = (uint8_t)d;  // free bit cleared

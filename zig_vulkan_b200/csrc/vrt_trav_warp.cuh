@@ -84,6 +84,29 @@ VRT_DI void march_step(float& sx, float& sy, float& sz, float dx, float dy, floa
         : "f"(dx), "f"(dy), "f"(dz), "r"(stx), "r"(sty), "r"(stz), "r"(one));
 }
 
+// The same step for the lanes with i < n only (the others keep their state): the lane predicate is the AND input of the first
+// compare, whose second output (!(sx<sy) & on) feeds the y compare; the z step is on & !x & !y.  11 instructions.
+VRT_DI void march_step_if(uint32_t i, uint32_t n, float& sx, float& sy, float& sz, float dx, float dy, float dz, int stx, int sty, int stz, int& idx, int one) {
+    asm("{\n\t"
+        ".reg .pred on, p1, q1, px, py, pz;\n\t"
+        "setp.lt.u32 on, %11, %12;\n\t"
+        "setp.lt.and.f32 p1|q1, %0, %1, on;\n\t"
+        "setp.lt.and.f32 px, %0, %2, p1;\n\t"
+        "setp.lt.and.f32 py, %1, %2, q1;\n\t"
+        "or.pred pz, px, py;\n\t"
+        "not.pred pz, pz;\n\t"
+        "and.pred pz, pz, on;\n\t"
+        "@px add.rn.f32 %0, %0, %4;\n\t"
+        "@py add.rn.f32 %1, %1, %5;\n\t"
+        "@pz add.rn.f32 %2, %2, %6;\n\t"
+        "@px mad.lo.s32 %3, %7, %10, %3;\n\t"
+        "@py mad.lo.s32 %3, %8, %10, %3;\n\t"
+        "@pz mad.lo.s32 %3, %9, %10, %3;\n\t"
+        "}"
+        : "+f"(sx), "+f"(sy), "+f"(sz), "+r"(idx)
+        : "f"(dx), "f"(dy), "f"(dz), "r"(stx), "r"(sty), "r"(stz), "r"(one), "r"(i), "r"(n));
+}
+
 // Voxel-level DDA inside one 4^3 brick (brick_raytracer.comp:378-471) with the whole state in registers: the brick's 64-bit
 // mask, and ONE integer that carries both the voxel index and the bounds test —
 //   bits 0-11: (x+4) | (z+4) << 4 | (y+4) << 8   (a coordinate is inside [0,4) iff bit 2 of its field is set: 3 = -1 and 8 = 4
@@ -148,6 +171,9 @@ VRT_DI int brick_hit_warp4(const TraceParams& P, const Ray& r, bool ignore_test,
 #endif
 #ifndef VRT_PREFETCH_K
 #define VRT_PREFETCH_K 3
+#endif
+#ifndef VRT_KSLACK
+#define VRT_KSLACK 0
 #endif
 #ifndef VRT_TMA_MASKS
 #define VRT_TMA_MASKS 0
@@ -383,7 +409,7 @@ VRT_DI bool grid_hit_warp(const TraceParams& P, const Ray& r, bool active, bool 
         for (;;) {
             uint32_t d = kIdle;
             if (mode == kMarching) {
-                d = __ldg(dist + idx);
+                d = __ldg(dist + dist_addr((uint32_t)idx, P.dist_xhi_mask, P.dist_zlo_mask, P.dist_wx));
 #if VRT_PREFETCH
                 // Near a surface the rounds are one or two steps long and the next lookup lands on a neighbouring cell: the x
                 // neighbours share this cell's 128-byte line, the z / y neighbours are one row / one plane away.  Ask for those
@@ -422,13 +448,52 @@ VRT_DI bool grid_hit_warp(const TraceParams& P, const Ray& r, bool active, bool 
             near_rounds = k <= VRT_PREFETCH_K;
 #endif
             const bool on = d != kIdle;
-            for (uint32_t i = 1; i < k; i++) {  // k-1 steps onto cells known to be empty and inside
-                march_step(sx, sy, sz, fdx, fdy, fdz, fsx, fsy, fsz, idx, one);
-                if (COUNT && on) {
-                    ti.grid_steps++;
-                    const uint32_t gi = cell_grid_index(P, idx - obase, log_px, log_pzx);
-                    if ((gi >> 5) != cnt_word) cnt_word = gi >> 5, ti.status_fetches++;
+#if VRT_KSLACK
+            // Rounds with slack.  All lanes taking the warp MINIMUM of the distances keeps the step loop uniform, but one ray grazing a
+            // surface (d = 1) then drags the other 31 through a lookup per cell.  When the distances differ, every lane instead takes its
+            // OWN distance, capped at minimum + VRT_KSLACK: d - 1 blind steps under a lane predicate (11 instructions per step instead
+            // of 10) and the landing step together.  Fewer rounds — fewer lookups on the critical path of the tile — for a bounded
+            // number of iterations in which the short-distance lanes idle.
+            if (!COUNT) {
+                const uint32_t mine = on ? d : 0u;
+                const uint32_t kcap = min(__reduce_max_sync(kFullMask, mine), k + (uint32_t)VRT_KSLACK);
+                if (kcap > k) {
+                    const uint32_t n = min(mine, kcap);  // steps of this lane in this round; 0: parked / finished
+                    for (uint32_t i = 1; i < kcap; i++) march_step_if(i, n, sx, sy, sz, fdx, fdy, fdz, fsx, fsy, fsz, idx, one);
+                    if (on) t_side = fminf(fminf(sx, sy), sz);
+                    const int before = idx;
+                    march_step(sx, sy, sz, fdx, fdy, fdz, fsx, fsy, fsz, idx, one);
+                    if (on) last_stride = idx - before;
+                    continue;
                 }
+            }
+#endif
+            if (COUNT) {
+                for (uint32_t i = 1; i < k; i++) {  // k-1 steps onto cells known to be empty and inside
+                    march_step(sx, sy, sz, fdx, fdy, fdz, fsx, fsy, fsz, idx, one);
+                    if (on) {
+                        ti.grid_steps++;
+                        const uint32_t gi = cell_grid_index(P, idx - obase, log_px, log_pzx);
+                        if ((gi >> 5) != cnt_word) cnt_word = gi >> 5, ti.status_fetches++;
+                    }
+                }
+            } else {
+                // k-1 steps onto cells known to be empty and inside.  Most rounds are short (near a surface k is 1 - 3): blocks of four,
+                // then the two low bits of the count by themselves — a handful of instructions of loop control per round, not a
+                // general unrolled loop's prologue + remainder loop.
+                uint32_t n = k - 1u;
+#pragma unroll 1
+                for (; n >= 4u; n -= 4u) {
+                    march_step(sx, sy, sz, fdx, fdy, fdz, fsx, fsy, fsz, idx, one);
+                    march_step(sx, sy, sz, fdx, fdy, fdz, fsx, fsy, fsz, idx, one);
+                    march_step(sx, sy, sz, fdx, fdy, fdz, fsx, fsy, fsz, idx, one);
+                    march_step(sx, sy, sz, fdx, fdy, fdz, fsx, fsy, fsz, idx, one);
+                }
+                if (n & 2u) {
+                    march_step(sx, sy, sz, fdx, fdy, fdz, fsx, fsy, fsz, idx, one);
+                    march_step(sx, sy, sz, fdx, fdy, fdz, fsx, fsy, fsz, idx, one);
+                }
+                if (n & 1u) march_step(sx, sy, sz, fdx, fdy, fdz, fsx, fsy, fsz, idx, one);
             }
             // the k-th step lands on a cell that is looked up next round; remember its side value and axis
             if (on) t_side = fminf(fminf(sx, sy), sz);  // = side_dist.<axis> before the increment (the picked side is the minimum)
