@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(256) trace_ref_kernel(const __grid_constant__ 
 #define VRT_TUNED_BLOCKS 8
 #endif
 #ifndef VRT_GENERAL_BLOCKS
-#define VRT_GENERAL_BLOCKS 6  // the general shading path (scatter functions, RNG, sample loop) keeps 80 registers: at 64 it spills 470 bytes
+#define VRT_GENERAL_BLOCKS 8  // the general shading path spills 470 bytes at 64 registers and is still 4 % faster than 24 warps at 80 (REF workload)
 #endif
 #ifndef VRT_TICKET_PREFETCH
 #define VRT_TICKET_PREFETCH 0
