@@ -285,6 +285,10 @@ int vrt_insert_voxels(vrt_ctx* ctx, const uint32_t* xyzm_host, size_t count, uin
                                           bringing them up to date with the uploads made so far */
 /* Debug / tests: the next trace rebuilds the distance planes from scratch instead of patching them for the bricks added since. */
 int vrt_debug_force_accel_rebuild(vrt_ctx* ctx);
+/* Analysis builds only (-DVRT_TILE_STATS=1, tools/gpu_tilestats.py; VRT_E_STATE otherwise): the first call arms per-tile counters, later
+ * calls read 8 words per tile: rounds, step-loop iterations, brick phases, voxel-loop iterations, lanes marching (summed over rounds),
+ * lanes testing (summed over brick phases), voxel hits, clock ticks / 32. */
+int vrt_debug_tile_stats(vrt_ctx* ctx, uint32_t* host, size_t tiles);
 /* Copy `count` elements starting at element `offset` of a grid buffer to the host (the inverse of vrt_upload_*).  Blocks. */
 int vrt_download_buffer(vrt_ctx* ctx, uint32_t which, size_t offset, void* host, size_t count);
 

@@ -272,7 +272,7 @@ struct TraceParams {
     vrt_aov* aov;                 // nullable
     unsigned long long* counters; // nullable, 8 x u64 in vrt_counters order
     // derived acceleration structures (built on the device from the buffers above, vrt_kernels.cu "build_*")
-    const unsigned long long* occ_dense;  // [n_bricks] 4^3 voxel mask per GRID cell (brick_dim == 4 only)
+    const uint4* cell_rec;                // [n_bricks] per GRID cell: 4^3 voxel mask (x, y), material start (z), brick index (w); brick_dim == 4 only
     const uint8_t* dist;                  // 8 padded directional Chebyshev distance grids (one per octant), see vrt_trav_warp.cuh
     unsigned long long dist_plane;        // bytes per octant
     uint32_t dist_log_px, dist_log_pz;    // row / plane strides of `dist` are powers of two: x + (z << log_px) + (y << (log_px+log_pz))

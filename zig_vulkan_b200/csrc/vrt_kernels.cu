@@ -96,6 +96,10 @@ __global__ void __launch_bounds__(kTunedThreads, SIMPLE ? VRT_TUNED_BLOCKS : VRT
         // convention image row 0 is up (sky); starting with the ground rows leaves the cheap sky tiles to fill the tail of the launch.
         const uint32_t tile = P.tile_order ? __ldg(P.tile_order + P.order_offset + (uint32_t)t * P.order_stride) : tiles_total - 1u - (uint32_t)t;
         const long long tick0 = P.tile_cost ? clock64() : 0ll;
+#if VRT_TILE_STATS
+        if (lane < 8u) warp_stats()[lane] = 0u;
+        __syncwarp();
+#endif
         const uint32_t px = (tile % tiles_x) * kTileW + lx;
         const uint32_t strip = tile / tiles_x;  // this launch's k-th strip of kTileH rows
         const uint32_t py = P.il_world ? (strip * P.il_world + P.il_rank) * kTileH + ly : P.row_begin + strip * kTileH + ly;
@@ -118,6 +122,10 @@ __global__ void __launch_bounds__(kTunedThreads, SIMPLE ? VRT_TUNED_BLOCKS : VRT
             P.fb[(size_t)out_row * width + px] = texel;
             for (uint32_t p = 0; p < P.n_peers; p++) P.peer_fb[p][(size_t)out_row * width + px] = texel;
         }
+#if VRT_TILE_STATS
+        __syncwarp();
+        if (lane < 8u && g_tile_stats) g_tile_stats[(size_t)tile * 8u + lane] = lane == 7u ? (uint32_t)((clock64() - tick0) >> 5) : warp_stats()[lane];
+#endif
         if (P.tile_cost) {  // what this tile cost: the sort key of the next frames' order (lane p also tells peer p)
             const long long ticks = (clock64() - tick0) >> 5;
             const uint16_t c = (uint16_t)(ticks > 65535ll ? 65535ll : (ticks < 1ll ? 1ll : ticks));
@@ -233,17 +241,20 @@ cudaError_t launch_trace_rays(const TraceParams& P, const vrt_ray* rays, vrt_ray
 // ----------------------------------------------------------------------------------------------------
 VRT_DI bool status_bit(const TraceParams& P, size_t g) { return (__ldg(P.statuses + g / 32) >> (g % 32)) & 1u; }
 
-// occ_dense[g] = the 64-bit voxel mask of the brick at grid cell g (0 if not loaded)
-__global__ void __launch_bounds__(256) build_occ_dense_kernel(const __grid_constant__ TraceParams P, unsigned long long* __restrict__ occ_dense,
-                                                              size_t n_bricks) {
+// cell_rec[g] = everything a brick test at grid cell g needs, in one 128-bit load: the 64-bit voxel mask of the brick (0 if not
+// loaded) and where its materials start (brick_type_and_index[brick] & 0x7fffffff, :422).  The shader reaches the same through
+// brick_indices -> brick_solid_mask bytes, and brick_indices -> brick_type_and_index -> material_indices on a hit (:337,:415,:422-425).
+__global__ void __launch_bounds__(256) build_cell_rec_kernel(const __grid_constant__ TraceParams P, uint4* __restrict__ cell_rec, size_t n_bricks) {
     const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n_bricks) return;
     unsigned long long occ = 0ull;
+    uint32_t mat_base = 0u, brick = 0u;
     if (status_bit(P, g)) {
-        const unsigned long long bi = __ldg(P.brick_indices + g);
-        if ((bi + 1ull) * 8ull <= P.n_occupancy) occ = __ldg(reinterpret_cast<const unsigned long long*>(P.occupancy) + bi);
+        brick = g < P.n_brick_indices ? __ldg(P.brick_indices + g) : 0u;
+        if (((unsigned long long)brick + 1ull) * 8ull <= P.n_occupancy) occ = __ldg(reinterpret_cast<const unsigned long long*>(P.occupancy) + brick);
+        mat_base = (brick < P.n_start_indices ? __ldg(P.start_indices + brick) : 0u) & 0x7fffffffu;
     }
-    occ_dense[g] = occ;
+    cell_rec[g] = make_uint4((uint32_t)occ, (uint32_t)(occ >> 32), mat_base, brick);
 }
 
 // Directional distance grids.  For each of the 8 direction octants o (bit0: x decreasing, bit1: y decreasing, bit2: z
@@ -372,11 +383,11 @@ __global__ void accel_delta_reset_kernel(AccelDelta* delta) {
 }
 
 // tmp: 6 * n_bricks bytes of scratch.  The border bytes of `dist` (255) are written once when it is allocated.
-cudaError_t launch_build_accel(const TraceParams& P, unsigned long long* occ_dense, uint8_t* dist, uint8_t* tmp, size_t n_bricks, bool occ_only,
+cudaError_t launch_build_accel(const TraceParams& P, uint4* cell_rec, uint8_t* dist, uint8_t* tmp, size_t n_bricks, bool occ_only,
                                AccelDelta* delta, cudaStream_t stream, LaunchInfo* info) {
     const unsigned blocks = (unsigned)((n_bricks + 255) / 256);
-    if (occ_dense) {
-        build_occ_dense_kernel<<<blocks, 256, 0, stream>>>(P, occ_dense, n_bricks);
+    if (cell_rec) {
+        build_cell_rec_kernel<<<blocks, 256, 0, stream>>>(P, cell_rec, n_bricks);
         if (info) info->launches++;
     }
     if (occ_only) return cudaGetLastError();
@@ -453,6 +464,15 @@ cudaError_t launch_peer_barrier(uint32_t* const flags[8], uint32_t rank, uint32_
     peer_barrier_kernel<<<1, 32, 0, stream>>>(pf, rank, world, frame, error);
     if (info) info->launches++;
     return cudaGetLastError();
+}
+
+cudaError_t debug_set_tile_stats(uint32_t* device_buffer) {
+#if VRT_TILE_STATS
+    return cudaMemcpyToSymbol(g_tile_stats, &device_buffer, sizeof(device_buffer));
+#else
+    (void)device_buffer;
+    return cudaErrorNotSupported;
+#endif
 }
 
 cudaError_t launch_trace(const TraceParams& P, TraceKernel which, bool aov, cudaStream_t stream, LaunchInfo* info) {

@@ -33,10 +33,10 @@ struct AccelDelta {
 // Write `count` freshly uploaded status words (staged at `staged`) over dst[0..count) and record what changed in *delta.
 cudaError_t launch_status_merge(uint32_t* dst, const uint32_t* staged, size_t count, size_t first_word, const vrt_grid_state& grid, AccelDelta* delta,
                                 cudaStream_t stream, LaunchInfo* info);
-// Rebuild the derived structures from the reference-format buffers: occ_dense always (brick_dim 4); the distance planes according
+// Rebuild the derived structures from the reference-format buffers: cell_rec always (brick_dim 4); the distance planes according
 // to *delta — untouched if no status bit changed, patched in place for a few new bricks, rebuilt by the three line scans otherwise;
 // *delta is cleared at the end.  occ_only: the distance planes are known to be current (host-side knowledge).  tmp: 6 * n_bricks bytes.
-cudaError_t launch_build_accel(const TraceParams& P, unsigned long long* occ_dense, uint8_t* dist, uint8_t* tmp, size_t n_bricks, bool occ_only,
+cudaError_t launch_build_accel(const TraceParams& P, uint4* cell_rec, uint8_t* dist, uint8_t* tmp, size_t n_bricks, bool occ_only,
                                AccelDelta* delta, cudaStream_t stream, LaunchInfo* info);
 // Tiles (8x4 pixels) of the launch launch_trace_tuned would make for P with no schedule attached: the tile space an order for it permutes.
 uint32_t trace_tile_space(const TraceParams& P);
@@ -76,6 +76,8 @@ size_t insert_scan_scratch_entries(size_t n);
 cudaError_t launch_insert_prepare(const InsertBuffers& B, const uint32_t* xyzm, size_t n, cudaStream_t stream, LaunchInfo* info);
 cudaError_t launch_insert_commit(const InsertBuffers& B, const uint32_t* xyzm, size_t n, uint32_t active_before, uint32_t* last_writer /* touched * brick_bits, zeroed */,
                                  cudaStream_t stream, LaunchInfo* info);
+// analysis builds (-DVRT_TILE_STATS=1): device buffer of 8 words per tile the trace kernel fills; cudaErrorNotSupported otherwise
+cudaError_t debug_set_tile_stats(uint32_t* device_buffer);
 constexpr size_t kPeerFlagBytes = 256;  // flag words appended to the IPC-shared framebuffer allocation
 constexpr uint32_t kStripRows = 4;  // rows per strip of the interleaved partition (= the tile height of the trace kernel)
 cudaError_t launch_trace_tuned(const TraceParams& P, bool aov, cudaStream_t stream, LaunchInfo* info);

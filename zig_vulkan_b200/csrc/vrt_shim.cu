@@ -119,14 +119,14 @@ struct vrt_ctx {
     unsigned long long* d_counters = nullptr;
 
     // derived acceleration structures (vrt_trav_warp.cuh)
-    unsigned long long* d_occ_dense = nullptr;
+    uint4* d_cell_rec = nullptr;  // per grid cell: voxel mask + material start + brick index (brick_dim 4)
     uint8_t* d_dist = nullptr;
     uint8_t* d_dist_tmp = nullptr;  // 6 x n_bricks bytes of scratch for the separable distance scans
     size_t dist_plane = 0;          // bytes per octant
     uint32_t dist_log_px = 0, dist_log_pz = 0;
     uint32_t accel_dim[3] = {0, 0, 0};
     bool accel_dirty = true;   // status words were uploaded: the distance planes MAY be stale (d_accel_delta knows)
-    bool occ_dirty = true;     // brick indices / occupancy bytes changed: occ_dense is stale, the distance planes are not
+    bool occ_dirty = true;     // brick indices / occupancy bytes changed: the per-cell records are stale, the distance planes are not
     bool accel_force = true;   // the distance planes must be rebuilt from scratch (new grid, device-side insert)
     AccelDelta* d_accel_delta = nullptr;  // which status bits the uploads since the last build changed
     uint32_t* d_status_stage = nullptr;   // uploaded status words land here; status_merge_kernel compares them with the live ones
@@ -231,14 +231,14 @@ int upload_range(vrt_ctx* ctx, T* dst, size_t capacity, size_t offset, const T* 
     return stage_upload(ctx, dst + offset, data, count * sizeof(T));
 }
 
-// Bring occ_dense / the distance planes up to date with the uploads (stream-ordered, nothing waits).
+// Bring the per-cell records / the distance planes up to date with the uploads (stream-ordered, nothing waits).
 int rebuild_accel(vrt_ctx* ctx, const TraceParams& P, LaunchInfo* info) {
     const size_t n_cells = (size_t)ctx->grid.dim_x * ctx->grid.dim_y * ctx->grid.dim_z;
     if (ctx->accel_force) {
         VRT_CUDA(ctx, cudaMemsetAsync(&ctx->d_accel_delta->force_full, 1, 1, ctx->stream));  // little-endian: the word becomes >= 1
         ctx->accel_dirty = true;
     }
-    VRT_CUDA(ctx, launch_build_accel(P, ctx->d_occ_dense, ctx->d_dist, ctx->d_dist_tmp, n_cells, !ctx->accel_dirty, ctx->d_accel_delta, ctx->stream, info));
+    VRT_CUDA(ctx, launch_build_accel(P, ctx->d_cell_rec, ctx->d_dist, ctx->d_dist_tmp, n_cells, !ctx->accel_dirty, ctx->d_accel_delta, ctx->stream, info));
     ctx->accel_dirty = ctx->occ_dirty = ctx->accel_force = false;
     return VRT_OK;
 }
@@ -274,7 +274,7 @@ void fill_params(const vrt_ctx* c, const vrt_camera* cam, const vrt_sun* sun, Tr
     P.fb = c->d_fb;
     P.aov = c->d_aov;
     P.counters = c->d_counters;
-    P.occ_dense = c->d_occ_dense;
+    P.cell_rec = c->d_cell_rec;
     P.dist = c->d_dist;
     P.dist_plane = c->dist_plane;
     P.dist_log_px = c->dist_log_px, P.dist_log_pz = c->dist_log_pz;
@@ -447,7 +447,7 @@ int vrt_init(vrt_ctx** out_ctx, const vrt_config* cfg) {
     INIT_CUDA(cudaMemsetAsync(ctx->d_material_indices, 0, ctx->n_material_indices, ctx->stream));
     INIT_CUDA(cudaMemsetAsync(ctx->d_fb_own, 0, shared_bytes, ctx->stream));
     INIT_CUDA(cudaMemsetAsync(ctx->d_tile_counter, 0, 16, ctx->stream));
-    if (cfg->brick_dim == 4) INIT_CUDA(cudaMalloc(&ctx->d_occ_dense, cfg->n_bricks * 8));
+    if (cfg->brick_dim == 4) INIT_CUDA(cudaMalloc(&ctx->d_cell_rec, cfg->n_bricks * sizeof(uint4)));
     if (cfg->flags & VRT_FLAG_AOV) {
         INIT_CUDA(cudaMalloc(&ctx->d_aov, (size_t)cfg->width * cfg->height * sizeof(vrt_aov)));
         INIT_CUDA(cudaMalloc(&ctx->d_counters, 8 * sizeof(unsigned long long)));
@@ -471,7 +471,7 @@ void vrt_deinit(vrt_ctx* ctx) {
     }
     cudaFree(ctx->d_materials), cudaFree(ctx->d_statuses), cudaFree(ctx->d_brick_indices), cudaFree(ctx->d_occupancy);
     cudaFree(ctx->d_start_indices), cudaFree(ctx->d_material_indices), cudaFree(ctx->d_fb_own), cudaFree(ctx->d_aov);
-    cudaFree(ctx->d_counters), cudaFree(ctx->d_occ_dense), cudaFree(ctx->d_dist), cudaFree(ctx->d_dist_tmp);
+    cudaFree(ctx->d_counters), cudaFree(ctx->d_cell_rec), cudaFree(ctx->d_dist), cudaFree(ctx->d_dist_tmp);
     cudaFree(ctx->d_order), cudaFree(ctx->d_sched_scratch), cudaFree(ctx->d_status_stage), cudaFree(ctx->d_accel_delta);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     for (int i = 0; i < 4; i++)
@@ -534,7 +534,7 @@ int vrt_upload_brick_statuses(vrt_ctx* ctx, size_t offset, const uint32_t* data,
 }
 int vrt_upload_brick_indices(vrt_ctx* ctx, size_t offset, const uint32_t* data, size_t count) {
     const int rc = upload_range(ctx, ctx ? ctx->d_brick_indices : nullptr, ctx ? ctx->n_brick_indices : 0, offset, data, count, "vrt_upload_brick_indices");
-    if (rc == VRT_OK && count) ctx->occ_dirty = true;  // occ_dense is indexed through brick_indices; the distance planes only read the status bits
+    if (rc == VRT_OK && count) ctx->occ_dirty = true;  // the per-cell records are indexed through brick_indices; the distance planes only read the status bits
     return rc;
 }
 int vrt_upload_brick_occupancy(vrt_ctx* ctx, size_t offset, const uint8_t* data, size_t count) {
@@ -543,7 +543,9 @@ int vrt_upload_brick_occupancy(vrt_ctx* ctx, size_t offset, const uint8_t* data,
     return rc;
 }
 int vrt_upload_brick_start_indices(vrt_ctx* ctx, size_t offset, const uint32_t* data, size_t count) {
-    return upload_range(ctx, ctx ? ctx->d_start_indices : nullptr, ctx ? ctx->n_start_indices : 0, offset, data, count, "vrt_upload_brick_start_indices");
+    const int rc = upload_range(ctx, ctx ? ctx->d_start_indices : nullptr, ctx ? ctx->n_start_indices : 0, offset, data, count, "vrt_upload_brick_start_indices");
+    if (rc == VRT_OK && count) ctx->occ_dirty = true;  // the per-cell records carry the material start index
+    return rc;
 }
 int vrt_upload_material_indices(vrt_ctx* ctx, size_t offset, const uint8_t* data, size_t count) {
     return upload_range(ctx, ctx ? ctx->d_material_indices : nullptr, ctx ? ctx->n_material_indices : 0, offset, data, count, "vrt_upload_material_indices");
@@ -881,6 +883,28 @@ int vrt_download_buffer(vrt_ctx* ctx, uint32_t which, size_t offset, void* host,
     VRT_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
     VRT_CUDA(ctx, cudaMemcpyAsync(host, src + offset * elem, count * elem, cudaMemcpyDeviceToHost, ctx->stream));
     VRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VRT_OK;
+}
+
+int vrt_debug_tile_stats(vrt_ctx* ctx, uint32_t* host, size_t tiles) {
+    if (!ctx || !host || tiles > ctx->tiles_global) return VRT_E_INVALID;
+    VRT_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    static uint32_t* d_stats = nullptr;  // analysis only: one buffer per process
+    static size_t d_tiles = 0;
+    if (d_tiles < ctx->tiles_global) {
+        cudaFree(d_stats);
+        VRT_CUDA(ctx, cudaMalloc(&d_stats, (size_t)ctx->tiles_global * 32));
+        d_tiles = ctx->tiles_global;
+        VRT_CUDA(ctx, cudaMemset(d_stats, 0, (size_t)ctx->tiles_global * 32));
+        if (debug_set_tile_stats(d_stats) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(ctx, VRT_E_STATE, "vrt_debug_tile_stats: this build has no tile statistics (-DVRT_TILE_STATS=1)");
+        }
+        std::memset(host, 0, tiles * 32);
+        return VRT_OK;  // armed: the next traces fill it
+    }
+    VRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    VRT_CUDA(ctx, cudaMemcpy(host, d_stats, tiles * 32, cudaMemcpyDeviceToHost));
     return VRT_OK;
 }
 

@@ -20,7 +20,7 @@
 //     the grid.  Phase B: the parked rays run the voxel-level DDA together.
 //     The expensive brick entry (three divides, a 64-bit mask fetch) is therefore executed coherently instead of once
 //     per ray at 32 different times.
-//   * The 4^3 voxel mask of a brick is one 64-bit load from a grid-indexed copy (`occ_dense`) and the voxel DDA runs in
+//   * The 4^3 voxel mask of a brick and the start of its materials are one 128-bit load from a grid-indexed record (`cell_rec`) and the voxel DDA runs in
 //     registers on ONE packed integer (bounds guard + voxel index, brick_hit_warp4); 8^3 / 16^3 bricks keep the current 32-bit
 //     mask word in a register (brick_hit_warp_n).  The shader does a dependent brick_indices load plus one byte load per
 //     voxel step (:337,:415).
@@ -36,6 +36,28 @@
 namespace vrt {
 
 constexpr unsigned kFullMask = 0xffffffffu;
+
+// -DVRT_TILE_STATS=1 (analysis builds only, tools/gpu_tilestats.py): per-warp counters of where a tile's instructions go —
+// rounds, step-loop iterations, brick phases, voxel-loop iterations — kept in shared memory, flushed per tile by the trace kernel.
+#ifndef VRT_TILE_STATS
+#define VRT_TILE_STATS 0
+#endif
+#if VRT_TILE_STATS
+__device__ uint32_t* g_tile_stats;  // [tiles][8]
+VRT_DI uint32_t* warp_stats() {
+    __shared__ uint32_t s[32][8];
+    return s[threadIdx.x >> 5];
+}
+#define VRT_STAT(i, v)                                          \
+    do {                                                        \
+        const uint32_t v_ = (v); /* evaluated by every lane */  \
+        if ((threadIdx.x & 31u) == 0u) warp_stats()[i] += v_;   \
+    } while (0)
+#else
+#define VRT_STAT(i, v) \
+    do {               \
+    } while (0)
+#endif
 
 // hit.normal as (axis, sign): every normal this path produces has one non-zero component (:350-370, :530-531)
 struct AxisNormal {
@@ -132,8 +154,14 @@ VRT_DI int brick_hit_warp4(const TraceParams& P, const Ray& r, bool ignore_test,
     const int stx = ray_step.x * (1 + (1 << 12)), stz = ray_step.z * ((1 << 4) + (4 << 12)), sty = ray_step.y * ((1 << 8) + (16 << 12));
     int prev = state;
     int found = -1;
+#if VRT_TILE_STATS
+    uint32_t my_iters = 0u;
+#endif
     while ((state & kInside) == kInside && t_value <= local_t_max) {  // :407-411
         if (INFO == 2) ti.voxel_steps++;
+#if VRT_TILE_STATS
+        my_iters++;
+#endif
         const int voxel_index = state >> 12;  // :412
         if ((occ >> voxel_index) & 1ull) {    // :415-417
             bool ignore_brick = false;
@@ -152,6 +180,12 @@ VRT_DI int brick_hit_warp4(const TraceParams& P, const Ray& r, bool ignore_test,
         march_step(sx, sy, sz, ray_delta.x, ray_delta.y, ray_delta.z, stx, sty, stz, state, one);  // :440-467
     }
     __syncwarp(lanes);  // the rays leave the loop at different trips: finish hits (and, in the caller, misses) together
+#if VRT_TILE_STATS
+    {
+        const uint32_t mx = __reduce_max_sync(lanes, my_iters);
+        if ((threadIdx.x & 31u) == (uint32_t)(__ffs((int)lanes) - 1)) warp_stats()[3] += mx, warp_stats()[6] += (uint32_t)__popc(__ballot_sync(__activemask(), found >= 0));
+    }
+#endif
     if (found >= 0) {
         const int moved = (state >> 12) - (prev >> 12);  // 0: hit in the entry voxel, the normal stays the brick-level one
         if (moved != 0) {
@@ -171,6 +205,9 @@ VRT_DI int brick_hit_warp4(const TraceParams& P, const Ray& r, bool ignore_test,
 #endif
 #ifndef VRT_PREFETCH_K
 #define VRT_PREFETCH_K 3
+#endif
+#ifndef VRT_PARK_PREFETCH
+#define VRT_PARK_PREFETCH 0
 #endif
 #ifndef VRT_KSLACK
 #define VRT_KSLACK 0
@@ -437,6 +474,13 @@ VRT_DI bool grid_hit_warp(const TraceParams& P, const Ray& r, bool active, bool 
                     }
                 }
                 if (out || d == 0u) {  // d == 0: status bit set (:328) -> park for phase B
+#if VRT_PARK_PREFETCH
+                    if (BD == 4 && !out) {  // the brick's record is wanted in phase B, however many rounds away that is: ask L1 for it now
+                        const int pc = idx - obase;
+                        const int qx = (pc & ((1 << log_px) - 1)) - 1, qz = ((pc >> log_px) & ((1 << (log_pzx - log_px)) - 1)) - 1, qy = (pc >> log_pzx) - 1;
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(P.cell_rec + (uint32_t)(qx + (int)P.grid.dim_x * (qz + (int)P.grid.dim_z * qy))));
+                    }
+#endif
                     mode = out ? kDone : kParked;
                     d = kIdle;
                     fdx = fdy = fdz = 0.0f, fsx = fsy = fsz = 0;
@@ -444,6 +488,9 @@ VRT_DI bool grid_hit_warp(const TraceParams& P, const Ray& r, bool active, bool 
             }
             const uint32_t k = __reduce_min_sync(kFullMask, d);
             if (k == kIdle) break;
+            VRT_STAT(0, 1u);                                           // rounds
+            VRT_STAT(1, k);                                            // step-loop iterations
+            VRT_STAT(4, (uint32_t)__popc(__ballot_sync(kFullMask, d != kIdle)));  // lanes marching in this round
 #if VRT_PREFETCH
             near_rounds = k <= VRT_PREFETCH_K;
 #endif
@@ -503,6 +550,10 @@ VRT_DI bool grid_hit_warp(const TraceParams& P, const Ray& r, bool active, bool 
         }
         // ---- phase B: the parked rays test their bricks together (:329-342)
         const unsigned parked_lanes = __ballot_sync(kFullMask, mode == kParked);
+        if (parked_lanes) {
+            VRT_STAT(2, 1u);                                // brick phases
+            VRT_STAT(5, (uint32_t)__popc(parked_lanes));    // lanes testing a brick in them
+        }
         if (mode == kParked) {
             if (last_stride != 0) {
                 const int a = last_stride < 0 ? -last_stride : last_stride;
@@ -512,7 +563,11 @@ VRT_DI bool grid_hit_warp(const TraceParams& P, const Ray& r, bool active, bool 
             const int x = (cell & ((1 << log_px) - 1)) - 1, z = ((cell >> log_px) & ((1 << (log_pzx - log_px)) - 1)) - 1, y = (cell >> log_pzx) - 1;
             const uint32_t grid_index = (uint32_t)(x + (int)P.grid.dim_x * (z + (int)P.grid.dim_z * y));  // :318
             unsigned long long occ = 0ull;
-            if (BD == 4) occ = __ldg(P.occ_dense + grid_index);
+            uint32_t mat_base = 0u;
+            if (BD == 4) {
+                const uint4 rec = __ldg(P.cell_rec + grid_index);
+                occ = (unsigned long long)rec.x | ((unsigned long long)rec.y << 32), mat_base = rec.z;
+            }
             const V3 brick_min = fma3(v3((float)x, (float)y, (float)z), v3s(g_scale), g_min);  // :331
             const float t_value = t_side * g_scale;                                            // :347,353,361,367
             hit.t = (t_value + grid_t_min) + 0.01f * g_scale;                                  // :332-334
@@ -520,7 +575,14 @@ VRT_DI bool grid_hit_warp(const TraceParams& P, const Ray& r, bool active, bool 
             const int voxel_index = BD == 4 ? brick_hit_warp4<INFO>(P, r, ignore_test, grid_t_max, ray_delta, ray_step, g_scale, brick_min, occ, grid_index, parked_lanes, hit, n, ti, one)
                                              : brick_hit_warp_n<INFO>(P, r, ignore_test, grid_t_max, ray_delta, ray_step, g_scale, brick_min, grid_index, parked_lanes, hit, n, ti, one);
             if (voxel_index >= 0) {
-                if (need_material && !ignore_test) hit.index = material_index_at(P, grid_index, voxel_index);
+                if (need_material && !ignore_test) {
+                    if (BD == 4) {  // material_indices[start + voxel_index] (:425) with the start index already in hand
+                        const unsigned long long mi = (unsigned long long)mat_base + (uint32_t)voxel_index;
+                        hit.index = mi < P.n_material_indices ? (uint32_t)__ldg(P.material_indices + mi) : 0u;
+                    } else {
+                        hit.index = material_index_at(P, grid_index, voxel_index);
+                    }
+                }
                 if (INFO >= 1) ti.grid_index = grid_index, ti.voxel_index = (uint32_t)voxel_index;
                 result = true;
                 mode = kDone;

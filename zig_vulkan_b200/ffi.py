@@ -169,6 +169,7 @@ VRT_SYMBOLS = {
     "vrt_last_trace_kernel_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "vrt_last_trace_launches": (C.c_int, [_P, C.POINTER(C.c_uint32)]),
     "vrt_debug_force_accel_rebuild": (C.c_int, [_P]),
+    "vrt_debug_tile_stats": (C.c_int, [_P, _P, _SZ]),
     "vrt_set_schedule": (C.c_int, [_P, C.c_uint32, C.c_uint32]),
     "vrt_sched_get_costs": (C.c_int, [_P, _P, _SZ]),
     "vrt_sched_set_costs": (C.c_int, [_P, _P, _SZ]),
