@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(256) build_cell_rec_kernel(const __grid_consta
 constexpr uint32_t kDistCap = 126u;
 
 __global__ void __launch_bounds__(128) dist_scan_kernel(const __grid_constant__ TraceParams P, const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
-                                                        size_t n_bricks, int axis, const AccelDelta* __restrict__ delta, uint8_t* __restrict__ lateral) {
+                                                        size_t n_bricks, int axis, const AccelDelta* __restrict__ delta) {
     if (delta && !(delta->force_full || delta->n_new > kAccelMaxNew)) return;  // nothing changed, or dist_patch_kernel has done it
     const size_t dim_x = P.grid.dim_x, dim_y = P.grid.dim_y, dim_z = P.grid.dim_z;
     const size_t lines = axis == 0 ? dim_z * dim_y : (axis == 1 ? dim_x * dim_y : dim_x * dim_z);
@@ -307,13 +307,6 @@ __global__ void __launch_bounds__(128) dist_scan_kernel(const __grid_constant__ 
             out[(size_t)v * P.dist_plane + dist_addr(cell, P.dist_xhi_mask, P.dist_zlo_mask, P.dist_wx)] = (uint8_t)byte;
         } else {
             out[(size_t)v * n_bricks + g] = (uint8_t)byte;
-            if (axis == 1 && lateral) {
-                // after the x and z passes the value is the L1 distance to the nearest blocker INSIDE THIS y-LAYER, in the (x, z)
-                // quadrant v: the lateral planes 8..11 (a ray that provably takes no y step for a while only meets those blockers)
-                const uint32_t x = (uint32_t)(line % dim_x), y = (uint32_t)(line / dim_x);
-                const uint32_t cell = (x + 1u) + ((uint32_t)(c + 1) << P.dist_log_px) + ((y + 1u) << (P.dist_log_px + P.dist_log_pz));
-                lateral[(size_t)(8 + v) * P.dist_plane + cell] = (uint8_t)byte;
-            }
         }
     }
 }
@@ -363,25 +356,22 @@ __global__ void __launch_bounds__(256) dist_patch_kernel(const __grid_constant__
     const uint32_t dim_x = P.grid.dim_x, dim_y = P.grid.dim_y, dim_z = P.grid.dim_z;
     const size_t cell = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (cell >= (size_t)dim_x * dim_y * dim_z) return;
-    const int o = (int)blockIdx.y;  // bit0: x decreasing, bit1: y decreasing, bit2: z decreasing (dist_scan_kernel); 8..11: lateral planes
-    const bool lateral = o >= 8;    // (x, z) quadrant bit0: x decreasing, bit1: z decreasing, blockers of the cell's own y-layer only
-    const int xneg = lateral ? (o - 8) & 1 : o & 1, zneg = lateral ? (o - 8) & 2 : o & 4, yneg = o & 2;
+    const int o = (int)blockIdx.y;  // bit0: x decreasing, bit1: y decreasing, bit2: z decreasing (dist_scan_kernel)
     const int px = (int)(cell % dim_x), pz = (int)((cell / dim_x) % dim_z), py = (int)(cell / ((size_t)dim_x * dim_z));
-    // the octant / quadrant of p must contain at least the extreme new cell
-    if (xneg ? px < (int)delta->lo[0] : px > (int)delta->hi[0]) return;
-    if (lateral ? (py < (int)delta->lo[1] || py > (int)delta->hi[1]) : (yneg ? py < (int)delta->lo[1] : py > (int)delta->hi[1])) return;
-    if (zneg ? pz < (int)delta->lo[2] : pz > (int)delta->hi[2]) return;
+    // the octant of p must contain at least the extreme new cell
+    if ((o & 1) ? px < (int)delta->lo[0] : px > (int)delta->hi[0]) return;
+    if ((o & 2) ? py < (int)delta->lo[1] : py > (int)delta->hi[1]) return;
+    if ((o & 4) ? pz < (int)delta->lo[2] : pz > (int)delta->hi[2]) return;
     uint32_t best = 0xffffu;
     for (uint32_t j = 0; j < n; j++) {
         const uint32_t g = delta->cell[j];
         const int qx = (int)(g % dim_x), qz = (int)((g / dim_x) % dim_z), qy = (int)(g / (dim_x * dim_z));
-        const int dx = xneg ? px - qx : qx - px, dz = zneg ? pz - qz : qz - pz;
-        const int dy = lateral ? (py == qy ? 0 : -1) : (yneg ? py - qy : qy - py);
+        const int dx = (o & 1) ? px - qx : qx - px, dy = (o & 2) ? py - qy : qy - py, dz = (o & 4) ? pz - qz : qz - pz;
         if (dx >= 0 && dy >= 0 && dz >= 0) best = min(best, (uint32_t)(dx + dy + dz));
     }
     if (best == 0xffffu) return;
     const uint32_t padded = (uint32_t)(px + 1) + ((uint32_t)(pz + 1) << P.dist_log_px) + ((uint32_t)(py + 1) << (P.dist_log_px + P.dist_log_pz));
-    uint8_t* at = dist + (size_t)o * P.dist_plane + (lateral ? padded : dist_addr(padded, P.dist_xhi_mask, P.dist_zlo_mask, P.dist_wx));
+    uint8_t* at = dist + (size_t)o * P.dist_plane + dist_addr(padded, P.dist_xhi_mask, P.dist_zlo_mask, P.dist_wx);
     const uint32_t cur = *at;
     const uint32_t d = min(min(cur & 0x7fu, best), kDistCap);
     if (d != cur) *at = (uint8_t)d;  // free bit cleared
@@ -405,12 +395,12 @@ cudaError_t launch_build_accel(const TraceParams& P, uint4* cell_rec, uint8_t* d
     uint8_t* tmp_z = tmp + 2 * n_bricks;  // [4][n]
     const size_t dx = P.grid.dim_x, dy = P.grid.dim_y, dz = P.grid.dim_z;
     if (delta) {
-        dist_patch_kernel<<<dim3(blocks, 12), 256, 0, stream>>>(P, dist, delta);
+        dist_patch_kernel<<<dim3(blocks, 8), 256, 0, stream>>>(P, dist, delta);
         if (info) info->launches++;
     }
-    dist_scan_kernel<<<dim3((unsigned)((dz * dy + 127) / 128), 2), 128, 0, stream>>>(P, nullptr, tmp_x, n_bricks, 0, delta, nullptr);
-    dist_scan_kernel<<<dim3((unsigned)((dx * dy + 127) / 128), 4), 128, 0, stream>>>(P, tmp_x, tmp_z, n_bricks, 1, delta, dist);
-    dist_scan_kernel<<<dim3((unsigned)((dx * dz + 127) / 128), 8), 128, 0, stream>>>(P, tmp_z, dist, n_bricks, 2, delta, nullptr);
+    dist_scan_kernel<<<dim3((unsigned)((dz * dy + 127) / 128), 2), 128, 0, stream>>>(P, nullptr, tmp_x, n_bricks, 0, delta);
+    dist_scan_kernel<<<dim3((unsigned)((dx * dy + 127) / 128), 4), 128, 0, stream>>>(P, tmp_x, tmp_z, n_bricks, 1, delta);
+    dist_scan_kernel<<<dim3((unsigned)((dx * dz + 127) / 128), 8), 128, 0, stream>>>(P, tmp_z, dist, n_bricks, 2, delta);
     if (info) info->launches += 3;
     if (delta) {
         accel_delta_reset_kernel<<<1, 1, 0, stream>>>(delta);

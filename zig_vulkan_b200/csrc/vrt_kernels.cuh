@@ -10,7 +10,6 @@ enum TraceKernel : int {
     KERNEL_TUNED = 1,  // warp-cooperative traversal over the derived distance grid (vrt_trav_warp.cuh)
 };
 
-constexpr uint32_t kDistPlanes = 12u;   // 8 octant planes + 4 lateral planes (per (x, z) quadrant: blockers of the cell's own y-layer only)
 constexpr uint32_t kDistBorder = 255u;  // dist byte of the one-cell border around the grid
 constexpr uint32_t kDistFree = 0x80u;   // dist bit: no loaded brick anywhere in this cell's octant (low 7 bits: distance, <= 126)
 

@@ -328,11 +328,11 @@ int ensure_accel(vrt_ctx* ctx) {
     while ((1u << lz) < dz + 2) lz++;
     ctx->dist_log_px = lx, ctx->dist_log_pz = lz;
     ctx->dist_plane = ((size_t)(dy + 2)) << (lx + lz);
-    if (kDistPlanes * ctx->dist_plane > 0x7fffffffull)
-        return fail(ctx, VRT_E_INVALID, "grid %ux%ux%u is too large for the 31-bit cell index of the march (%u padded distance planes)", dx, dy, dz, kDistPlanes);
-    VRT_CUDA(ctx, cudaMalloc(&ctx->d_dist, kDistPlanes * ctx->dist_plane));
+    if (8 * ctx->dist_plane > 0x7fffffffull)
+        return fail(ctx, VRT_E_INVALID, "grid %ux%ux%u is too large for the 31-bit cell index of the march (8 padded distance planes)", dx, dy, dz);
+    VRT_CUDA(ctx, cudaMalloc(&ctx->d_dist, 8 * ctx->dist_plane));
     VRT_CUDA(ctx, cudaMalloc(&ctx->d_dist_tmp, 6 * (size_t)dx * dy * dz));
-    VRT_CUDA(ctx, cudaMemsetAsync(ctx->d_dist, 255, kDistPlanes * ctx->dist_plane, ctx->stream));  // the border; interiors are rewritten by every build
+    VRT_CUDA(ctx, cudaMemsetAsync(ctx->d_dist, 255, 8 * ctx->dist_plane, ctx->stream));  // the border; interiors are rewritten by every build
     ctx->accel_dim[0] = dx, ctx->accel_dim[1] = dy, ctx->accel_dim[2] = dz;
     ctx->accel_dirty = ctx->accel_force = true;
     return VRT_OK;
@@ -872,7 +872,7 @@ int vrt_download_buffer(vrt_ctx* ctx, uint32_t which, size_t offset, void* host,
                 const int rcb = rebuild_accel(ctx, P, nullptr);
                 if (rcb != VRT_OK) return rcb;
             }
-            src = ctx->d_dist, capacity = kDistPlanes * ctx->dist_plane, elem = 1;
+            src = ctx->d_dist, capacity = 8 * ctx->dist_plane, elem = 1;
             break;
         }
         default: return fail(ctx, VRT_E_INVALID, "vrt_download_buffer: unknown buffer %u", which);

@@ -206,9 +206,6 @@ VRT_DI int brick_hit_warp4(const TraceParams& P, const Ray& r, bool ignore_test,
 #ifndef VRT_PREFETCH_K
 #define VRT_PREFETCH_K 3
 #endif
-#ifndef VRT_LATERAL
-#define VRT_LATERAL 0
-#endif
 #ifndef VRT_PARK_PREFETCH
 #define VRT_PARK_PREFETCH 0
 #endif
@@ -422,11 +419,6 @@ VRT_DI bool grid_hit_warp(const TraceParams& P, const Ray& r, bool active, bool 
     // valid for it): the octant's plane offset is folded into the index and removed again when a cell is decoded
     const int obase = (int)(((ray_step.x < 0 ? 1u : 0u) | (ray_step.y < 0 ? 2u : 0u) | (ray_step.z < 0 ? 4u : 0u)) * (uint32_t)P.dist_plane);
     idx += obase;
-#if VRT_LATERAL
-    // the lateral plane of this ray's (x, z) quadrant, addressed with the same index: plane 8 + quadrant, minus the octant offset in idx
-    const int lbase = (int)((8u + ((ray_step.x < 0 ? 1u : 0u) | (ray_step.z < 0 ? 2u : 0u))) * (uint32_t)P.dist_plane) - obase;
-    const float adx = fabsf(r.direction.x), adz = fabsf(r.direction.z);  // = 1 / ray_delta (0 for an axis the ray does not move along)
-#endif
     const uint8_t* __restrict__ dist = P.dist;
     const int one = (int)P.one;
     int last_stride = 0;  // stride of the most recent step (0: none yet -> slab normal)
@@ -455,9 +447,6 @@ VRT_DI bool grid_hit_warp(const TraceParams& P, const Ray& r, bool active, bool 
             uint32_t d = kIdle;
             if (mode == kMarching) {
                 d = __ldg(dist + dist_addr((uint32_t)idx, P.dist_xhi_mask, P.dist_zlo_mask, P.dist_wx));
-#if VRT_LATERAL
-                const uint32_t dl = __ldg(dist + idx + lbase);
-#endif
 #if VRT_PREFETCH
                 // Near a surface the rounds are one or two steps long and the next lookup lands on a neighbouring cell: the x
                 // neighbours share this cell's 128-byte line, the z / y neighbours are one row / one plane away.  Ask for those
@@ -478,18 +467,6 @@ VRT_DI bool grid_hit_warp(const TraceParams& P, const Ray& r, bool active, bool 
                 const bool out = COUNT ? d == kDistBorder : (d & kDistFree) != 0u;
                 if (!out) {
                     d &= 0x7fu;
-#if VRT_LATERAL
-                    // Lateral shortcut.  The octant distance counts the terrain right below a ray that skims over it (d = 1 cell after
-                    // cell) although the ray hardly ever steps in y.  A y step needs sx >= sy AND sy < sz (:345-372), so before the next
-                    // one the DDA must take at least a x steps and b z steps, a = (sy - sx) / dx, b = (sy - sz) / dz — counted here one
-                    // short each, which covers the rounding of the running sums by orders of magnitude.  For those a + b steps the ray
-                    // stays in its y-layer and can only meet the blockers of that layer: the lateral distance dl.
-                    if (d != 0u) {
-                        const int na = (int)floorf(fminf((sy - sx) * adx, 127.0f)) - 1, nb = (int)floorf(fminf((sy - sz) * adz, 127.0f)) - 1;
-                        const uint32_t no_y = (uint32_t)(max(na, 0) + max(nb, 0));
-                        d = max(d, min(no_y, dl & 0x7fu));
-                    }
-#endif
                     if (COUNT) {  // an in-grid cell = one iteration of the shader's loop; emulate its one-word status cache (:321-326)
                         ti.grid_steps++;
                         const uint32_t gi = cell_grid_index(P, idx - obase, log_px, log_pzx);

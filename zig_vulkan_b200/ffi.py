@@ -756,7 +756,7 @@ class Context:
         return ms.value
 
     def debug_dist_planes(self) -> np.ndarray:
-        """The derived distance planes (8 octant + 4 lateral planes x padded grid bytes), up to date with the uploads so far.  Tests only."""
+        """The derived distance planes (8 octants x padded grid bytes), up to date with the uploads so far.  Tests only."""
         n = C.c_size_t(0)
         # capacity is 8 * plane bytes: ask for everything by probing with the grid's padded size
         g = self._grid_dims
@@ -766,10 +766,10 @@ class Context:
         lz = 1
         while (1 << lz) < g[2] + 2:
             lz += 1
-        count = 12 * ((g[1] + 2) << (lx + lz))
+        count = 8 * ((g[1] + 2) << (lx + lz))
         out = np.empty(count, dtype=np.uint8)
         self._check(self._l.vrt_download_buffer(self.handle, 100, 0, _ptr(out), count))
-        return out.reshape(12, g[1] + 2, 1 << lz, 1 << lx)
+        return out.reshape(8, g[1] + 2, 1 << lz, 1 << lx)
 
     def debug_force_accel_rebuild(self):
         self._check(self._l.vrt_debug_force_accel_rebuild(self.handle))
