@@ -231,20 +231,6 @@ VRT_DI uint32_t unorm8(float c) {
 }
 VRT_DI uint32_t pack_rgba8(V3 c) { return unorm8(c.x) | (unorm8(c.y) << 8) | (unorm8(c.z) << 16) | 0xff000000u; }
 
-#ifndef VRT_DIST_BLOCK2D
-#define VRT_DIST_BLOCK2D 0
-#endif
-// Byte address of padded cell index `idx` inside the distance planes (see TraceParams::dist_xhi_mask).  The march keeps the
-// linear index (one add per step, decodable with shifts); the swap is paid once per lookup.
-__host__ __device__ __forceinline__ uint32_t dist_addr(uint32_t idx, uint32_t xhi_mask, uint32_t zlo_mask, uint32_t wx) {
-#if VRT_DIST_BLOCK2D
-    return (idx & ~(xhi_mask | zlo_mask)) | ((idx & zlo_mask) >> wx) | ((idx & xhi_mask) << 3);
-#else
-    (void)xhi_mask, (void)zlo_mask, (void)wx;
-    return idx;
-#endif
-}
-
 // Everything a trace kernel needs, passed by value as a __grid_constant__ (lands in the constant bank, the
 // CUDA analogue of the reference's push constants + UBO + descriptor set).
 struct TraceParams {
@@ -276,9 +262,6 @@ struct TraceParams {
     const uint8_t* dist;                  // 8 padded directional Chebyshev distance grids (one per octant), see vrt_trav_warp.cuh
     unsigned long long dist_plane;        // bytes per octant
     uint32_t dist_log_px, dist_log_pz;    // row / plane strides of `dist` are powers of two: x + (z << log_px) + (y << (log_px+log_pz))
-    // Where cell `idx` of that padded index space lives in memory: with two bit fields swapped (x bits 4.. <-> z bits 0-2), so that a
-    // 128-byte line holds a 16 x 8 patch of an (x, z) plane instead of 128 cells of one row (dist_addr below).  All zero: idx itself.
-    uint32_t dist_xhi_mask, dist_zlo_mask, dist_wx;
     uint32_t scale_pow2, voxel_scale_pow2;  // brick / voxel scale is a power of two -> divide by multiplying with the exact inverse
     float inv_scale, inv_voxel_scale;
     // persistent-kernel work queue: counter[0] = next ticket, counter[1] = warps that have left the queue; the last warp to

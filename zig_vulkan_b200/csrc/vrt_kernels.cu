@@ -45,9 +45,6 @@ __global__ void __launch_bounds__(256) trace_ref_kernel(const __grid_constant__ 
 #ifndef VRT_GENERAL_BLOCKS
 #define VRT_GENERAL_BLOCKS 8  // the general shading path spills 470 bytes at 64 registers and is still 4 % faster than 24 warps at 80 (REF workload)
 #endif
-#ifndef VRT_TICKET_PREFETCH
-#define VRT_TICKET_PREFETCH 0
-#endif
 constexpr int kTunedThreads = VRT_TUNED_THREADS;
 constexpr uint32_t kTileW = 8, kTileH = 4;
 
@@ -75,23 +72,11 @@ __global__ void __launch_bounds__(kTunedThreads, SIMPLE ? VRT_TUNED_BLOCKS : VRT
     if (BD != 4 && P.brick_dim == 16) brick_stage_init();
 #endif
 
-#if VRT_TICKET_PREFETCH
-    // the ticket of the NEXT tile is drawn while this one is traced: the atomic's round trip to L2 (4 % of the stall samples at the
-    // head of every tile) overlaps the tile instead of preceding it
-    unsigned long long t_next = 0ull;
-    if (lane == 0) t_next = atomicAdd(P.tile_counter, 1ull);
-#endif
     for (;;) {
         unsigned long long t = 0ull;
-#if VRT_TICKET_PREFETCH
-        t = __shfl_sync(kFullMask, t_next, 0);
-        if (t >= (unsigned long long)tiles_total) break;
-        if (lane == 0) t_next = atomicAdd(P.tile_counter, 1ull);
-#else
         if (lane == 0) t = atomicAdd(P.tile_counter, 1ull);
         t = __shfl_sync(kFullMask, t, 0);
         if (t >= (unsigned long long)tiles_total) break;
-#endif
         // Scheduled: the most expensive tiles of the previous frames first (vrt_sched.cu).  Otherwise bottom-up: in the reference's
         // convention image row 0 is up (sky); starting with the ground rows leaves the cheap sky tiles to fill the tail of the launch.
         const uint32_t tile = P.tile_order ? __ldg(P.tile_order + P.order_offset + (uint32_t)t * P.order_stride) : tiles_total - 1u - (uint32_t)t;
@@ -303,8 +288,7 @@ __global__ void __launch_bounds__(128) dist_scan_kernel(const __grid_constant__ 
         const uint32_t byte = d | fr;
         if (axis == 2) {
             const uint32_t x = (uint32_t)(g % dim_x), z = (uint32_t)((g / dim_x) % dim_z);
-            const uint32_t cell = (x + 1u) + ((z + 1u) << P.dist_log_px) + ((uint32_t)(c + 1) << (P.dist_log_px + P.dist_log_pz));
-            out[(size_t)v * P.dist_plane + dist_addr(cell, P.dist_xhi_mask, P.dist_zlo_mask, P.dist_wx)] = (uint8_t)byte;
+            out[(size_t)v * P.dist_plane + (size_t)(x + 1) + ((size_t)(z + 1) << P.dist_log_px) + ((size_t)(c + 1) << (P.dist_log_px + P.dist_log_pz))] = (uint8_t)byte;
         } else {
             out[(size_t)v * n_bricks + g] = (uint8_t)byte;
         }
@@ -371,7 +355,7 @@ __global__ void __launch_bounds__(256) dist_patch_kernel(const __grid_constant__
     }
     if (best == 0xffffu) return;
     const uint32_t padded = (uint32_t)(px + 1) + ((uint32_t)(pz + 1) << P.dist_log_px) + ((uint32_t)(py + 1) << (P.dist_log_px + P.dist_log_pz));
-    uint8_t* at = dist + (size_t)o * P.dist_plane + dist_addr(padded, P.dist_xhi_mask, P.dist_zlo_mask, P.dist_wx);
+    uint8_t* at = dist + (size_t)o * P.dist_plane + padded;
     const uint32_t cur = *at;
     const uint32_t d = min(min(cur & 0x7fu, best), kDistCap);
     if (d != cur) *at = (uint8_t)d;  // free bit cleared

@@ -278,11 +278,6 @@ void fill_params(const vrt_ctx* c, const vrt_camera* cam, const vrt_sun* sun, Tr
     P.dist = c->d_dist;
     P.dist_plane = c->dist_plane;
     P.dist_log_px = c->dist_log_px, P.dist_log_pz = c->dist_log_pz;
-    if (VRT_DIST_BLOCK2D && c->dist_log_px >= 5 && c->dist_log_pz >= 3) {  // x bits [4, log_px) <-> z bits [0, 3): 16 x 8 cells per 128-byte line
-        P.dist_wx = c->dist_log_px - 4;
-        P.dist_xhi_mask = ((1u << P.dist_wx) - 1u) << 4;
-        P.dist_zlo_mask = 7u << c->dist_log_px;
-    }
     const float scale = c->grid.max_point_scale[3];
     const float voxel_scale = scale * P.brick_voxel_scale;  // :389, same f32 product the kernels form
     P.scale_pow2 = is_pow2(scale) ? 1u : 0u;

@@ -106,29 +106,6 @@ VRT_DI void march_step(float& sx, float& sy, float& sz, float dx, float dy, floa
         : "f"(dx), "f"(dy), "f"(dz), "r"(stx), "r"(sty), "r"(stz), "r"(one));
 }
 
-// The same step for the lanes with i < n only (the others keep their state): the lane predicate is the AND input of the first
-// compare, whose second output (!(sx<sy) & on) feeds the y compare; the z step is on & !x & !y.  11 instructions.
-VRT_DI void march_step_if(uint32_t i, uint32_t n, float& sx, float& sy, float& sz, float dx, float dy, float dz, int stx, int sty, int stz, int& idx, int one) {
-    asm("{\n\t"
-        ".reg .pred on, p1, q1, px, py, pz;\n\t"
-        "setp.lt.u32 on, %11, %12;\n\t"
-        "setp.lt.and.f32 p1|q1, %0, %1, on;\n\t"
-        "setp.lt.and.f32 px, %0, %2, p1;\n\t"
-        "setp.lt.and.f32 py, %1, %2, q1;\n\t"
-        "or.pred pz, px, py;\n\t"
-        "not.pred pz, pz;\n\t"
-        "and.pred pz, pz, on;\n\t"
-        "@px add.rn.f32 %0, %0, %4;\n\t"
-        "@py add.rn.f32 %1, %1, %5;\n\t"
-        "@pz add.rn.f32 %2, %2, %6;\n\t"
-        "@px mad.lo.s32 %3, %7, %10, %3;\n\t"
-        "@py mad.lo.s32 %3, %8, %10, %3;\n\t"
-        "@pz mad.lo.s32 %3, %9, %10, %3;\n\t"
-        "}"
-        : "+f"(sx), "+f"(sy), "+f"(sz), "+r"(idx)
-        : "f"(dx), "f"(dy), "f"(dz), "r"(stx), "r"(sty), "r"(stz), "r"(one), "r"(i), "r"(n));
-}
-
 // Voxel-level DDA inside one 4^3 brick (brick_raytracer.comp:378-471) with the whole state in registers: the brick's 64-bit
 // mask, and ONE integer that carries both the voxel index and the bounds test —
 //   bits 0-11: (x+4) | (z+4) << 4 | (y+4) << 8   (a coordinate is inside [0,4) iff bit 2 of its field is set: 3 = -1 and 8 = 4
@@ -200,18 +177,6 @@ VRT_DI int brick_hit_warp4(const TraceParams& P, const Ray& r, bool ignore_test,
     return found;
 }
 
-#ifndef VRT_PREFETCH
-#define VRT_PREFETCH 0
-#endif
-#ifndef VRT_PREFETCH_K
-#define VRT_PREFETCH_K 3
-#endif
-#ifndef VRT_PARK_PREFETCH
-#define VRT_PARK_PREFETCH 0
-#endif
-#ifndef VRT_KSLACK
-#define VRT_KSLACK 0
-#endif
 #ifndef VRT_TMA_MASKS
 #define VRT_TMA_MASKS 0
 #endif
@@ -432,12 +397,6 @@ VRT_DI bool grid_hit_warp(const TraceParams& P, const Ray& r, bool active, bool 
     float fdx = marching ? dx : 0.0f, fdy = marching ? dy : 0.0f, fdz = marching ? dz : 0.0f;
     int fsx = stx, fsy = sty, fsz = stz;  // (stx.. are 0 when not marching)
 
-#if VRT_PREFETCH
-    bool near_rounds = false;  // warp-uniform: the previous round was at most VRT_PREFETCH_K steps long
-#if VRT_PREFETCH == 2
-    uint32_t pf_sink0, pf_sink1;
-#endif
-#endif
     while (__any_sync(kFullMask, mode != kDone)) {
         // ---- phase A (:313-373 without the per-cell tests): rounds of { every marching ray looks its cell up; all of
         // them take k = min over the warp of the distances found steps }.  k is warp-uniform, so the step loop has no
@@ -446,21 +405,7 @@ VRT_DI bool grid_hit_warp(const TraceParams& P, const Ray& r, bool active, bool 
         for (;;) {
             uint32_t d = kIdle;
             if (mode == kMarching) {
-                d = __ldg(dist + dist_addr((uint32_t)idx, P.dist_xhi_mask, P.dist_zlo_mask, P.dist_wx));
-#if VRT_PREFETCH
-                // Near a surface the rounds are one or two steps long and the next lookup lands on a neighbouring cell: the x
-                // neighbours share this cell's 128-byte line, the z / y neighbours are one row / one plane away.  Ask for those
-                // two lines now, so that the next round's lookup finds them in L1 instead of paying the L2 round trip.
-                if (near_rounds) {
-#if VRT_PREFETCH == 1
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(dist + idx + fsz));
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(dist + idx + fsy));
-#else
-                    asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(pf_sink0) : "l"(dist + idx + fsz));
-                    asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(pf_sink1) : "l"(dist + idx + fsy));
-#endif
-                }
-#endif
+                d = __ldg(dist + idx);
                 // bit 7: left the grid (border byte 255, :313-315), or — exact shortcut — no loaded brick exists anywhere in
                 // the octant this DDA can reach, so the shader's loop would only step through empty cells until it
                 // leaves the grid.  (COUNT keeps marching through free octants so that its step counters equal the shader's.)
@@ -474,13 +419,6 @@ VRT_DI bool grid_hit_warp(const TraceParams& P, const Ray& r, bool active, bool 
                     }
                 }
                 if (out || d == 0u) {  // d == 0: status bit set (:328) -> park for phase B
-#if VRT_PARK_PREFETCH
-                    if (BD == 4 && !out) {  // the brick's record is wanted in phase B, however many rounds away that is: ask L1 for it now
-                        const int pc = idx - obase;
-                        const int qx = (pc & ((1 << log_px) - 1)) - 1, qz = ((pc >> log_px) & ((1 << (log_pzx - log_px)) - 1)) - 1, qy = (pc >> log_pzx) - 1;
-                        asm volatile("prefetch.global.L1 [%0];" ::"l"(P.cell_rec + (uint32_t)(qx + (int)P.grid.dim_x * (qz + (int)P.grid.dim_z * qy))));
-                    }
-#endif
                     mode = out ? kDone : kParked;
                     d = kIdle;
                     fdx = fdy = fdz = 0.0f, fsx = fsy = fsz = 0;
@@ -491,30 +429,7 @@ VRT_DI bool grid_hit_warp(const TraceParams& P, const Ray& r, bool active, bool 
             VRT_STAT(0, 1u);                                           // rounds
             VRT_STAT(1, k);                                            // step-loop iterations
             VRT_STAT(4, (uint32_t)__popc(__ballot_sync(kFullMask, d != kIdle)));  // lanes marching in this round
-#if VRT_PREFETCH
-            near_rounds = k <= VRT_PREFETCH_K;
-#endif
             const bool on = d != kIdle;
-#if VRT_KSLACK
-            // Rounds with slack.  All lanes taking the warp MINIMUM of the distances keeps the step loop uniform, but one ray grazing a
-            // surface (d = 1) then drags the other 31 through a lookup per cell.  When the distances differ, every lane instead takes its
-            // OWN distance, capped at minimum + VRT_KSLACK: d - 1 blind steps under a lane predicate (11 instructions per step instead
-            // of 10) and the landing step together.  Fewer rounds — fewer lookups on the critical path of the tile — for a bounded
-            // number of iterations in which the short-distance lanes idle.
-            if (!COUNT) {
-                const uint32_t mine = on ? d : 0u;
-                const uint32_t kcap = min(__reduce_max_sync(kFullMask, mine), k + (uint32_t)VRT_KSLACK);
-                if (kcap > k) {
-                    const uint32_t n = min(mine, kcap);  // steps of this lane in this round; 0: parked / finished
-                    for (uint32_t i = 1; i < kcap; i++) march_step_if(i, n, sx, sy, sz, fdx, fdy, fdz, fsx, fsy, fsz, idx, one);
-                    if (on) t_side = fminf(fminf(sx, sy), sz);
-                    const int before = idx;
-                    march_step(sx, sy, sz, fdx, fdy, fdz, fsx, fsy, fsz, idx, one);
-                    if (on) last_stride = idx - before;
-                    continue;
-                }
-            }
-#endif
             if (COUNT) {
                 for (uint32_t i = 1; i < k; i++) {  // k-1 steps onto cells known to be empty and inside
                     march_step(sx, sy, sz, fdx, fdy, fdz, fsx, fsy, fsz, idx, one);
