@@ -431,6 +431,11 @@ def e2e_host_assembled(rig, ctx, cam, sun, W, H, steps, want_img):
     dist.barrier()
     if shm is None:
         shm = shared_memory.SharedMemory(name=name[0])
+        try:  # this process only attaches: keep its resource tracker from unlinking (and complaining about) rank 0's segment at exit
+            from multiprocessing import resource_tracker
+            resource_tracker.unregister(shm._name, "shared_memory")
+        except Exception:
+            pass
     frames = np.frombuffer(shm.buf, dtype=np.uint8, count=2 * fb)
     ptr = frames.ctypes.data
     rt = torch.cuda.cudart()

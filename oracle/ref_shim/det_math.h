@@ -76,11 +76,24 @@ inline float det_exp2f(float y) {
     p = __builtin_fmaf(p, r, 1.0f);
     return p * from_bits((uint32_t)(((int32_t)n + 127) << 23));
 }
-// pow(x, y) for x >= 0 (image.frag:29 clamps the base itself): pow(0, y) = 0, bases below FLT_MIN count as 0
+// x^n for a whole n >= 1 by binary exponentiation, lowest bit first: exact FP32 products in a fixed order
+inline float det_powif(float a, unsigned n) {
+    float r = 1.0f, p = a;
+    while (n) {
+        if (n & 1u) r = r * p;
+        n >>= 1;
+        if (n) p = p * p;
+    }
+    return r;
+}
+// pow(x, y) for x >= 0 (image.frag:29 clamps the base itself): pow(0, y) = 0, bases below FLT_MIN count as 0; a whole exponent
+// 1 <= y <= 64 (image.frag's literal 8, the default hue tolerance 20) is a chain of multiplications, as a shader compiler folds
+// pow(x, 8.) — more accurate than exp2(y * log2(x)) and well inside what GLSL lets a driver do
 inline float det_powf(float a, float b) {
     if (a != a) return a;
     if (a < 1.17549435e-38f) return 0.0f;
     if (a > 3.4028234e38f) return a;
+    if (b >= 1.0f && b <= 64.0f && b == __builtin_floorf(b)) return det_powif(a, (unsigned)b);
     return det_exp2f(b * det_log2f(a));
 }
 

@@ -20,7 +20,9 @@
  *   - pow(a, b) (after the shader's own `max(a, 0.)` macro, image.frag:29) = exp2(b * log2(a)) with the explicit
  *     det_log2f / det_exp2f below (atanh series / degree-6 polynomial, only + - * / fmaf and bit operations), so that x86
  *     and the GPU agree bit for bit; pow(0, b) = 0; arguments below FLT_MIN count as 0.  GLSL's pow precision is
- *     "inherited from exp2(x * log2(y))", which this is.
+ *     "inherited from exp2(x * log2(y))", which this is — except for whole exponents 1..64 (the shader's literal 8 and the default
+ *     inverse hue tolerance 20), which are a fixed chain of FP32 multiplications (binary exponentiation), the way a shader
+ *     compiler folds pow(x, 8.): more accurate, and a third of the instructions of the pass.
  *   - cos / sin(GOLDEN_ANGLE) are the correctly rounded FP32 constants; sqrt and / are IEEE; normalize, dot, length, max,
  *     abs as in vrt_oracle.cpp (normalize(0) = 0 * inf = NaN: a black texel poisons the weights, exactly as written upstream).
  *   - UNORM store as in the trace path: clamp to [0,1], (uint8_t)(c * 255 + 0.5), NaN stores 0.
@@ -78,11 +80,22 @@ inline float det_exp2f(float y) {
 }
 
 // image.frag:29  #define pow(a,b) pow(max(a,0.),b)
+// x^n for a whole n >= 1: binary exponentiation, lowest bit first (exact FP32 products in a fixed order)
+inline float det_powif(float a, unsigned n) {
+    float r = 1.0f, p = a;
+    while (n) {
+        if (n & 1u) r = r * p;
+        n >>= 1;
+        if (n) p = p * p;
+    }
+    return r;
+}
 inline float gpow(float a, float b) {
     a = gmax(a, 0.0f);
     if (a != a) return a;
     if (a < 1.17549435e-38f) return 0.0f;
     if (a > 3.4028234e38f) return a;  // +inf
+    if (b >= 1.0f && b <= 64.0f && b == floorf(b)) return det_powif(a, (unsigned)b);  // whole exponents: multiplication chain
     return det_exp2f(b * det_log2f(a));
 }
 

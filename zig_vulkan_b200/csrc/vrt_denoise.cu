@@ -61,11 +61,22 @@ __device__ __forceinline__ float det_exp2f(float y) {
 }
 
 // image.frag:29  #define pow(a,b) pow(max(a,0.),b)
+// x^n for a whole n >= 1: binary exponentiation, lowest bit first — the oracle's fixed order of exact FP32 products
+__device__ __forceinline__ float det_powif(float a, unsigned n) {
+    float r = 1.0f, p = a;
+    while (n) {
+        if (n & 1u) r = r * p;
+        n >>= 1;
+        if (n) p = p * p;
+    }
+    return r;
+}
 __device__ __forceinline__ float gpow(float a, float b) {
     a = dn_max(a, 0.0f);
     if (a != a) return a;
     if (a < 1.17549435e-38f) return 0.0f;
     if (a > 3.4028234e38f) return a;
+    if (b >= 1.0f && b <= 64.0f && b == floorf(b)) return det_powif(a, (unsigned)b);  // whole exponents (8, 20): a few multiplications instead of log2 + exp2
     return det_exp2f(b * det_log2f(a));
 }
 

@@ -40,9 +40,9 @@ cudaError_t launch_build_accel(const TraceParams& P, uint4* cell_rec, uint8_t* d
                                AccelDelta* delta, cudaStream_t stream, LaunchInfo* info);
 // Tiles (8x4 pixels) of the launch launch_trace_tuned would make for P with no schedule attached: the tile space an order for it permutes.
 uint32_t trace_tile_space(const TraceParams& P);
-// Tile schedule (vrt_sched.cu): order[i] = n - 1 - i and zeroed costs; stable sort of the tiles by cost, most expensive first.
+// Tile schedule (vrt_sched.cu): order[i] = n - 1 - i; stable sort of the tiles by cost, most expensive first.
 size_t sched_scratch_words(uint32_t n_tiles);
-cudaError_t launch_sched_init(uint32_t* order, uint16_t* cost0, uint16_t* cost1, uint32_t n_tiles, cudaStream_t stream, LaunchInfo* info);
+cudaError_t launch_sched_init(uint32_t* order, uint32_t n_tiles, cudaStream_t stream, LaunchInfo* info);
 cudaError_t launch_sched_sort(const uint16_t* cost, uint32_t n_tiles, uint32_t* order, uint32_t* scratch, cudaStream_t stream, LaunchInfo* info);
 // Explicit-ray mode: GridHit on caller-supplied rays (device pointers).
 cudaError_t launch_trace_rays(const TraceParams& P, const vrt_ray* rays, vrt_ray_hit* hits, size_t count, cudaStream_t stream, LaunchInfo* info);

@@ -33,12 +33,12 @@ __device__ __forceinline__ uint32_t cost_bin(uint32_t c) {
     return 255u - q;
 }
 
-__global__ void __launch_bounds__(256) sched_init_kernel(uint32_t* __restrict__ order, uint16_t* __restrict__ cost0, uint16_t* __restrict__ cost1, uint32_t n) {
+// The cost arrays are NOT touched here: with a dealt schedule a faster peer may already be writing this frame's costs into them
+// (its first frame does not wait for this rank's set-up), and every tile's cost is written before the first sort reads it anyway.
+__global__ void __launch_bounds__(256) sched_init_kernel(uint32_t* __restrict__ order, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     order[i] = n - 1u - i;  // bottom-up: ground rows first (vrt_kernels.cu)
-    if (cost0) cost0[i] = 0;
-    if (cost1) cost1[i] = 0;
 }
 
 // hist[bin * nblk + blk] = tiles of block blk in bin
@@ -134,9 +134,9 @@ __global__ void __launch_bounds__(kSortThreads) sched_scatter_kernel(const uint1
 
 size_t sched_scratch_words(uint32_t n_tiles) { return (size_t)kBins * ((n_tiles + kSortThreads - 1) / kSortThreads); }
 
-cudaError_t launch_sched_init(uint32_t* order, uint16_t* cost0, uint16_t* cost1, uint32_t n_tiles, cudaStream_t stream, LaunchInfo* info) {
+cudaError_t launch_sched_init(uint32_t* order, uint32_t n_tiles, cudaStream_t stream, LaunchInfo* info) {
     if (n_tiles == 0) return cudaSuccess;
-    sched_init_kernel<<<(n_tiles + 255) / 256, 256, 0, stream>>>(order, cost0, cost1, n_tiles);
+    sched_init_kernel<<<(n_tiles + 255) / 256, 256, 0, stream>>>(order, n_tiles);
     if (info) info->launches++;
     return cudaGetLastError();
 }

@@ -631,7 +631,7 @@ int trace_frame(vrt_ctx* ctx, const vrt_camera* camera, const vrt_sun* sun, bool
         Q.tile_order = nullptr;
         const uint32_t space = trace_tile_space(Q);
         if (space != ctx->sched_tiles) {
-            VRT_CUDA(ctx, launch_sched_init(ctx->d_order, ctx->d_cost[0], ctx->d_cost[1], space, ctx->stream, &info));
+            VRT_CUDA(ctx, launch_sched_init(ctx->d_order, space, ctx->stream, &info));
             ctx->sched_tiles = space, ctx->sched_frames = 0;
             P.tile_cost = ctx->d_cost[0];
             if (ctx->sched_mode == VRT_SCHED_DEAL && P.n_peers) {  // parity 0 again
