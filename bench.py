@@ -33,7 +33,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--workload", default="C3", choices=["C1", "C2", "C3", "C4", "C5"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--exchange", default="auto", choices=["auto", "allgather", "peer", "peerflags"],
+    ap.add_argument("--exchange", default="auto", choices=["auto", "allgather", "peer", "peerflags", "peerpush"],
                     help="N > 1: fused peer stores from the trace kernel (frame barrier = NCCL 4-byte all-reduce, or peer flag words: "
                          "peerflags), or an NCCL all-gather after it; auto = every combination of exchange and schedule is timed for a few "
                          "frames on this box and the fastest one runs the timed region")
@@ -267,7 +267,8 @@ class Rig:
         from zig_vulkan_b200 import ffi
 
         if self.world > 1:
-            ctx.comm_set_exchange({"allgather": ffi.VRT_EXCHANGE_ALLGATHER, "peer": ffi.VRT_EXCHANGE_PEER_STORE, "peerflags": ffi.VRT_EXCHANGE_PEER_FLAGS}[exchange])
+            ctx.comm_set_exchange({"allgather": ffi.VRT_EXCHANGE_ALLGATHER, "peer": ffi.VRT_EXCHANGE_PEER_STORE, "peerflags": ffi.VRT_EXCHANGE_PEER_FLAGS,
+                                   "peerpush": ffi.VRT_EXCHANGE_PEER_PUSH}[exchange])
         ctx.set_schedule({"static": ffi.VRT_SCHED_STATIC, "lpt": ffi.VRT_SCHED_LPT, "deal": ffi.VRT_SCHED_DEAL}[schedule], interval)
 
     def choose_mode(self, ctx, cam, sun):
@@ -275,7 +276,7 @@ class Rig:
         args = self.args
         if args.baseline_kernel:
             return ("allgather" if self.world > 1 else "none", "static"), {}
-        exchanges = (["allgather", "peerflags", "peer"] if args.exchange == "auto" else [args.exchange]) if self.world > 1 else ["none"]
+        exchanges = (["allgather", "peerflags", "peerpush"] if args.exchange == "auto" else [args.exchange]) if self.world > 1 else ["none"]
         cands = []
         for ex in exchanges:
             for sc in (["static", "lpt", "deal"] if args.schedule == "auto" else [args.schedule]):

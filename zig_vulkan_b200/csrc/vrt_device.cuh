@@ -275,6 +275,7 @@ struct TraceParams {
     uint32_t order_offset, order_stride;
     uint16_t* tile_cost;
     uint16_t* peer_cost[8];
+    uint32_t n_cost_peers;  // entries of peer_cost in use (dealt schedules across GPUs)
     uint32_t vec_store_ok;                // framebuffer rows are 16-B aligned -> 128-bit stores
     // fused peer-store exchange (multi-GPU): framebuffers of every rank, this rank included
     uint32_t* peer_fb[8];

@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(kTunedThreads, SIMPLE ? VRT_TUNED_BLOCKS : VRT
             const long long ticks = (clock64() - tick0) >> 5;
             const uint16_t c = (uint16_t)(ticks > 65535ll ? 65535ll : (ticks < 1ll ? 1ll : ticks));
             if (lane == 0) P.tile_cost[tile] = c;
-            if (lane < P.n_peers && P.peer_cost[lane]) P.peer_cost[lane][tile] = c;
+            if (lane < P.n_cost_peers) P.peer_cost[lane][tile] = c;
         }
     }
     leave_queue(P, lane);
@@ -146,6 +146,42 @@ cudaError_t launch_warp_kernel(const TraceParams& P, int num_sms, cudaStream_t s
     const uint32_t needed = (tiles_total + warps_per_block - 1) / warps_per_block;
     if (grid > needed) grid = needed;
     trace_warp_kernel<BD, AOV, SIMPLE><<<grid, kTunedThreads, 0, stream>>>(P, tiles_x, tiles_total);
+    if (info) info->launches++;
+    return cudaGetLastError();
+}
+
+// The exchange of VRT_EXCHANGE_PEER_PUSH: after the trace kernel, copy this rank's tiles from its own framebuffer (L2-hot) into the
+// same place of every peer's framebuffer.  Same tile enumeration as the trace kernel (ticket -> tile -> pixels); a warp moves four
+// tiles per trip — lane = (tile of the four, row of the tile, left / right half) -> one 128-bit load and one 128-bit store per peer.
+// Against storing from inside the trace kernel this keeps the NVLink traffic out of the march's instruction stream.
+__global__ void __launch_bounds__(256) push_tiles_kernel(const __grid_constant__ TraceParams P, const uint32_t tiles_x, const uint32_t tiles_total) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t sub = lane >> 3, row = (lane >> 1) & 3u, half = lane & 1u;
+    const uint32_t width = P.cam.image_width;
+    for (uint32_t t0 = warp * 4u; t0 < tiles_total; t0 += n_warps * 4u) {
+        const uint32_t t = t0 + sub;
+        if (t >= tiles_total) continue;
+        const uint32_t tile = P.tile_order ? __ldg(P.tile_order + P.order_offset + t * P.order_stride) : tiles_total - 1u - t;
+        const uint32_t px = (tile % tiles_x) * kTileW + half * 4u;
+        const uint32_t strip = tile / tiles_x;
+        const uint32_t py = (P.il_world ? (strip * P.il_world + P.il_rank) * kTileH : P.row_begin + strip * kTileH) + row;
+        if (px + 3u >= width || py >= P.row_end) continue;  // (width % 4 == 0 is a precondition of this mode)
+        const size_t at = (size_t)py * width + px;
+        const uint4 v = *reinterpret_cast<const uint4*>(P.fb + at);
+        for (uint32_t p = 0; p < P.n_peers; p++) *reinterpret_cast<uint4*>(P.peer_fb[p] + at) = v;
+    }
+}
+
+cudaError_t launch_push_tiles(const TraceParams& P, cudaStream_t stream, LaunchInfo* info) {
+    const uint32_t tiles_x = (P.cam.image_width + kTileW - 1) / kTileW;
+    uint32_t tiles_total = trace_tile_space(P);
+    if (P.tile_order && P.order_stride > 1u) tiles_total = P.order_offset < tiles_total ? (tiles_total - P.order_offset + P.order_stride - 1u) / P.order_stride : 0u;
+    if (tiles_total == 0 || P.n_peers == 0) return cudaSuccess;
+    const uint32_t warps = (tiles_total + 3u) / 4u;
+    uint32_t blocks = (warps + 7u) / 8u;
+    if (blocks > 148u * 4u) blocks = 148u * 4u;
+    push_tiles_kernel<<<blocks, 256, 0, stream>>>(P, tiles_x, tiles_total);
     if (info) info->launches++;
     return cudaGetLastError();
 }

@@ -53,6 +53,8 @@ cudaError_t launch_deinterleave(const uint32_t* gathered, uint32_t* frame, uint3
 // decoded: width * height float4 of scratch (the UNORM-decoded image).
 cudaError_t launch_denoise(const uint32_t* image, float4* decoded, uint32_t width, uint32_t height, const vrt_denoise_params& params, uint32_t* out,
                            uint32_t out_width, uint32_t out_height, bool bgra, cudaStream_t stream, LaunchInfo* info);
+// VRT_EXCHANGE_PEER_PUSH: copy the tiles P describes (as the trace launch would enumerate them) from P.fb into every P.peer_fb.
+cudaError_t launch_push_tiles(const TraceParams& P, cudaStream_t stream, LaunchInfo* info);
 // Frame barrier over peer-mapped flag words (fused peer-store exchange, VRT_EXCHANGE_PEER_FLAGS); see vrt_kernels.cu.
 cudaError_t launch_peer_barrier(uint32_t* const flags[8], uint32_t rank, uint32_t world, uint32_t frame, int* error, cudaStream_t stream, LaunchInfo* info);
 // BrickGrid.insert for a batch of voxels on the device (vrt_build.cu): `prepare` only reads the grid buffers (first occurrences,

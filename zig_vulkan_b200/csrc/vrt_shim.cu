@@ -288,7 +288,7 @@ void fill_params(const vrt_ctx* c, const vrt_camera* cam, const vrt_sun* sun, Tr
     P.vec_store_ok = (cam->image_width % 4 == 0) && ((reinterpret_cast<uintptr_t>(c->d_fb) & 15u) == 0);
     P.n_peers = 0;
     P.one = 1u;
-    if (c->world > 1 && (c->exchange_mode == VRT_EXCHANGE_PEER_STORE || c->exchange_mode == VRT_EXCHANGE_PEER_FLAGS) && c->peers_open) {
+    if (c->world > 1 && (c->exchange_mode == VRT_EXCHANGE_PEER_STORE || c->exchange_mode == VRT_EXCHANGE_PEER_FLAGS || c->exchange_mode == VRT_EXCHANGE_PEER_PUSH) && c->peers_open) {
         const size_t slot_words = (c->d_fb == c->d_fb_ring1) ? c->fb_bytes / 4 : 0;  // same ring slot on every rank
         for (int r = 0; r < c->world; r++)
             if (r != c->rank) P.peer_fb[P.n_peers++] = static_cast<uint32_t*>(c->peer_fb[r]) + slot_words;
@@ -304,9 +304,8 @@ void fill_params(const vrt_ctx* c, const vrt_camera* cam, const vrt_sun* sun, Tr
             P.il_world = 0u, P.il_gather = 0u;
             P.row_begin = 0u, P.row_end = c->cfg.height;
             const size_t cost_off = 2 * c->fb_bytes + kPeerFlagBytes + (size_t)parity * cost_bytes(c);
-            uint32_t p = 0;
             for (int r = 0; r < c->world && P.n_peers; r++)
-                if (r != c->rank) P.peer_cost[p++] = reinterpret_cast<uint16_t*>(static_cast<uint8_t*>(c->peer_fb[r]) + cost_off);
+                if (r != c->rank) P.peer_cost[P.n_cost_peers++] = reinterpret_cast<uint16_t*>(static_cast<uint8_t*>(c->peer_fb[r]) + cost_off);
         }
     }
 }
@@ -549,7 +548,8 @@ int vrt_upload_material_indices(vrt_ctx* ctx, size_t offset, const uint8_t* data
 namespace {
 
 bool peer_mode(const vrt_ctx* c) {
-    return c->world > 1 && c->peers_open && (c->exchange_mode == VRT_EXCHANGE_PEER_STORE || c->exchange_mode == VRT_EXCHANGE_PEER_FLAGS);
+    return c->world > 1 && c->peers_open &&
+           (c->exchange_mode == VRT_EXCHANGE_PEER_STORE || c->exchange_mode == VRT_EXCHANGE_PEER_FLAGS || c->exchange_mode == VRT_EXCHANGE_PEER_PUSH);
 }
 bool owns_fb(const vrt_ctx* c) { return c->d_fb == c->d_fb_own || c->d_fb == c->d_fb_ring1; }
 
@@ -583,7 +583,8 @@ int trace_frame(vrt_ctx* ctx, const vrt_camera* camera, const vrt_sun* sun, bool
                     ctx->cfg.width, ctx->cfg.height);
     if (camera->samples_per_pixel < 1) return fail(ctx, VRT_E_INVALID, "vrt_trace: samples_per_pixel < 1");
     const bool gather = ctx->world > 1 && ctx->exchange_mode == VRT_EXCHANGE_ALLGATHER;
-    if (ctx->world > 1 && !ctx->comm && ctx->exchange_mode != VRT_EXCHANGE_PEER_FLAGS && ctx->exchange_mode != VRT_EXCHANGE_HOST)  // neither needs a communicator
+    if (ctx->world > 1 && !ctx->comm && ctx->exchange_mode != VRT_EXCHANGE_PEER_FLAGS && ctx->exchange_mode != VRT_EXCHANGE_PEER_PUSH &&
+        ctx->exchange_mode != VRT_EXCHANGE_HOST)  // none of these needs a communicator
         return fail(ctx, VRT_E_STATE, "vrt_trace: world > 1 but vrt_comm_init has not been called");
     if (ctx->sched_mode == VRT_SCHED_DEAL && ctx->world > 1 && !peer_mode(ctx))
         return fail(ctx, VRT_E_STATE, "vrt_trace: VRT_SCHED_DEAL scatters a rank's tiles over the image and needs a peer-store exchange mode");
@@ -642,8 +643,16 @@ int trace_frame(vrt_ctx* ctx, const vrt_camera* camera, const vrt_sun* sun, bool
             }
         }
     }
-    VRT_CUDA(ctx, launch_trace(P, which, aov, ctx->stream, &info));
+    const bool push = peer_mode(ctx) && ctx->exchange_mode == VRT_EXCHANGE_PEER_PUSH && P.vec_store_ok && which == KERNEL_TUNED && !aov;
+    if (push) {  // the trace kernel keeps its pixels local (the costs of a dealt schedule still go to the peers); a copy kernel ships them afterwards
+        TraceParams Q = P;
+        Q.n_peers = 0u;
+        VRT_CUDA(ctx, launch_trace(Q, which, aov, ctx->stream, &info));
+    } else {
+        VRT_CUDA(ctx, launch_trace(P, which, aov, ctx->stream, &info));
+    }
     VRT_CUDA(ctx, cudaEventRecord(ctx->ev_kernel_end, ctx->stream));
+    if (push) VRT_CUDA(ctx, launch_push_tiles(P, ctx->stream, &info));
 
     if (gather) {
         // in place: the kernel already wrote this rank's pixels at their offset in the gathered buffer
@@ -665,7 +674,7 @@ int trace_frame(vrt_ctx* ctx, const vrt_camera* camera, const vrt_sun* sun, bool
         // barrier also waits until this rank has copied that slot's previous frame to its host (pipelined frames).
         const int other = (int)((ctx->ring_seq + 1u) & 1u);
         if (ring && ctx->slot_used[other]) VRT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[other], 0));
-        if (ctx->exchange_mode == VRT_EXCHANGE_PEER_FLAGS) {
+        if (ctx->exchange_mode == VRT_EXCHANGE_PEER_FLAGS || ctx->exchange_mode == VRT_EXCHANGE_PEER_PUSH) {
             uint32_t* flags[8] = {nullptr};
             for (int r = 0; r < ctx->world; r++) flags[r] = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(ctx->peer_fb[r]) + 2 * ctx->fb_bytes);
             VRT_CUDA(ctx, launch_peer_barrier(flags, (uint32_t)ctx->rank, (uint32_t)ctx->world, ++ctx->barrier_frame, ctx->h_barrier_error, ctx->stream, &info));
@@ -1218,17 +1227,16 @@ int vrt_comm_open_peers(vrt_ctx* ctx, int rank, int world, const uint8_t* handle
 
 int vrt_comm_set_exchange(vrt_ctx* ctx, uint32_t mode) {
     if (!ctx) return VRT_E_INVALID;
-    if (mode != VRT_EXCHANGE_ALLGATHER && mode != VRT_EXCHANGE_PEER_STORE && mode != VRT_EXCHANGE_PEER_FLAGS && mode != VRT_EXCHANGE_HOST)
-        return fail(ctx, VRT_E_INVALID, "vrt_comm_set_exchange: unknown mode %u", mode);
-    if ((mode == VRT_EXCHANGE_PEER_STORE || mode == VRT_EXCHANGE_PEER_FLAGS) && !ctx->peers_open)
+    if (mode > VRT_EXCHANGE_PEER_PUSH) return fail(ctx, VRT_E_INVALID, "vrt_comm_set_exchange: unknown mode %u", mode);
+    if ((mode == VRT_EXCHANGE_PEER_STORE || mode == VRT_EXCHANGE_PEER_FLAGS || mode == VRT_EXCHANGE_PEER_PUSH) && !ctx->peers_open)
         return fail(ctx, VRT_E_STATE, "vrt_comm_set_exchange: call vrt_comm_open_peers first");
-    if (mode == VRT_EXCHANGE_PEER_FLAGS && !ctx->h_barrier_error) {
+    if ((mode == VRT_EXCHANGE_PEER_FLAGS || mode == VRT_EXCHANGE_PEER_PUSH) && !ctx->h_barrier_error) {
         VRT_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
         VRT_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_barrier_error), sizeof(int), cudaHostAllocMapped));
         *ctx->h_barrier_error = 0;
     }
     ctx->exchange_mode = mode;
-    if (mode == VRT_EXCHANGE_PEER_FLAGS && ctx->world > 1) {
+    if ((mode == VRT_EXCHANGE_PEER_FLAGS || mode == VRT_EXCHANGE_PEER_PUSH) && ctx->world > 1) {
         // one round of the flag barrier now (every rank makes this call): the first touch of each peer mapping happens here, and
         // all ranks leave set-up together
         uint32_t* flags[8] = {nullptr};
