@@ -257,14 +257,6 @@ int vrt_last_trace_launches(vrt_ctx* ctx, uint32_t* out);
 #define VRT_SCHED_LPT 1u
 #define VRT_SCHED_DEAL 2u
 int vrt_set_schedule(vrt_ctx* ctx, uint32_t mode, uint32_t interval /* frames between sorts; 0 = 8 */);
-/* Placement of the derived distance planes in memory (extension; the images are identical).  LINEAR: 128 consecutive x cells per
- * 128-byte line — the cheapest lookups, best when the GPU is full (one GPU on a frame).  BLOCKED: an 8 x 4 x 4 block of cells per
- * line for ten more instructions per lookup — a ray's consecutive lookups mostly hit L1, which shortens the dependent chain of the
- * most expensive tiles: best when a GPU holds a fraction of a frame and its launch is as long as its slowest tile.  Takes effect
- * (with a rebuild of the planes) at the next trace.  Call it after vrt_upload_grid_state. */
-#define VRT_DIST_LAYOUT_LINEAR 0u
-#define VRT_DIST_LAYOUT_BLOCKED 1u
-int vrt_set_dist_layout(vrt_ctx* ctx, uint32_t layout);
 /* Debug / tests: read the per-tile costs of the last frame (clock ticks / 32, 0 = never traced), or install costs and sort them
  * into the order right away.  count <= tiles of the image = ceil(width/8) * ceil(height/4). */
 int vrt_sched_get_costs(vrt_ctx* ctx, uint16_t* costs_host, size_t count);

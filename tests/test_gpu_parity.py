@@ -400,57 +400,6 @@ def test_tile_schedules_trace_the_same_frame(materials):
             assert np.array_equal(total.astype(np.uint8), ref_img)
 
 
-def test_blocked_distance_layout_renders_the_same(materials):
-    """vrt_set_dist_layout(BLOCKED) moves the distance bytes (8 x 4 x 4 cells per line), never a result: frames, hit records and
-    the request counters of the counting variant stay those of the oracle; switching back and forth rebuilds the planes; edits
-    patch them in either layout."""
-    for n, bd, dims in [(64, 4, None), (128, 8, None), (None, 4, (40, 12, 24))]:
-        if dims is None:
-            grid = scenes.build_grid(n, brick_dim=bd)
-        else:
-            grid = ffi.Grid(dims, brick_dim=bd, min_point=(-20.0, -6.0, -12.0), scale=1.0)
-            assert grid.fill_synthetic(scenes.SEED) == 0
-        cam = scenes.camera(203, 90, origin=(0.0, -10.0, 28.0) if dims is None else (0.0, -4.0, 10.0), euler_deg=(25.0, 0.0, 0.0))
-        sun = scenes.sun(True)
-        ref_img, ref_aov, ref_cnt = orc.OracleScene.from_grid(grid, materials).render(cam, sun, aov=True)
-        for flags in (0, ffi.VRT_FLAG_AOV):
-            ctx = ffi.Context(203, 90, len(grid.brick_indices), brick_dim=bd, flags=flags)
-            ctx.upload_grid(grid, materials)
-            for blocked in (True, False, True):
-                ctx.set_dist_layout(blocked)
-                ctx.trace(cam, sun)
-                assert np.array_equal(ctx.read_framebuffer(), ref_img), (n, bd, dims, flags, blocked)
-                if flags:
-                    aov = ctx.read_aov()
-                    for f in EXACT:
-                        assert np.array_equal(aov[f], ref_aov[f]), f
-                    assert np.array_equal(aov["t"].view(np.uint32), ref_aov["t"].view(np.uint32))
-                    c = ctx.counters()
-                    assert c["rays"] == ref_cnt["rays"] and c["grid_steps"] == ref_cnt["grid_steps"] and c["hits"] == ref_cnt["hits"]
-            ctx.close()
-    # edits with the blocked layout: patched planes == rebuilt planes, frame == oracle
-    grid = scenes.build_grid(64)
-    cam, sun = scenes.camera(160, 90, **POSE0), scenes.sun(True)
-    ctx = ffi.Context(160, 90, len(grid.brick_indices))
-    ctx.upload_grid(grid, materials)
-    ctx.set_dist_layout(True)
-    for which in range(5):
-        grid.delta_reset(which)
-    ctx.trace(cam, sun)
-    rng = np.random.default_rng(9)
-    for _ in range(4):
-        for _ in range(3):
-            x, y, z = (int(v) for v in rng.integers(0, 64, 3))
-            grid.insert(x, y, z, 5)
-        ctx.upload_grid_delta(grid)
-        img = ctx.trace_to_host(cam, sun)
-        patched = ctx.debug_dist_planes().copy()
-        ctx.debug_force_accel_rebuild()
-        assert np.array_equal(patched, ctx.debug_dist_planes())
-        assert np.array_equal(img, orc.OracleScene.from_grid(grid, materials).render(cam, sun)[0])
-    ctx.close()
-
-
 def test_host_assembled_frame_from_strips(materials):
     """VRT_EXCHANGE_HOST: every part copies exactly its own 4-row strips (ragged last strip included) into its place of one host
     frame; the parts of all ranks put together are the oracle's frame.  Needs no communicator: one GPU plays every rank in turn."""

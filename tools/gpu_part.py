@@ -8,7 +8,6 @@ import zig_vulkan_b200 as zv
 from zig_vulkan_b200 import ffi, scenes
 POSE0 = dict(origin=(0.0, -10.0, 28.0), euler_deg=(25.0, 0.0, 0.0))
 wl = scenes.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "C3"]
-BLOCKED = "--blocked" in sys.argv
 grid = scenes.build_grid(wl.n_voxels, wl.brick_dim)
 mats = zv.terrain_materials()
 cam = scenes.camera(wl.width, wl.height, **POSE0)
@@ -24,7 +23,6 @@ def best(ctx, n=14, skip=4):
 
 full = ffi.Context(wl.width, wl.height, len(grid.brick_indices))
 full.upload_grid(grid, mats)
-full.set_dist_layout(BLOCKED)
 t_static = best(full)
 full.set_schedule(ffi.VRT_SCHED_LPT, 2)
 t_lpt = best(full)
@@ -37,7 +35,6 @@ for world in (2, 4, 8):
     for r in range(world):
         ctx = ffi.Context(wl.width, wl.height, len(grid.brick_indices), part=(r, world))
         ctx.upload_grid(grid, mats)
-        ctx.set_dist_layout(BLOCKED)
         res["static"].append(best(ctx))
         ctx.set_schedule(ffi.VRT_SCHED_LPT, 2)
         res["lpt"].append(best(ctx))

@@ -231,15 +231,6 @@ VRT_DI uint32_t unorm8(float c) {
 }
 VRT_DI uint32_t pack_rgba8(V3 c) { return unorm8(c.x) | (unorm8(c.y) << 8) | (unorm8(c.z) << 16) | 0xff000000u; }
 
-// Byte address of padded cell index `idx` inside its distance plane.  The march keeps the linear index (one add per step,
-// decodable with shifts); with the blocked layout the bit fields are rearranged once per lookup:
-//   idx  = [ y_hi | y_lo(2) | z_hi | z_lo(2) | x_hi | x_lo(3) ]  ->  [ y_hi | z_hi | x_hi | y_lo | z_lo | x_lo ]
-__host__ __device__ __forceinline__ uint32_t dist_addr(uint32_t idx, uint32_t m_zlo, uint32_t m_ylo, uint32_t m_xhi, uint32_t m_zhi, uint32_t s_zlo, uint32_t s_ylo) {
-    const uint32_t moved = m_zlo | m_ylo | m_xhi | m_zhi;
-    return (idx & ~moved) | ((idx & m_zlo) >> s_zlo) | ((idx & m_ylo) >> s_ylo) | ((idx & m_xhi) << 4) | ((idx & m_zhi) << 2);
-}
-#define VRT_DIST_ADDR(P, idx) dist_addr((uint32_t)(idx), (P).dist_m_zlo, (P).dist_m_ylo, (P).dist_m_xhi, (P).dist_m_zhi, (P).dist_s_zlo, (P).dist_s_ylo)
-
 // Everything a trace kernel needs, passed by value as a __grid_constant__ (lands in the constant bank, the
 // CUDA analogue of the reference's push constants + UBO + descriptor set).
 struct TraceParams {
@@ -271,9 +262,6 @@ struct TraceParams {
     const uint8_t* dist;                  // 8 padded directional Chebyshev distance grids (one per octant), see vrt_trav_warp.cuh
     unsigned long long dist_plane;        // bytes per octant
     uint32_t dist_log_px, dist_log_pz;    // row / plane strides of `dist` are powers of two: x + (z << log_px) + (y << (log_px+log_pz))
-    // Optional 3D-blocked placement of that index space in memory (dist_addr below): a 128-byte line holds an 8 x 4 x 4 (x, z, y) block
-    // of cells instead of 128 cells of one row.  All masks zero: the linear layout.
-    uint32_t dist_m_zlo, dist_m_ylo, dist_m_xhi, dist_m_zhi, dist_s_zlo, dist_s_ylo;
     uint32_t scale_pow2, voxel_scale_pow2;  // brick / voxel scale is a power of two -> divide by multiplying with the exact inverse
     float inv_scale, inv_voxel_scale;
     // persistent-kernel work queue: counter[0] = next ticket, counter[1] = warps that have left the queue; the last warp to

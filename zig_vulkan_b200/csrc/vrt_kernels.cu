@@ -324,8 +324,7 @@ __global__ void __launch_bounds__(128) dist_scan_kernel(const __grid_constant__ 
         const uint32_t byte = d | fr;
         if (axis == 2) {
             const uint32_t x = (uint32_t)(g % dim_x), z = (uint32_t)((g / dim_x) % dim_z);
-            const uint32_t cell = (x + 1u) + ((z + 1u) << P.dist_log_px) + ((uint32_t)(c + 1) << (P.dist_log_px + P.dist_log_pz));
-            out[(size_t)v * P.dist_plane + VRT_DIST_ADDR(P, cell)] = (uint8_t)byte;
+            out[(size_t)v * P.dist_plane + (size_t)(x + 1) + ((size_t)(z + 1) << P.dist_log_px) + ((size_t)(c + 1) << (P.dist_log_px + P.dist_log_pz))] = (uint8_t)byte;
         } else {
             out[(size_t)v * n_bricks + g] = (uint8_t)byte;
         }
@@ -392,7 +391,7 @@ __global__ void __launch_bounds__(256) dist_patch_kernel(const __grid_constant__
     }
     if (best == 0xffffu) return;
     const uint32_t padded = (uint32_t)(px + 1) + ((uint32_t)(pz + 1) << P.dist_log_px) + ((uint32_t)(py + 1) << (P.dist_log_px + P.dist_log_pz));
-    uint8_t* at = dist + (size_t)o * P.dist_plane + VRT_DIST_ADDR(P, padded);
+    uint8_t* at = dist + (size_t)o * P.dist_plane + padded;
     const uint32_t cur = *at;
     const uint32_t d = min(min(cur & 0x7fu, best), kDistCap);
     if (d != cur) *at = (uint8_t)d;  // free bit cleared

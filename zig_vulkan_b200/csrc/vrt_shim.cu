@@ -127,8 +127,7 @@ struct vrt_ctx {
     uint32_t accel_dim[3] = {0, 0, 0};
     bool accel_dirty = true;   // status words were uploaded: the distance planes MAY be stale (d_accel_delta knows)
     bool occ_dirty = true;     // brick indices / occupancy bytes changed: the per-cell records are stale, the distance planes are not
-    bool accel_force = true;   // the distance planes must be rebuilt from scratch (new grid, device-side insert, layout change)
-    bool dist_blocked = false; // 3D-blocked placement of the distance planes (vrt_set_dist_layout)
+    bool accel_force = true;   // the distance planes must be rebuilt from scratch (new grid, device-side insert)
     AccelDelta* d_accel_delta = nullptr;  // which status bits the uploads since the last build changed
     uint32_t* d_status_stage = nullptr;   // uploaded status words land here; status_merge_kernel compares them with the live ones
 
@@ -279,13 +278,6 @@ void fill_params(const vrt_ctx* c, const vrt_camera* cam, const vrt_sun* sun, Tr
     P.dist = c->d_dist;
     P.dist_plane = c->dist_plane;
     P.dist_log_px = c->dist_log_px, P.dist_log_pz = c->dist_log_pz;
-    if (c->dist_blocked) {  // [y_hi | y_lo(2) | z_hi | z_lo(2) | x_hi | x_lo(3)] -> [y_hi | z_hi | x_hi | y_lo | z_lo | x_lo]
-        const uint32_t lx = c->dist_log_px, lz = c->dist_log_pz;
-        P.dist_m_zlo = 3u << lx, P.dist_s_zlo = lx - 3u;
-        P.dist_m_ylo = 3u << (lx + lz), P.dist_s_ylo = lx + lz - 5u;
-        P.dist_m_xhi = ((1u << (lx - 3u)) - 1u) << 3;
-        P.dist_m_zhi = ((1u << (lz - 2u)) - 1u) << (lx + 2u);
-    }
     const float scale = c->grid.max_point_scale[3];
     const float voxel_scale = scale * P.brick_voxel_scale;  // :389, same f32 product the kernels form
     P.scale_pow2 = is_pow2(scale) ? 1u : 0u;
@@ -917,16 +909,6 @@ int vrt_debug_tile_stats(vrt_ctx* ctx, uint32_t* host, size_t tiles) {
     }
     VRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     VRT_CUDA(ctx, cudaMemcpy(host, d_stats, tiles * 32, cudaMemcpyDeviceToHost));
-    return VRT_OK;
-}
-
-int vrt_set_dist_layout(vrt_ctx* ctx, uint32_t layout) {
-    if (!ctx) return VRT_E_INVALID;
-    if (layout > VRT_DIST_LAYOUT_BLOCKED) return fail(ctx, VRT_E_INVALID, "vrt_set_dist_layout: unknown layout %u", layout);
-    bool want = layout == VRT_DIST_LAYOUT_BLOCKED;
-    if (want && ctx->have_grid && (ctx->dist_log_px < 4 || ctx->dist_log_pz < 3)) want = false;  // grids too small to have the fields to swap
-    if (want != ctx->dist_blocked) ctx->accel_dirty = ctx->accel_force = true;  // same bytes, other places: rebuild before the next trace
-    ctx->dist_blocked = want;
     return VRT_OK;
 }
 

@@ -385,7 +385,6 @@ VRT_DI bool grid_hit_warp(const TraceParams& P, const Ray& r, bool active, bool 
     const int obase = (int)(((ray_step.x < 0 ? 1u : 0u) | (ray_step.y < 0 ? 2u : 0u) | (ray_step.z < 0 ? 4u : 0u)) * (uint32_t)P.dist_plane);
     idx += obase;
     const uint8_t* __restrict__ dist = P.dist;
-    const bool blocked = P.dist_m_xhi != 0u;
     const int one = (int)P.one;
     int last_stride = 0;  // stride of the most recent step (0: none yet -> slab normal)
     bool result = false;
@@ -406,9 +405,7 @@ VRT_DI bool grid_hit_warp(const TraceParams& P, const Ray& r, bool active, bool 
         for (;;) {
             uint32_t d = kIdle;
             if (mode == kMarching) {
-                uint32_t at = (uint32_t)idx;
-                if (blocked) at = VRT_DIST_ADDR(P, idx);  // warp-uniform: the blocked layout's field swap, only when it is in use
-                d = __ldg(dist + at);
+                d = __ldg(dist + idx);
                 // bit 7: left the grid (border byte 255, :313-315), or — exact shortcut — no loaded brick exists anywhere in
                 // the octant this DDA can reach, so the shader's loop would only step through empty cells until it
                 // leaves the grid.  (COUNT keeps marching through free octants so that its step counters equal the shader's.)

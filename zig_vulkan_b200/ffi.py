@@ -172,7 +172,6 @@ VRT_SYMBOLS = {
     "vrt_debug_force_accel_rebuild": (C.c_int, [_P]),
     "vrt_debug_tile_stats": (C.c_int, [_P, _P, _SZ]),
     "vrt_set_schedule": (C.c_int, [_P, C.c_uint32, C.c_uint32]),
-    "vrt_set_dist_layout": (C.c_int, [_P, C.c_uint32]),
     "vrt_sched_get_costs": (C.c_int, [_P, _P, _SZ]),
     "vrt_sched_set_costs": (C.c_int, [_P, _P, _SZ]),
     "vrt_set_stream": (C.c_int, [_P, _P]),
@@ -781,9 +780,6 @@ class Context:
         ms = C.c_float()
         self._check(self._l.vrt_last_trace_kernel_ms(self.handle, C.byref(ms)))
         return ms.value
-
-    def set_dist_layout(self, blocked: bool):
-        self._check(self._l.vrt_set_dist_layout(self.handle, 1 if blocked else 0))
 
     def set_schedule(self, mode: int, interval: int = 0):
         self._check(self._l.vrt_set_schedule(self.handle, mode, interval))
