@@ -37,7 +37,7 @@ def parse_args():
                     help="N > 1: fused peer stores from the trace kernel (frame barrier = NCCL 4-byte all-reduce, or peer flag words: "
                          "peerflags), or an NCCL all-gather after it; auto = every combination of exchange and schedule is timed for a few "
                          "frames on this box and the fastest one runs the timed region")
-    ap.add_argument("--schedule", default="auto", choices=["auto", "static", "lpt", "deal"],
+    ap.add_argument("--schedule", default="auto", choices=["auto", "static", "lpt", "deal", "shared"],
                     help="tile order: static bottom-up, cost-sorted (longest first), or cost-sorted and dealt across the ranks (peer exchange modes)")
     ap.add_argument("--partition", default="interleave", choices=["interleave", "slab"], help="N > 1: 4-row strips round-robin, or one row slab per rank")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -269,19 +269,19 @@ class Rig:
         if self.world > 1:
             ctx.comm_set_exchange({"allgather": ffi.VRT_EXCHANGE_ALLGATHER, "peer": ffi.VRT_EXCHANGE_PEER_STORE, "peerflags": ffi.VRT_EXCHANGE_PEER_FLAGS,
                                    "peerpush": ffi.VRT_EXCHANGE_PEER_PUSH}[exchange])
-        ctx.set_schedule({"static": ffi.VRT_SCHED_STATIC, "lpt": ffi.VRT_SCHED_LPT, "deal": ffi.VRT_SCHED_DEAL}[schedule], interval)
+        ctx.set_schedule({"static": ffi.VRT_SCHED_STATIC, "lpt": ffi.VRT_SCHED_LPT, "deal": ffi.VRT_SCHED_DEAL, "shared": ffi.VRT_SCHED_SHARED}[schedule], interval)
 
     def choose_mode(self, ctx, cam, sun):
         """Exchange x schedule by measurement on this box: each candidate runs 4 + 12 flushed frames, the smallest max-over-ranks mean wins."""
         args = self.args
         if args.baseline_kernel:
             return ("allgather" if self.world > 1 else "none", "static"), {}
-        exchanges = (["allgather", "peerflags", "peerpush"] if args.exchange == "auto" else [args.exchange]) if self.world > 1 else ["none"]
+        exchanges = (["allgather", "peerflags"] if args.exchange == "auto" else [args.exchange]) if self.world > 1 else ["none"]
         cands = []
         for ex in exchanges:
-            for sc in (["static", "lpt", "deal"] if args.schedule == "auto" else [args.schedule]):
-                if sc == "deal" and (self.world == 1 or ex == "allgather" or not ctx.interleaved):
-                    continue  # dealing needs a peer exchange (a rank's tiles are scattered over the image) and is pointless on one GPU
+            for sc in (["static", "lpt", "deal", "shared"] if args.schedule == "auto" else [args.schedule]):
+                if sc in ("deal", "shared") and (self.world == 1 or ex == "allgather" or not ctx.interleaved):
+                    continue  # these need a peer exchange (a rank's tiles are scattered over the image) and are pointless on one GPU
                 cands.append((ex, sc))
         if not cands:
             raise SystemExit("no exchange / schedule combination fits these options")

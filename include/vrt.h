@@ -256,6 +256,10 @@ int vrt_last_trace_launches(vrt_ctx* ctx, uint32_t* out);
 #define VRT_SCHED_STATIC 0u
 #define VRT_SCHED_LPT 1u
 #define VRT_SCHED_DEAL 2u
+#define VRT_SCHED_SHARED 3u /* like DEAL, but nothing is dealt in advance: the warps of ALL ranks draw their tiles from one queue (in rank 0's
+                               memory, atomics over NVLink) in cost order — whichever GPU has a free warp takes the next most expensive tile, so
+                               the ranks finish together whatever the frame looks like.  Same requirements as DEAL; every rank must launch the
+                               same frame. */
 int vrt_set_schedule(vrt_ctx* ctx, uint32_t mode, uint32_t interval /* frames between sorts; 0 = 8 */);
 /* Debug / tests: read the per-tile costs of the last frame (clock ticks / 32, 0 = never traced), or install costs and sort them
  * into the order right away.  count <= tiles of the image = ceil(width/8) * ceil(height/4). */

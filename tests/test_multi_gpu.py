@@ -39,9 +39,9 @@ def _worker(rank, world, port, out_dir):
     sc = orc.OracleScene.from_grid(grid, mats)
     refs = [sc.render(c, sun)[0] for c in cams]
     failures = []
-    S, L, D = ffi.VRT_SCHED_STATIC, ffi.VRT_SCHED_LPT, ffi.VRT_SCHED_DEAL
+    S, L, D, SH = ffi.VRT_SCHED_STATIC, ffi.VRT_SCHED_LPT, ffi.VRT_SCHED_DEAL, ffi.VRT_SCHED_SHARED
     modes = [("interleave", "allgather", S), ("interleave", "allgather", L), ("interleave", "peer", S), ("interleave", "peer", D), ("interleave", "peerflags", L),
-             ("interleave", "peerflags", D), ("interleave", "peerpush", L), ("interleave", "peerpush", D), ("slab", "allgather", S), ("slab", "peer", L),
+             ("interleave", "peerflags", D), ("interleave", "peerflags", SH), ("interleave", "peer", SH), ("interleave", "peerpush", L), ("interleave", "peerpush", D), ("slab", "allgather", S), ("slab", "peer", L),
              ("slab", "peerflags", S), ("slab", "peerpush", S)]
     for partition, exchange, sched in modes:
         tag = f"{partition}/{exchange}/sched{sched}"
@@ -88,7 +88,7 @@ def _worker(rank, world, port, out_dir):
                     failures.append(f"{tag}: pipelined frame {i} differs on rank {rank}")
         dist.barrier()
         # the host as the consumer (VRT_EXCHANGE_HOST): no device exchange, each rank copies exactly its own rows / strips
-        if sched != D:
+        if sched not in (D, SH):
             ctx.comm_set_exchange(ffi.VRT_EXCHANGE_HOST)
             mine = np.zeros(H, dtype=bool)
             if partition == "slab":

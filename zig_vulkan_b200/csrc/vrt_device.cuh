@@ -267,6 +267,7 @@ struct TraceParams {
     // persistent-kernel work queue: counter[0] = next ticket, counter[1] = warps that have left the queue; the last warp to
     // leave resets both, so every launch starts from 0 with identical parameters (frames can be replayed from a CUDA graph)
     unsigned long long* tile_counter;
+    uint32_t queue_world;  // GPUs whose warps pull from this queue (1: private; > 1: it lives in rank 0's memory, reached over NVLink)
     // Tile schedule (vrt_sched.cu).  order: a permutation of this launch's tile space, most expensive tile first (longest-
     // processing-time-first keeps the tail of the launch short); ticket i traces tile order[order_offset + i * order_stride].
     // NULL: bottom-up (ground rows first, sky tiles fill the tail).  cost: clock ticks / 32 each tile took, written by whoever

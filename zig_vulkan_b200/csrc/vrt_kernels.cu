@@ -51,15 +51,28 @@ constexpr uint32_t kTileW = 8, kTileH = 4;
 // 3 CTAs of 256 threads per SM (80 registers): measured 10 % faster than 2 (102 registers, no spills) and equal to 4 (64, spills).
 // SIMPLE: the configuration shade_pixel_warp_simple covers (chosen per launch by launch_trace_tuned).
 // A warp leaves the work queue: the last one out resets the ticket counter for the next launch (see TraceParams::tile_counter).
+// With a queue shared by several GPUs (VRT_SCHED_SHARED) every rank launches the same grid, so the warps of all of them add up.
 VRT_DI void leave_queue(const TraceParams& P, uint32_t lane) {
     if (lane == 0) {
-        const unsigned long long warps = (unsigned long long)gridDim.x * (blockDim.x >> 5);
-        __threadfence();
-        if (atomicAdd(P.tile_counter + 1, 1ull) == warps - 1ull) {
-            P.tile_counter[0] = 0ull;
-            P.tile_counter[1] = 0ull;
+        const unsigned long long warps = (unsigned long long)gridDim.x * (blockDim.x >> 5) * (P.queue_world ? P.queue_world : 1u);
+        if (P.queue_world > 1u) {
+            __threadfence_system();
+            if (atomicAdd_system(P.tile_counter + 1, 1ull) == warps - 1ull) {
+                *reinterpret_cast<volatile unsigned long long*>(P.tile_counter) = 0ull;
+                *reinterpret_cast<volatile unsigned long long*>(P.tile_counter + 1) = 0ull;
+                __threadfence_system();
+            }
+        } else {
+            __threadfence();
+            if (atomicAdd(P.tile_counter + 1, 1ull) == warps - 1ull) {
+                P.tile_counter[0] = 0ull;
+                P.tile_counter[1] = 0ull;
+            }
         }
     }
+}
+VRT_DI unsigned long long draw_ticket(const TraceParams& P) {
+    return P.queue_world > 1u ? atomicAdd_system(P.tile_counter, 1ull) : atomicAdd(P.tile_counter, 1ull);
 }
 
 template <int BD, bool AOV, bool SIMPLE>
@@ -74,7 +87,7 @@ __global__ void __launch_bounds__(kTunedThreads, SIMPLE ? VRT_TUNED_BLOCKS : VRT
 
     for (;;) {
         unsigned long long t = 0ull;
-        if (lane == 0) t = atomicAdd(P.tile_counter, 1ull);
+        if (lane == 0) t = draw_ticket(P);
         t = __shfl_sync(kFullMask, t, 0);
         if (t >= (unsigned long long)tiles_total) break;
         // Scheduled: the most expensive tiles of the previous frames first (vrt_sched.cu).  Otherwise bottom-up: in the reference's
@@ -219,7 +232,7 @@ __global__ void __launch_bounds__(kTunedThreads, VRT_TUNED_BLOCKS) trace_rays_ke
 #endif
     for (;;) {  // blocks of 32 rays from the same work counter as the pixel kernel: rays differ in cost by orders of magnitude
         unsigned long long t = 0ull;
-        if (lane == 0) t = atomicAdd(P.tile_counter, 1ull);
+        if (lane == 0) t = draw_ticket(P);
         t = __shfl_sync(kFullMask, t, 0);
         if (t >= blocks) break;
         const unsigned long long base = t * 32ull;

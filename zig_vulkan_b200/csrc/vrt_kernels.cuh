@@ -80,6 +80,7 @@ cudaError_t launch_insert_commit(const InsertBuffers& B, const uint32_t* xyzm, s
                                  cudaStream_t stream, LaunchInfo* info);
 // analysis builds (-DVRT_TILE_STATS=1): device buffer of 8 words per tile the trace kernel fills; cudaErrorNotSupported otherwise
 cudaError_t debug_set_tile_stats(uint32_t* device_buffer);
+constexpr size_t kSharedQueueOffset = 128;  // inside the flag words' 256 bytes: the tile queue all ranks pull from under VRT_SCHED_SHARED (rank 0's copy)
 constexpr size_t kPeerFlagBytes = 256;  // flag words appended to the IPC-shared framebuffer allocation
 constexpr uint32_t kStripRows = 4;  // rows per strip of the interleaved partition (= the tile height of the trace kernel)
 cudaError_t launch_trace_tuned(const TraceParams& P, bool aov, cudaStream_t stream, LaunchInfo* info);

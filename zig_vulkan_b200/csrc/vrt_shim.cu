@@ -299,8 +299,15 @@ void fill_params(const vrt_ctx* c, const vrt_camera* cam, const vrt_sun* sun, Tr
         P.tile_order = c->d_order;
         P.tile_cost = c->d_cost[parity];
         P.order_offset = 0u, P.order_stride = 1u;
-        if (c->sched_mode == VRT_SCHED_DEAL) {  // the whole image is one tile space, this rank takes every part_world-th entry of the order
-            P.order_offset = c->part_rank, P.order_stride = c->part_world;
+        if (c->sched_mode == VRT_SCHED_DEAL || c->sched_mode == VRT_SCHED_SHARED) {
+            // the whole image is one tile space: this rank takes every part_world-th entry of the order (DEAL), or whatever ticket its
+            // warps draw from the ONE queue all ranks share — rank 0's, reached through the peer mapping (SHARED)
+            if (c->sched_mode == VRT_SCHED_DEAL) {
+                P.order_offset = c->part_rank, P.order_stride = c->part_world;
+            } else if (c->world > 1 && P.n_peers) {
+                P.tile_counter = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(c->peer_fb[0]) + 2 * c->fb_bytes + kSharedQueueOffset);
+                P.queue_world = (uint32_t)c->world;
+            }
             P.il_world = 0u, P.il_gather = 0u;
             P.row_begin = 0u, P.row_end = c->cfg.height;
             const size_t cost_off = 2 * c->fb_bytes + kPeerFlagBytes + (size_t)parity * cost_bytes(c);
@@ -551,6 +558,7 @@ bool peer_mode(const vrt_ctx* c) {
     return c->world > 1 && c->peers_open &&
            (c->exchange_mode == VRT_EXCHANGE_PEER_STORE || c->exchange_mode == VRT_EXCHANGE_PEER_FLAGS || c->exchange_mode == VRT_EXCHANGE_PEER_PUSH);
 }
+bool scattered(const vrt_ctx* c) { return c->sched_mode == VRT_SCHED_DEAL || c->sched_mode == VRT_SCHED_SHARED; }
 bool owns_fb(const vrt_ctx* c) { return c->d_fb == c->d_fb_own || c->d_fb == c->d_fb_ring1; }
 
 int ensure_ring(vrt_ctx* ctx) {  // copy stream + per-slot events of the two-slot frame ring
@@ -586,8 +594,8 @@ int trace_frame(vrt_ctx* ctx, const vrt_camera* camera, const vrt_sun* sun, bool
     if (ctx->world > 1 && !ctx->comm && ctx->exchange_mode != VRT_EXCHANGE_PEER_FLAGS && ctx->exchange_mode != VRT_EXCHANGE_PEER_PUSH &&
         ctx->exchange_mode != VRT_EXCHANGE_HOST)  // none of these needs a communicator
         return fail(ctx, VRT_E_STATE, "vrt_trace: world > 1 but vrt_comm_init has not been called");
-    if (ctx->sched_mode == VRT_SCHED_DEAL && ctx->world > 1 && !peer_mode(ctx))
-        return fail(ctx, VRT_E_STATE, "vrt_trace: VRT_SCHED_DEAL scatters a rank's tiles over the image and needs a peer-store exchange mode");
+    if (scattered(ctx) && ctx->world > 1 && !peer_mode(ctx))
+        return fail(ctx, VRT_E_STATE, "vrt_trace: VRT_SCHED_DEAL / SHARED scatter a rank's tiles over the image and need a peer-store exchange mode");
     VRT_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
 
     // Frame ring.  Async frames always use it.  In the peer-store modes EVERY frame does: a peer's frame k+1 stores straight into this
@@ -635,7 +643,7 @@ int trace_frame(vrt_ctx* ctx, const vrt_camera* camera, const vrt_sun* sun, bool
             VRT_CUDA(ctx, launch_sched_init(ctx->d_order, space, ctx->stream, &info));
             ctx->sched_tiles = space, ctx->sched_frames = 0;
             P.tile_cost = ctx->d_cost[0];
-            if (ctx->sched_mode == VRT_SCHED_DEAL && P.n_peers) {  // parity 0 again
+            if (scattered(ctx) && P.n_peers) {  // parity 0 again
                 const size_t cost_off = 2 * ctx->fb_bytes + kPeerFlagBytes;
                 uint32_t p = 0;
                 for (int r = 0; r < ctx->world; r++)
@@ -643,7 +651,8 @@ int trace_frame(vrt_ctx* ctx, const vrt_camera* camera, const vrt_sun* sun, bool
             }
         }
     }
-    const bool push = peer_mode(ctx) && ctx->exchange_mode == VRT_EXCHANGE_PEER_PUSH && P.vec_store_ok && which == KERNEL_TUNED && !aov;
+    // (with a shared queue a rank does not know in advance which tiles it will trace: the stores stay in the trace kernel)
+    const bool push = peer_mode(ctx) && ctx->exchange_mode == VRT_EXCHANGE_PEER_PUSH && P.vec_store_ok && which == KERNEL_TUNED && !aov && ctx->sched_mode != VRT_SCHED_SHARED;
     if (push) {  // the trace kernel keeps its pixels local (the costs of a dealt schedule still go to the peers); a copy kernel ships them afterwards
         TraceParams Q = P;
         Q.n_peers = 0u;
@@ -704,7 +713,7 @@ int copy_frame_to_host(vrt_ctx* ctx, uint8_t* host, cudaStream_t stream) {
     const uint8_t* fb = reinterpret_cast<const uint8_t*>(ctx->d_fb);
     const size_t row_bytes = (size_t)ctx->cfg.width * 4;
     const bool host_mode = ctx->exchange_mode == VRT_EXCHANGE_HOST;
-    if (ctx->interleave && host_mode && ctx->sched_mode != VRT_SCHED_DEAL) {
+    if (ctx->interleave && host_mode && !scattered(ctx)) {
         const size_t chunk = kStripRows * row_bytes, pitch = (size_t)ctx->part_world * chunk, first = (size_t)ctx->part_rank * chunk;
         const uint32_t strips = (ctx->cfg.height + kStripRows - 1) / kStripRows;
         const uint32_t mine = strips > ctx->part_rank ? (strips - ctx->part_rank + ctx->part_world - 1) / ctx->part_world : 0u;
@@ -719,11 +728,11 @@ int copy_frame_to_host(vrt_ctx* ctx, uint8_t* host, cudaStream_t stream) {
         }
         return VRT_OK;
     }
-    const bool whole = !host_mode && (ctx->world > 1 || ctx->interleave || ctx->sched_mode == VRT_SCHED_DEAL);
+    const bool whole = !host_mode && (ctx->world > 1 || ctx->interleave || scattered(ctx));
     const size_t from = whole ? 0 : (size_t)ctx->row_begin * row_bytes;
     const size_t n = whole ? ctx->fb_bytes : (size_t)(ctx->row_end - ctx->row_begin) * row_bytes;
-    if (ctx->interleave && !whole && ctx->sched_mode == VRT_SCHED_DEAL)
-        return fail(ctx, VRT_E_STATE, "VRT_EXCHANGE_HOST cannot be combined with VRT_SCHED_DEAL (a rank's tiles are scattered over the image)");
+    if (ctx->interleave && !whole && scattered(ctx))
+        return fail(ctx, VRT_E_STATE, "VRT_EXCHANGE_HOST cannot be combined with VRT_SCHED_DEAL / SHARED (a rank's tiles are scattered over the image)");
     VRT_CUDA(ctx, cudaMemcpyAsync(host + from, fb + from, n, cudaMemcpyDeviceToHost, stream));
     return VRT_OK;
 }
@@ -1100,10 +1109,10 @@ int vrt_last_trace_kernel_ms(vrt_ctx* ctx, float* out_ms) {
 
 int vrt_set_schedule(vrt_ctx* ctx, uint32_t mode, uint32_t interval) {
     if (!ctx) return VRT_E_INVALID;
-    if (mode > VRT_SCHED_DEAL) return fail(ctx, VRT_E_INVALID, "vrt_set_schedule: unknown mode %u", mode);
-    if (mode == VRT_SCHED_DEAL) {
-        if (!ctx->interleave) return fail(ctx, VRT_E_STATE, "vrt_set_schedule: VRT_SCHED_DEAL needs a context created with VRT_FLAG_INTERLEAVE (part_rank / part_world)");
-        if (!ctx->d_fb_own || !owns_fb(ctx)) return fail(ctx, VRT_E_STATE, "vrt_set_schedule: VRT_SCHED_DEAL needs the context-owned framebuffer");
+    if (mode > VRT_SCHED_SHARED) return fail(ctx, VRT_E_INVALID, "vrt_set_schedule: unknown mode %u", mode);
+    if (mode == VRT_SCHED_DEAL || mode == VRT_SCHED_SHARED) {
+        if (!ctx->interleave) return fail(ctx, VRT_E_STATE, "vrt_set_schedule: VRT_SCHED_DEAL / SHARED need a context created with VRT_FLAG_INTERLEAVE (part_rank / part_world)");
+        if (!ctx->d_fb_own || !owns_fb(ctx)) return fail(ctx, VRT_E_STATE, "vrt_set_schedule: VRT_SCHED_DEAL / SHARED need the context-owned framebuffer");
     }
     if (mode != ctx->sched_mode) ctx->sched_tiles = 0;  // another tile space / another set of tiles per rank: start from the default order
     ctx->sched_mode = mode;
