@@ -10,7 +10,7 @@ timeout -k 5 300 python bench.py --workload C4 --no-cpu-baseline --no-extras --s
 timeout -k 5 200 python bench.py --baseline-kernel --no-cpu-baseline --no-extras --steps 40 > gpurun_out/bench_C3_baseline_kernel.json 2>> gpurun_out/bench.err
 timeout -k 5 300 python bench.py --impl reference --steps 10 --warmup 1 > gpurun_out/bench_C3_reference.json 2>> gpurun_out/bench.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_C3.csv timeout -k 5 200 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/bench_under_ncu.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:trace_warp -s 60 -c 1 -f -o gpurun_out/prof_warp_C3 timeout -k 5 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extras --schedule lpt > gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:trace_warp -s 20 -c 1 -f -o gpurun_out/prof_warp_C3 timeout -k 5 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extras --schedule lpt > gpurun_out/ncu_full.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:denoise_kernel -s 3 -c 1 -f -o gpurun_out/prof_denoise_1080p timeout -k 5 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_denoise.log 2>&1
 cp zig_vulkan_b200/libvrt.so /tmp/libvrt_orig.so; cp build/ab/libvrt_stats.so zig_vulkan_b200/libvrt.so
 timeout -k 5 200 python tools/gpu_tilestats.py C3 > gpurun_out/tilestats_C3.log 2>&1; head -4 gpurun_out/tilestats_C3.log

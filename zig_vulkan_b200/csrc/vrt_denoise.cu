@@ -63,6 +63,10 @@ __device__ __forceinline__ float det_exp2f(float y) {
 // image.frag:29  #define pow(a,b) pow(max(a,0.),b)
 // x^n for a whole n >= 1: binary exponentiation, lowest bit first — the oracle's fixed order of exact FP32 products
 __device__ __forceinline__ float det_powif(float a, unsigned n) {
+    if (n == 20u) {  // the default hue tolerance: the loop below unrolled for 10100b — the same five products in the same order
+        const float p2 = a * a, p4 = p2 * p2, p8 = p4 * p4, p16 = p8 * p8;
+        return p4 * p16;
+    }
     float r = 1.0f, p = a;
     while (n) {
         if (n & 1u) r = r * p;

@@ -383,13 +383,19 @@ cudaError_t launch_status_merge(uint32_t* dst, const uint32_t* staged, size_t co
 // only LOWER values, and only for the cells p that have q in their closed octant: dist_o(p) = min(dist_o(p), |q - p|_1), and p's
 // octant is not free any more.  One thread per cell and octant; O(cells) bytes touched in the worst case, against the three
 // serial line scans of the full rebuild.  Same bytes as a rebuild from scratch (tests/test_accel_update.py).
+__device__ __forceinline__ void dist_patch_cell(const TraceParams& P, uint8_t* __restrict__ dist, const AccelDelta* __restrict__ delta, uint32_t n, int o, size_t cell);
 __global__ void __launch_bounds__(256) dist_patch_kernel(const __grid_constant__ TraceParams P, uint8_t* __restrict__ dist, const AccelDelta* __restrict__ delta) {
     const uint32_t n = delta->n_new;
     if (n == 0u || n > kAccelMaxNew || delta->force_full) return;
     const uint32_t dim_x = P.grid.dim_x, dim_y = P.grid.dim_y, dim_z = P.grid.dim_z;
-    const size_t cell = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (cell >= (size_t)dim_x * dim_y * dim_z) return;
     const int o = (int)blockIdx.y;  // bit0: x decreasing, bit1: y decreasing, bit2: z decreasing (dist_scan_kernel)
+    // a modest fixed grid walks the cells (most launches find n == 0 above and must cost next to nothing)
+    for (size_t cell = (size_t)blockIdx.x * blockDim.x + threadIdx.x; cell < (size_t)dim_x * dim_y * dim_z; cell += (size_t)gridDim.x * blockDim.x)
+        dist_patch_cell(P, dist, delta, n, o, cell);
+}
+
+__device__ __forceinline__ void dist_patch_cell(const TraceParams& P, uint8_t* __restrict__ dist, const AccelDelta* __restrict__ delta, uint32_t n, int o, size_t cell) {
+    const uint32_t dim_x = P.grid.dim_x, dim_z = P.grid.dim_z;
     const int px = (int)(cell % dim_x), pz = (int)((cell / dim_x) % dim_z), py = (int)(cell / ((size_t)dim_x * dim_z));
     // the octant of p must contain at least the extreme new cell
     if ((o & 1) ? px < (int)delta->lo[0] : px > (int)delta->hi[0]) return;
@@ -428,7 +434,7 @@ cudaError_t launch_build_accel(const TraceParams& P, uint4* cell_rec, uint8_t* d
     uint8_t* tmp_z = tmp + 2 * n_bricks;  // [4][n]
     const size_t dx = P.grid.dim_x, dy = P.grid.dim_y, dz = P.grid.dim_z;
     if (delta) {
-        dist_patch_kernel<<<dim3(blocks, 8), 256, 0, stream>>>(P, dist, delta);
+        dist_patch_kernel<<<dim3(blocks < 592u ? blocks : 592u, 8), 256, 0, stream>>>(P, dist, delta);
         if (info) info->launches++;
     }
     dist_scan_kernel<<<dim3((unsigned)((dz * dy + 127) / 128), 2), 128, 0, stream>>>(P, nullptr, tmp_x, n_bricks, 0, delta);
