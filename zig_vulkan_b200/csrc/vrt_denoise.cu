@@ -145,11 +145,12 @@ __device__ __forceinline__ uint32_t dn_unorm8(float c) {
 
 constexpr float kCosGolden = -0.7373688f, kSinGolden = 0.6754904f;  // cos / sin(2.3999632), image.frag:25,29
 
-template <bool NEAR>
-__global__ void __launch_bounds__(kDnBlockX* kDnBlockY) denoise_kernel(const float4* __restrict__ img, int w, int h, const vrt_denoise_params pc, uint32_t* __restrict__ out,
-                                                                        uint32_t out_w, uint32_t out_h, uint32_t bgra) {
-    __shared__ float s_off_x[kDnMaxSamples + 1], s_off_y[kDnMaxSamples + 1], s_radial[kDnMaxSamples + 1];
-    const int tid = threadIdx.y * kDnBlockX + threadIdx.x;
+// What every fragment derives from the push constants alone (:35-37, :45-53) — the rotated, scaled sample offsets and the radial
+// weight term of each of the samples + 1 taps — once per launch, with the fragment's own operation order: table[0..255] = offset x,
+// [256..511] = offset y, [512..767] = radial term.  (It used to be recomputed by every CTA behind a barrier: 18 % of the pass's stall
+// samples, profiles/r02_denoise_1080p_summary.json.)
+__global__ void __launch_bounds__(kDnMaxSamples + 1) denoise_table_kernel(int w, int h, const vrt_denoise_params pc, float* __restrict__ table) {
+    const int tid = (int)threadIdx.x;
     if (tid <= pc.samples) {
         const float sample_radius = sqrtf((float)pc.samples);                       // :35
         const float sample_true_radius = 0.5f / (sample_radius * sample_radius);    // :36
@@ -161,9 +162,17 @@ __global__ void __launch_bounds__(kDnBlockX* kDnBlockY) denoise_kernel(const flo
         }
         const float sq = sqrtf((float)tid);
         const float off_x = ((pc.pixel_multiplier * rot_x) * sq) * 0.5f, off_y = ((pc.pixel_multiplier * rot_y) * sq) * 0.5f;  // :51
-        s_radial[tid] = 1.0f - sample_true_radius * gpow(off_x * off_x + off_y * off_y, pc.distribution_bias);                // :52
-        s_off_x[tid] = off_x * (1.0f / (float)w), s_off_y[tid] = off_y * (1.0f / (float)h);                                   // :37,:53
+        table[2 * (kDnMaxSamples + 1) + tid] = 1.0f - sample_true_radius * gpow(off_x * off_x + off_y * off_y, pc.distribution_bias);  // :52
+        table[tid] = off_x * (1.0f / (float)w), table[kDnMaxSamples + 1 + tid] = off_y * (1.0f / (float)h);                             // :37,:53
     }
+}
+
+template <bool NEAR>
+__global__ void __launch_bounds__(kDnBlockX* kDnBlockY) denoise_kernel(const float4* __restrict__ img, int w, int h, const vrt_denoise_params pc, uint32_t* __restrict__ out,
+                                                                        uint32_t out_w, uint32_t out_h, uint32_t bgra, const float* __restrict__ table) {
+    __shared__ float s_off_x[kDnMaxSamples + 1], s_off_y[kDnMaxSamples + 1], s_radial[kDnMaxSamples + 1];
+    const int tid = threadIdx.y * kDnBlockX + threadIdx.x;
+    if (tid <= pc.samples) s_off_x[tid] = table[tid], s_off_y[tid] = table[kDnMaxSamples + 1 + tid], s_radial[tid] = table[2 * (kDnMaxSamples + 1) + tid];
     __syncthreads();
 
     const uint32_t ox = blockIdx.x * kDnBlockX + threadIdx.x, oy = blockIdx.y * kDnBlockY + threadIdx.y;
@@ -201,16 +210,18 @@ cudaError_t launch_denoise(const uint32_t* image, float4* decoded, uint32_t widt
                            uint32_t out_width, uint32_t out_height, bool bgra, cudaStream_t stream, LaunchInfo* info) {
     const size_t n = (size_t)width * height;
     decode_unorm_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(image, decoded, n);
-    if (info) info->launches++;
+    float* table = reinterpret_cast<float*>(decoded + n);  // 3 x 256 floats behind the decoded image (kDenoiseScratchTail)
+    denoise_table_kernel<<<1, kDnMaxSamples + 1, 0, stream>>>((int)width, (int)height, params, table);
+    if (info) info->launches += 2;
     const dim3 block(kDnBlockX, kDnBlockY);
     const dim3 grid((out_width + kDnBlockX - 1) / kDnBlockX, (out_height + kDnBlockY - 1) / kDnBlockY);
     // largest sample offset in input texels (:51): |pixelMultiplier| * sqrt(samples) * 0.5, plus the bilinear footprint and slack
     const float reach = fabsf(params.pixel_multiplier) * sqrtf((float)params.samples) * 0.5f + 3.0f;
     const bool near = reach < (float)(width < height ? width : height);  // false also for a NaN multiplier
     if (near)
-        denoise_kernel<true><<<grid, block, 0, stream>>>(decoded, (int)width, (int)height, params, out, out_width, out_height, bgra ? 1u : 0u);
+        denoise_kernel<true><<<grid, block, 0, stream>>>(decoded, (int)width, (int)height, params, out, out_width, out_height, bgra ? 1u : 0u, table);
     else
-        denoise_kernel<false><<<grid, block, 0, stream>>>(decoded, (int)width, (int)height, params, out, out_width, out_height, bgra ? 1u : 0u);
+        denoise_kernel<false><<<grid, block, 0, stream>>>(decoded, (int)width, (int)height, params, out, out_width, out_height, bgra ? 1u : 0u, table);
     if (info) info->launches++;
     return cudaGetLastError();
 }
