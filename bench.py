@@ -33,7 +33,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--workload", default="C3", choices=["C1", "C2", "C3", "C4", "C5"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--exchange", default="auto", choices=["auto", "allgather", "peer", "peerflags", "peerpush"],
+    ap.add_argument("--exchange", default="auto", choices=["auto", "allgather", "peer", "peerflags", "peerpush", "peertiles"],
                     help="N > 1: fused peer stores from the trace kernel (frame barrier = NCCL 4-byte all-reduce, or peer flag words: "
                          "peerflags), or an NCCL all-gather after it; auto = every combination of exchange and schedule is timed for a few "
                          "frames on this box and the fastest one runs the timed region")
@@ -268,15 +268,17 @@ class Rig:
 
         if self.world > 1:
             ctx.comm_set_exchange({"allgather": ffi.VRT_EXCHANGE_ALLGATHER, "peer": ffi.VRT_EXCHANGE_PEER_STORE, "peerflags": ffi.VRT_EXCHANGE_PEER_FLAGS,
-                                   "peerpush": ffi.VRT_EXCHANGE_PEER_PUSH}[exchange])
+                                   "peerpush": ffi.VRT_EXCHANGE_PEER_PUSH, "peertiles": ffi.VRT_EXCHANGE_PEER_TILES}[exchange])
         ctx.set_schedule({"static": ffi.VRT_SCHED_STATIC, "lpt": ffi.VRT_SCHED_LPT, "deal": ffi.VRT_SCHED_DEAL, "shared": ffi.VRT_SCHED_SHARED}[schedule], interval)
 
-    def choose_mode(self, ctx, cam, sun):
-        """Exchange x schedule by measurement on this box: each candidate runs 4 + 12 flushed frames, the smallest max-over-ranks mean wins."""
+    def choose_mode(self, ctx, cam, sun, want_crc=None):
+        """Exchange x schedule by measurement on this box: each candidate runs 4 + 12 flushed frames, the smallest max-over-ranks mean wins.
+        A candidate whose frame is not the single-GPU frame on every rank (want_crc) is out, whatever its time."""
+        import zlib
         args = self.args
         if args.baseline_kernel:
             return ("allgather" if self.world > 1 else "none", "static"), {}
-        exchanges = (["allgather", "peerflags"] if args.exchange == "auto" else [args.exchange]) if self.world > 1 else ["none"]
+        exchanges = (["allgather", "peerflags", "peertiles"] if args.exchange == "auto" else [args.exchange]) if self.world > 1 else ["none"]
         cands = []
         for ex in exchanges:
             for sc in (["static", "lpt", "deal", "shared"] if args.schedule == "auto" else [args.schedule]):
@@ -292,8 +294,16 @@ class Rig:
         for ex, sc in cands:
             self.set_mode(ctx, ex, sc)
             ms, _ = self.timed(ctx, cam, sun, 12, 4)
-            table[f"{ex}/{sc}"] = self.reduce([sum(ms) / len(ms)])[0]
-        best = min(table, key=table.get)
+            mean = self.reduce([sum(ms) / len(ms)])[0]
+            if want_crc is not None:
+                bad = float(zlib.crc32(ctx.read_framebuffer().tobytes()) != want_crc)
+                if self.reduce([bad])[0] > 0:
+                    mean = None  # wrong frame on some rank
+            table[f"{ex}/{sc}"] = mean
+        good = {k: v for k, v in table.items() if v is not None}
+        if not good:
+            raise SystemExit("bench.py: no exchange / schedule combination reproduced the single-GPU frame")
+        best = min(good, key=good.get)
         ex, sc = best.split("/")
         self.set_mode(ctx, ex, sc)
         return (ex, sc), table
@@ -332,8 +342,15 @@ def measure(rig, grid, mats, W, H, brick_dim, cam, sun, steps, warmup, with_e2e=
     if rig.args.baseline_kernel:
         from zig_vulkan_b200 import ffi
         flags = ffi.VRT_FLAG_BASELINE
+    # the frame one GPU traces alone: what every rank must end up with, whatever the exchange and the schedule
+    solo_crc = 0
+    if rank == 0:
+        solo = rig.make_ctx(grid, mats, W, H, brick_dim, flags, solo=True)
+        solo_crc = zlib.crc32(solo.trace_to_host(cam, sun).tobytes())
+        solo.close()
+    solo_crc = int(rig.reduce([float(solo_crc)])[0])  # (a CRC32 is exact in a float64)
     ctx = rig.make_ctx(grid, mats, W, H, brick_dim, flags)
-    (exchange, schedule), table = rig.choose_mode(ctx, cam, sun)
+    (exchange, schedule), table = rig.choose_mode(ctx, cam, sun, want_crc=solo_crc)
 
     step_ms, wall_ms = rig.timed(ctx, cam, sun, steps, max(warmup, 3))
     launches_per_step = ctx.last_trace_launches()
@@ -363,14 +380,6 @@ def measure(rig, grid, mats, W, H, brick_dim, cam, sun, steps, warmup, with_e2e=
         out = [torch.empty_like(t) for _ in range(world)]
         dist.all_gather(out, t)
         crcs = [int(o[0]) for o in out]
-    solo_crc = None
-    if rank == 0:
-        if world > 1:
-            solo = rig.make_ctx(grid, mats, W, H, brick_dim, flags, solo=True)
-            solo_crc = zlib.crc32(solo.trace_to_host(cam, sun).tobytes())
-            solo.close()
-        else:
-            solo_crc = crc
 
     res = {"ctx": ctx, "exchange": exchange, "schedule": schedule, "candidates_ms": table, "step_ms": step_ms, "step_max": step_max, "total_ms": total_ms,
            "wall_ms": wall_ms, "launches_per_step": launches_per_step, "kernel_ms_max": kmax, "kernel_ms_min": kmin, "exchange_ms": xmax,

@@ -351,6 +351,10 @@ int vrt_framebuffer_device_ptr(vrt_ctx* ctx, void** out_device_ptr);
 #define VRT_EXCHANGE_PEER_FLAGS 2u
 #define VRT_EXCHANGE_PEER_PUSH 4u /* mode 2 with the peer stores moved out of the trace kernel: the kernel writes its own framebuffer only and a
                                      copy kernel then ships this rank's tiles to every peer (128-bit loads / stores), followed by the flag barrier */
+#define VRT_EXCHANGE_PEER_TILES 5u /* mode 2 with a tile-major wire format: the trace kernel stores each finished 8x4 tile as ONE contiguous 128-byte
+                                      record into a staging buffer of every rank (its own included) instead of four 32-byte row segments into
+                                      every peer's image; after the flag barrier each rank un-tiles its staging buffer into its framebuffer.
+                                      A quarter of the NVLink packets, each four times the size.  Tuned kernel, strip-aligned partitions. */
 #define VRT_EXCHANGE_HOST 3u /* no device-side exchange at all: the consumer is the host.  vrt_trace_to_host(_async) copies only this
                                 rank's own rows / 4-row strips into their place of the full-image host buffer, so N ranks given the same
                                 (shared, pinned) buffer assemble the frame over N PCIe links at once instead of funnelling it through one

@@ -41,7 +41,8 @@ def _worker(rank, world, port, out_dir):
     failures = []
     S, L, D, SH = ffi.VRT_SCHED_STATIC, ffi.VRT_SCHED_LPT, ffi.VRT_SCHED_DEAL, ffi.VRT_SCHED_SHARED
     modes = [("interleave", "allgather", S), ("interleave", "allgather", L), ("interleave", "peer", S), ("interleave", "peer", D), ("interleave", "peerflags", L),
-             ("interleave", "peerflags", D), ("interleave", "peerflags", SH), ("interleave", "peer", SH), ("interleave", "peerpush", L), ("interleave", "peerpush", D), ("slab", "allgather", S), ("slab", "peer", L),
+             ("interleave", "peerflags", D), ("interleave", "peerflags", SH), ("interleave", "peer", SH), ("interleave", "peerpush", L), ("interleave", "peerpush", D), ("interleave", "peertiles", L), ("interleave", "peertiles", D),
+             ("interleave", "peertiles", SH), ("slab", "peertiles", S), ("slab", "allgather", S), ("slab", "peer", L),
              ("slab", "peerflags", S), ("slab", "peerpush", S)]
     for partition, exchange, sched in modes:
         tag = f"{partition}/{exchange}/sched{sched}"
@@ -58,7 +59,8 @@ def _worker(rank, world, port, out_dir):
             handles = [None] * world
             dist.all_gather_object(handles, ctx.comm_ipc_handle())
             ctx.comm_open_peers(rank, world, b"".join(handles))
-            ctx.comm_set_exchange({"peer": ffi.VRT_EXCHANGE_PEER_STORE, "peerflags": ffi.VRT_EXCHANGE_PEER_FLAGS, "peerpush": ffi.VRT_EXCHANGE_PEER_PUSH}[exchange])
+            ctx.comm_set_exchange({"peer": ffi.VRT_EXCHANGE_PEER_STORE, "peerflags": ffi.VRT_EXCHANGE_PEER_FLAGS, "peerpush": ffi.VRT_EXCHANGE_PEER_PUSH,
+                                   "peertiles": ffi.VRT_EXCHANGE_PEER_TILES}[exchange])
         ctx.set_schedule(sched, 2)
         # blocking frames of a MOVING camera, no host-side barrier anywhere: a fast rank's next frame must not tear the frame a
         # slow rank is still reading (the ranks are skewed on purpose)

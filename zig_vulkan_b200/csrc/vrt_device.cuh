@@ -281,6 +281,11 @@ struct TraceParams {
     // fused peer-store exchange (multi-GPU): framebuffers of every rank, this rank included
     uint32_t* peer_fb[8];
     uint32_t n_peers;
+    // tile-major exchange (VRT_EXCHANGE_PEER_TILES): instead of four 32-byte row segments into every peer's row-major image, a tile
+    // goes as ONE contiguous 128-byte record (32 texels, lane order) into the tile-major staging buffer of every rank, this one
+    // included; each rank un-tiles its own staging buffer into its framebuffer after the frame barrier (untile_kernel)
+    uint32_t* stage[8];
+    uint32_t n_stage;
     uint32_t one;  // = 1, opaque to the compiler: multiplier of the march's index IMADs (vrt_trav_warp.cuh march_step)
 };
 

@@ -56,6 +56,8 @@ cudaError_t launch_denoise(const uint32_t* image, float4* decoded, uint32_t widt
                            uint32_t out_width, uint32_t out_height, bool bgra, cudaStream_t stream, LaunchInfo* info);
 // VRT_EXCHANGE_PEER_PUSH: copy the tiles P describes (as the trace launch would enumerate them) from P.fb into every P.peer_fb.
 cudaError_t launch_push_tiles(const TraceParams& P, cudaStream_t stream, LaunchInfo* info);
+// VRT_EXCHANGE_PEER_TILES: un-tile this rank's tile-major staging buffer (128 bytes per 8x4 tile of the whole image) into fb.
+cudaError_t launch_untile(const uint32_t* stage, uint32_t* fb, uint32_t width, uint32_t height, bool vec_ok, cudaStream_t stream, LaunchInfo* info);
 // Frame barrier over peer-mapped flag words (fused peer-store exchange, VRT_EXCHANGE_PEER_FLAGS); see vrt_kernels.cu.
 cudaError_t launch_peer_barrier(uint32_t* const flags[8], uint32_t rank, uint32_t world, uint32_t frame, int* error, cudaStream_t stream, LaunchInfo* info);
 // BrickGrid.insert for a batch of voxels on the device (vrt_build.cu): `prepare` only reads the grid buffers (first occurrences,

@@ -105,6 +105,7 @@ struct vrt_ctx {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_traced[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
     bool slot_used[2] = {false, false};
+    uint64_t stage_seq = 0; // frames exchanged tile-major (parity picks the staging buffer)
     uint64_t ring_seq = 0;  // frames that went through the two-slot ring (async frames; every frame in the peer-store modes)
 
     // post-process output (vrt_denoise)
@@ -243,7 +244,14 @@ int rebuild_accel(vrt_ctx* ctx, const TraceParams& P, LaunchInfo* info) {
     return VRT_OK;
 }
 
+// the tile-major exchange is for the tuned kernel on partitions aligned to the image's 4-row strips
+bool tiles_exchange_ok(const vrt_ctx* c) {
+    return !(c->cfg.flags & (VRT_FLAG_AOV | VRT_FLAG_BASELINE)) &&
+           (c->interleave || (c->row_begin % kStripRows == 0 && (c->row_end % kStripRows == 0 || c->row_end == c->cfg.height)));
+}
 size_t cost_bytes(const vrt_ctx* c) { return ((size_t)c->tiles_global * sizeof(uint16_t) + 255u) & ~(size_t)255u; }
+size_t stage_bytes(const vrt_ctx* c) { return (size_t)c->tiles_global * 128u; }  // tile-major staging of one frame (VRT_EXCHANGE_PEER_TILES)
+size_t stage_offset(const vrt_ctx* c, int parity) { return 2 * c->fb_bytes + kPeerFlagBytes + 2 * cost_bytes(c) + (size_t)parity * stage_bytes(c); }
 
 void fill_params(const vrt_ctx* c, const vrt_camera* cam, const vrt_sun* sun, TraceParams& P) {
     std::memset(&P, 0, sizeof(P));
@@ -288,10 +296,16 @@ void fill_params(const vrt_ctx* c, const vrt_camera* cam, const vrt_sun* sun, Tr
     P.vec_store_ok = (cam->image_width % 4 == 0) && ((reinterpret_cast<uintptr_t>(c->d_fb) & 15u) == 0);
     P.n_peers = 0;
     P.one = 1u;
-    if (c->world > 1 && (c->exchange_mode == VRT_EXCHANGE_PEER_STORE || c->exchange_mode == VRT_EXCHANGE_PEER_FLAGS || c->exchange_mode == VRT_EXCHANGE_PEER_PUSH) && c->peers_open) {
+    if (c->world > 1 && (c->exchange_mode == VRT_EXCHANGE_PEER_STORE || c->exchange_mode == VRT_EXCHANGE_PEER_FLAGS || c->exchange_mode == VRT_EXCHANGE_PEER_PUSH ||
+                         c->exchange_mode == VRT_EXCHANGE_PEER_TILES) && c->peers_open) {
         const size_t slot_words = (c->d_fb == c->d_fb_ring1) ? c->fb_bytes / 4 : 0;  // same ring slot on every rank
         for (int r = 0; r < c->world; r++)
             if (r != c->rank) P.peer_fb[P.n_peers++] = static_cast<uint32_t*>(c->peer_fb[r]) + slot_words;
+        if (c->exchange_mode == VRT_EXCHANGE_PEER_TILES && tiles_exchange_ok(c)) {
+            // tile-major exchange: every rank's staging buffer of this frame's parity, this rank's own included (peer_fb[rank] is d_fb_own)
+            for (int r = 0; r < c->world; r++)
+                P.stage[P.n_stage++] = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(c->peer_fb[r]) + stage_offset(c, (int)(c->stage_seq & 1u)));
+        }
     }
     // tile schedule (tuned kernel, not the counting / AOV variant)
     if (c->sched_mode != VRT_SCHED_STATIC && !(c->cfg.flags & (VRT_FLAG_AOV | VRT_FLAG_BASELINE))) {
@@ -422,8 +436,8 @@ int vrt_init(vrt_ctx** out_ctx, const vrt_config* cfg) {
     INIT_CUDA(cudaMalloc(&ctx->d_occupancy, ctx->n_occupancy));
     INIT_CUDA(cudaMalloc(&ctx->d_start_indices, ctx->n_start_indices * 4));
     INIT_CUDA(cudaMalloc(&ctx->d_material_indices, ctx->n_material_indices));
-    // slot 0 + slot 1 of the frame ring + barrier flags + the two tile-cost arrays: one allocation = one IPC handle
-    const size_t shared_bytes = 2 * ctx->fb_bytes + kPeerFlagBytes + 2 * cost_bytes(ctx);
+    // slot 0 + slot 1 of the frame ring + barrier flags + the two tile-cost arrays + two tile-major staging frames: one allocation = one IPC handle
+    const size_t shared_bytes = 2 * ctx->fb_bytes + kPeerFlagBytes + 2 * cost_bytes(ctx) + 2 * stage_bytes(ctx);
     INIT_CUDA(cudaMalloc(&ctx->d_fb_own, shared_bytes));
     ctx->d_fb_ring1 = ctx->d_fb_own + ctx->fb_bytes / 4;
     ctx->d_cost[0] = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(ctx->d_fb_own) + 2 * ctx->fb_bytes + kPeerFlagBytes);
@@ -556,7 +570,8 @@ namespace {
 
 bool peer_mode(const vrt_ctx* c) {
     return c->world > 1 && c->peers_open &&
-           (c->exchange_mode == VRT_EXCHANGE_PEER_STORE || c->exchange_mode == VRT_EXCHANGE_PEER_FLAGS || c->exchange_mode == VRT_EXCHANGE_PEER_PUSH);
+           (c->exchange_mode == VRT_EXCHANGE_PEER_STORE || c->exchange_mode == VRT_EXCHANGE_PEER_FLAGS || c->exchange_mode == VRT_EXCHANGE_PEER_PUSH ||
+            c->exchange_mode == VRT_EXCHANGE_PEER_TILES);
 }
 bool scattered(const vrt_ctx* c) { return c->sched_mode == VRT_SCHED_DEAL || c->sched_mode == VRT_SCHED_SHARED; }
 bool owns_fb(const vrt_ctx* c) { return c->d_fb == c->d_fb_own || c->d_fb == c->d_fb_ring1; }
@@ -592,7 +607,7 @@ int trace_frame(vrt_ctx* ctx, const vrt_camera* camera, const vrt_sun* sun, bool
     if (camera->samples_per_pixel < 1) return fail(ctx, VRT_E_INVALID, "vrt_trace: samples_per_pixel < 1");
     const bool gather = ctx->world > 1 && ctx->exchange_mode == VRT_EXCHANGE_ALLGATHER;
     if (ctx->world > 1 && !ctx->comm && ctx->exchange_mode != VRT_EXCHANGE_PEER_FLAGS && ctx->exchange_mode != VRT_EXCHANGE_PEER_PUSH &&
-        ctx->exchange_mode != VRT_EXCHANGE_HOST)  // none of these needs a communicator
+        ctx->exchange_mode != VRT_EXCHANGE_PEER_TILES && ctx->exchange_mode != VRT_EXCHANGE_HOST)  // none of these needs a communicator
         return fail(ctx, VRT_E_STATE, "vrt_trace: world > 1 but vrt_comm_init has not been called");
     if (scattered(ctx) && ctx->world > 1 && !peer_mode(ctx))
         return fail(ctx, VRT_E_STATE, "vrt_trace: VRT_SCHED_DEAL / SHARED scatter a rank's tiles over the image and need a peer-store exchange mode");
@@ -683,7 +698,7 @@ int trace_frame(vrt_ctx* ctx, const vrt_camera* camera, const vrt_sun* sun, bool
         // barrier also waits until this rank has copied that slot's previous frame to its host (pipelined frames).
         const int other = (int)((ctx->ring_seq + 1u) & 1u);
         if (ring && ctx->slot_used[other]) VRT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[other], 0));
-        if (ctx->exchange_mode == VRT_EXCHANGE_PEER_FLAGS || ctx->exchange_mode == VRT_EXCHANGE_PEER_PUSH) {
+        if (ctx->exchange_mode == VRT_EXCHANGE_PEER_FLAGS || ctx->exchange_mode == VRT_EXCHANGE_PEER_PUSH || ctx->exchange_mode == VRT_EXCHANGE_PEER_TILES) {
             uint32_t* flags[8] = {nullptr};
             for (int r = 0; r < ctx->world; r++) flags[r] = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(ctx->peer_fb[r]) + 2 * ctx->fb_bytes);
             VRT_CUDA(ctx, launch_peer_barrier(flags, (uint32_t)ctx->rank, (uint32_t)ctx->world, ++ctx->barrier_frame, ctx->h_barrier_error, ctx->stream, &info));
@@ -691,6 +706,11 @@ int trace_frame(vrt_ctx* ctx, const vrt_camera* camera, const vrt_sun* sun, bool
             const ncclResult_t r = g_nccl.AllReduce(ctx->d_barrier, ctx->d_barrier, 1, ncclInt32, ncclSum, ctx->comm, ctx->stream);
             if (r != ncclSuccess) return fail(ctx, VRT_E_NCCL, "ncclAllReduce failed: %s", g_nccl.GetErrorString(r));
         }
+    }
+    if (P.n_stage) {  // every rank's tiles of this frame are in this rank's staging buffer now: into the row-major framebuffer
+        const uint32_t* mine = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(ctx->d_fb_own) + stage_offset(ctx, (int)(ctx->stage_seq & 1u)));
+        VRT_CUDA(ctx, launch_untile(mine, ctx->d_fb, ctx->cfg.width, ctx->cfg.height, P.vec_store_ok != 0u, ctx->stream, &info));
+        ctx->stage_seq++;
     }
     if (P.tile_order) {
         // every `interval` frames (and after the first): sort the costs this frame reported into the next frames' order.  Dealt
@@ -1236,16 +1256,16 @@ int vrt_comm_open_peers(vrt_ctx* ctx, int rank, int world, const uint8_t* handle
 
 int vrt_comm_set_exchange(vrt_ctx* ctx, uint32_t mode) {
     if (!ctx) return VRT_E_INVALID;
-    if (mode > VRT_EXCHANGE_PEER_PUSH) return fail(ctx, VRT_E_INVALID, "vrt_comm_set_exchange: unknown mode %u", mode);
-    if ((mode == VRT_EXCHANGE_PEER_STORE || mode == VRT_EXCHANGE_PEER_FLAGS || mode == VRT_EXCHANGE_PEER_PUSH) && !ctx->peers_open)
+    if (mode > VRT_EXCHANGE_PEER_TILES) return fail(ctx, VRT_E_INVALID, "vrt_comm_set_exchange: unknown mode %u", mode);
+    if ((mode == VRT_EXCHANGE_PEER_STORE || mode == VRT_EXCHANGE_PEER_FLAGS || mode == VRT_EXCHANGE_PEER_PUSH || mode == VRT_EXCHANGE_PEER_TILES) && !ctx->peers_open)
         return fail(ctx, VRT_E_STATE, "vrt_comm_set_exchange: call vrt_comm_open_peers first");
-    if ((mode == VRT_EXCHANGE_PEER_FLAGS || mode == VRT_EXCHANGE_PEER_PUSH) && !ctx->h_barrier_error) {
+    if ((mode == VRT_EXCHANGE_PEER_FLAGS || mode == VRT_EXCHANGE_PEER_PUSH || mode == VRT_EXCHANGE_PEER_TILES) && !ctx->h_barrier_error) {
         VRT_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
         VRT_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_barrier_error), sizeof(int), cudaHostAllocMapped));
         *ctx->h_barrier_error = 0;
     }
     ctx->exchange_mode = mode;
-    if ((mode == VRT_EXCHANGE_PEER_FLAGS || mode == VRT_EXCHANGE_PEER_PUSH) && ctx->world > 1) {
+    if ((mode == VRT_EXCHANGE_PEER_FLAGS || mode == VRT_EXCHANGE_PEER_PUSH || mode == VRT_EXCHANGE_PEER_TILES) && ctx->world > 1) {
         // one round of the flag barrier now (every rank makes this call): the first touch of each peer mapping happens here, and
         // all ranks leave set-up together
         uint32_t* flags[8] = {nullptr};

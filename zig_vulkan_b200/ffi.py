@@ -21,6 +21,7 @@ VRT_EXCHANGE_PEER_STORE = 1
 VRT_EXCHANGE_PEER_FLAGS = 2
 VRT_EXCHANGE_HOST = 3
 VRT_EXCHANGE_PEER_PUSH = 4
+VRT_EXCHANGE_PEER_TILES = 5
 VRT_SCHED_STATIC, VRT_SCHED_LPT, VRT_SCHED_DEAL, VRT_SCHED_SHARED = 0, 1, 2, 3
 VRT_NCCL_ID_BYTES = 128
 VRT_IPC_HANDLE_BYTES = 64
