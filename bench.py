@@ -278,10 +278,11 @@ class Rig:
         args = self.args
         if args.baseline_kernel:
             return ("allgather" if self.world > 1 else "none", "static"), {}
-        exchanges = (["allgather", "peerflags", "peertiles"] if args.exchange == "auto" else [args.exchange]) if self.world > 1 else ["none"]
+        # (peerpush, peertiles and the NCCL-barrier variant `peer` lose to peerflags at every N measured — profiles/README.md — and stay selectable by name)
+        exchanges = (["allgather", "peerflags"] if args.exchange == "auto" else [args.exchange]) if self.world > 1 else ["none"]
         cands = []
         for ex in exchanges:
-            for sc in (["static", "lpt", "deal", "shared"] if args.schedule == "auto" else [args.schedule]):
+            for sc in (["static", "lpt", "deal"] if args.schedule == "auto" else [args.schedule]):  # (`shared` loses at every N: by name only)
                 if sc in ("deal", "shared") and (self.world == 1 or ex == "allgather" or not ctx.interleaved):
                     continue  # these need a peer exchange (a rank's tiles are scattered over the image) and are pointless on one GPU
                 cands.append((ex, sc))
