@@ -1,6 +1,6 @@
 #!/bin/bash
 # Final 1-GPU visit of the round: tests, smoke, bench lines (C3 default, C2, C4, baseline kernel, reference arm), ncu launch list + full
-# captures (trace kernel on C3, general path on the reference default workload, present pass), tile statistics of the final kernel.
+# captures (trace kernel on C3, present pass), tile statistics and partition simulation of the final kernel.
 mkdir -p gpurun_out
 timeout -k 5 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_gpu.log; tail -4 gpurun_out/pytest_gpu.log
 timeout -k 5 120 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/smoke.log
