@@ -236,7 +236,8 @@ int vrt_trace_rays_host(vrt_ctx* ctx, const vrt_ray* rays_host, vrt_ray_hit* hit
 int vrt_read_aov(vrt_ctx* ctx, vrt_aov* aov_host, size_t count);
 int vrt_get_counters(vrt_ctx* ctx, vrt_counters* out);
 
-/* Milliseconds the device spent in the last vrt_trace (kernels + exchange), CUDA events on ctx's stream. */
+/* Milliseconds the device spent in the last vrt_trace / vrt_trace_to_host (kernels + exchange), CUDA events on ctx's stream.
+ * (Pipelined frames, vrt_trace_to_host_async, are not timed.) */
 int vrt_last_trace_ms(vrt_ctx* ctx, float* out_ms);
 /* The part of it before the exchange: (derived-structure rebuild +) the trace kernel alone.  exchange = total - this. */
 int vrt_last_trace_kernel_ms(vrt_ctx* ctx, float* out_ms);

@@ -605,6 +605,7 @@ int trace_frame(vrt_ctx* ctx, const vrt_camera* camera, const vrt_sun* sun, bool
         return fail(ctx, VRT_E_INVALID, "vrt_trace: camera image %ux%u != target image %ux%u", camera->image_width, camera->image_height,
                     ctx->cfg.width, ctx->cfg.height);
     if (camera->samples_per_pixel < 1) return fail(ctx, VRT_E_INVALID, "vrt_trace: samples_per_pixel < 1");
+    const bool pipelined = ring;  // vrt_trace_to_host_async: nobody can ask for this frame's device time, so its three timing events are not recorded
     const bool gather = ctx->world > 1 && ctx->exchange_mode == VRT_EXCHANGE_ALLGATHER;
     if (ctx->world > 1 && !ctx->comm && ctx->exchange_mode != VRT_EXCHANGE_PEER_FLAGS && ctx->exchange_mode != VRT_EXCHANGE_PEER_PUSH &&
         ctx->exchange_mode != VRT_EXCHANGE_PEER_TILES && ctx->exchange_mode != VRT_EXCHANGE_HOST)  // none of these needs a communicator
@@ -635,7 +636,7 @@ int trace_frame(vrt_ctx* ctx, const vrt_camera* camera, const vrt_sun* sun, bool
     const bool aov = (ctx->cfg.flags & VRT_FLAG_AOV) != 0;
     const TraceKernel which = (ctx->cfg.flags & VRT_FLAG_BASELINE) ? KERNEL_REF : KERNEL_TUNED;
 
-    VRT_CUDA(ctx, cudaEventRecord(ctx->ev_begin, ctx->stream));
+    if (!pipelined) VRT_CUDA(ctx, cudaEventRecord(ctx->ev_begin, ctx->stream));
     if (which == KERNEL_TUNED && (ctx->accel_dirty || ctx->occ_dirty)) {  // (vrt_trace_rays does the same)
         // Uploads changed statuses / indices / occupancy: rebuild the derived structures before tracing.  Stream order gives
         // upload -> build -> trace, where the reference has no barrier at all between its staging copy and the next dispatch
@@ -675,7 +676,7 @@ int trace_frame(vrt_ctx* ctx, const vrt_camera* camera, const vrt_sun* sun, bool
     } else {
         VRT_CUDA(ctx, launch_trace(P, which, aov, ctx->stream, &info));
     }
-    VRT_CUDA(ctx, cudaEventRecord(ctx->ev_kernel_end, ctx->stream));
+    if (!pipelined) VRT_CUDA(ctx, cudaEventRecord(ctx->ev_kernel_end, ctx->stream));
     if (push) VRT_CUDA(ctx, launch_push_tiles(P, ctx->stream, &info));
 
     if (gather) {
@@ -719,8 +720,10 @@ int trace_frame(vrt_ctx* ctx, const vrt_camera* camera, const vrt_sun* sun, bool
             VRT_CUDA(ctx, launch_sched_sort(P.tile_cost, ctx->sched_tiles, ctx->d_order, ctx->d_sched_scratch, ctx->stream, &info));
         ctx->sched_frames++;
     }
-    VRT_CUDA(ctx, cudaEventRecord(ctx->ev_end, ctx->stream));
-    ctx->timing_valid = true;
+    if (!pipelined) {
+        VRT_CUDA(ctx, cudaEventRecord(ctx->ev_end, ctx->stream));
+        ctx->timing_valid = true;
+    }
     ctx->last_launches = info.launches;
     if (ring) ctx->ring_seq++;
     return VRT_OK;
