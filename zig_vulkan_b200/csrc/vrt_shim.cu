@@ -1027,6 +1027,9 @@ int vrt_trace_rays(vrt_ctx* ctx, const vrt_ray* rays_device, vrt_ray_hit* hits_d
     std::memset(&sun, 0, sizeof(sun));
     TraceParams P;
     fill_params(ctx, &cam, &sun, P);
+    // the ray list is this context's own: its private queue, no tile schedule, no peers
+    P.tile_counter = ctx->d_tile_counter, P.queue_world = 0u;
+    P.tile_order = nullptr, P.tile_cost = nullptr, P.n_cost_peers = 0u, P.n_peers = 0u, P.n_stage = 0u;
     LaunchInfo info = {0u};
     if (ctx->accel_dirty || ctx->occ_dirty) {
         const int rcb = rebuild_accel(ctx, P, &info);
