@@ -156,7 +156,10 @@ def _ctx_with_frame(img):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("params", [DEFAULT, (1, 0.6, 1.5, 20.0), (64, 0.9, 2.5, 4.0), (255, 0.5, 1.0, 10.0), (0, 0.6, 1.5, 20.0)])
+# the first six take the padded fast path (whole hue tolerance 2..64, sample offsets within the 16-texel border: default 20, even,
+# odd, 255 samples, none); the last three the general kernel (fractional tolerance, tolerance 1, offsets beyond the border)
+@pytest.mark.parametrize("params", [DEFAULT, (1, 0.6, 1.5, 20.0), (64, 0.9, 2.5, 4.0), (255, 0.5, 1.0, 10.0), (0, 0.6, 1.5, 20.0), (20, 0.6, 1.5, 3.0),
+                                    (20, 0.6, 1.5, 2.5), (12, 0.6, 1.5, 1.0), (30, 0.6, 8.0, 20.0)])
 @pytest.mark.parametrize("size", [(160, 90, None, None), (160, 90, 240, 135), (67, 41, 50, 29), (1, 1, 3, 2)])
 def test_cuda_denoise_is_bit_exact(params, size):
     w, h, ow, oh = size

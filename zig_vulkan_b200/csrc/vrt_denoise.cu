@@ -7,6 +7,12 @@
 // times per sample.  The per-sample work left is the bilinear fetch (four 128-bit loads), one sqrt + one divide for
 // normalize / length, and two pow.
 //
+// Fast path (denoise_padded_kernel — every configuration whose largest sample offset stays inside kDenoisePad texels and whose hue
+// tolerance is a whole number 2..64, i.e. the reference's defaults): the decoded image carries a kDenoisePad-texel border filled by
+// the sampler's repeat addressing, so a bilinear tap is one index computation and four loads at fixed offsets — no wrap selects,
+// no second row / column index — and both pow are multiplication chains without the range checks (max(a,0)^n by products gives the
+// guarded results by itself: 0 for a < FLT_MIN, inf for inf, NaN for NaN).  Everything else takes denoise_kernel, the general one.
+//
 // Arithmetic discipline = the oracle's (oracle/vrt_oracle_denoise.cpp header): FP32, no contraction (--fmad=false) except
 // the explicit fmaf of det_log2f / det_exp2f, IEEE sqrt and divide, FP32 bilinear weights.  Bound: FP32 / SFU issue, not HBM
 // (algorithmic traffic is 4 B read + 4 B written per pixel).
@@ -204,19 +210,116 @@ __global__ void __launch_bounds__(kDnBlockX* kDnBlockY) denoise_kernel(const flo
     out[(size_t)oy * out_w + ox] = bgra ? (b | (g << 8) | (r << 16) | 0xff000000u) : (r | (g << 8) | (b << 16) | 0xff000000u);
 }
 
+// UNORM decode into the padded image: (w + 2 pad) x (h + 2 pad) texels, padded texel (px, py) = image texel ((px - pad) mod w,
+// (py - pad) mod h) — the sampler's repeat addressing (Pipeline.zig:193-212) applied once per border texel instead of per tap.
+__global__ void __launch_bounds__(256) decode_unorm_padded_kernel(const uint32_t* __restrict__ img, float4* __restrict__ out, int w, int h, int pad) {
+    const int pw = w + 2 * pad, ph = h + 2 * pad;
+    const int px = (int)(blockIdx.x * 256 + threadIdx.x), py = (int)blockIdx.y;
+    if (px >= pw || py >= ph) return;
+    int sx = (px - pad) % w, sy = (py - pad) % h;
+    sx = sx < 0 ? sx + w : sx, sy = sy < 0 ? sy + h : sy;
+    const uint32_t p = __ldg(img + (size_t)sy * w + sx);
+    out[(size_t)py * pw + px] = make_float4((float)(p & 255u) / 255.0f, (float)((p >> 8) & 255u) / 255.0f, (float)((p >> 16) & 255u) / 255.0f, (float)(p >> 24) / 255.0f);
+}
+
+// The table of denoise_table_kernel, one float4 per tap: offset x, offset y, the radial term cubed (:57, same two products).
+__global__ void __launch_bounds__(kDnMaxSamples + 1) denoise_pack_table_kernel(const float* __restrict__ table, float4* __restrict__ packed, int samples) {
+    const int tid = (int)threadIdx.x;
+    if (tid <= samples) {
+        float influence = table[2 * (kDnMaxSamples + 1) + tid];
+        influence *= influence * influence;
+        packed[tid] = make_float4(table[tid], table[kDnMaxSamples + 1 + tid], influence, 0.0f);
+    }
+}
+
+// max(a, 0)^n for a whole n in 2..64 (image.frag:29 with a whole exponent): a NaN stays a NaN through the products, a < FLT_MIN
+// squares to 0, inf stays inf — gpow's guarded results without the guards
+template <unsigned N>
+__device__ __forceinline__ float gpow_whole(float a, unsigned n) {
+    a = a < 0.0f ? 0.0f : a;
+    return det_powif(a, N ? N : n);
+}
+
+// texture(imageSampler, uv).rgb on the padded image: `origin` = padded texel (pad, pad), `stride` = padded row length
+__device__ __forceinline__ Rgb sample_padded(const float4* __restrict__ origin, int stride, float fw, float fh, float u, float v) {
+    const float x = u * fw - 0.5f, y = v * fh - 0.5f;
+    const float fx = floorf(x), fy = floorf(y);
+    const float a = x - fx, b = y - fy;
+    const float4* p = origin + ((int)fy * stride + (int)fx);
+    const float4 t00 = __ldg(p), t10 = __ldg(p + 1), t01 = __ldg(p + stride), t11 = __ldg(p + stride + 1);
+    const float w00 = (1.0f - a) * (1.0f - b), w10 = a * (1.0f - b), w01 = (1.0f - a) * b, w11 = a * b;
+    Rgb c;
+    c.x = ((w00 * t00.x + w10 * t10.x) + w01 * t01.x) + w11 * t11.x;
+    c.y = ((w00 * t00.y + w10 * t10.y) + w01 * t01.y) + w11 * t11.y;
+    c.z = ((w00 * t00.z + w10 * t10.z) + w01 * t01.z) + w11 * t11.z;
+    return c;
+}
+
+// HUE = the hue tolerance when it is the default 20 (its product chain unrolled), 0 = any whole exponent 2..64 (hue_n)
+template <unsigned HUE>
+__global__ void __launch_bounds__(kDnBlockX* kDnBlockY) denoise_padded_kernel(const float4* __restrict__ origin, int stride, int w, int h, int samples, unsigned hue_n,
+                                                                               uint32_t* __restrict__ out, uint32_t out_w, uint32_t out_h, uint32_t bgra,
+                                                                               const float4* __restrict__ packed) {
+    __shared__ float4 s_tap[kDnMaxSamples + 1];
+    const int tid = threadIdx.y * kDnBlockX + threadIdx.x;
+    if (tid <= samples) s_tap[tid] = packed[tid];
+    __syncthreads();
+
+    const uint32_t ox = blockIdx.x * kDnBlockX + threadIdx.x, oy = blockIdx.y * kDnBlockY + threadIdx.y;
+    if (ox >= out_w || oy >= out_h) return;
+    const float fw = (float)w, fh = (float)h;
+    const float uvx = ((float)ox + 0.5f) / (float)out_w, uvy = ((float)oy + 0.5f) / (float)out_h;
+
+    const Rgb center = sample_padded(origin, stride, fw, fh, uvx, uvy);                                 // :38
+    const float center_sat = sqrtf((center.x * center.x + center.y * center.y) + center.z * center.z);  // :40
+    const float center_inv = 1.0f / center_sat;                                                         // :39 normalize
+    const float cnx = center.x * center_inv, cny = center.y * center_inv, cnz = center.z * center_inv;
+    const float abs_center_sat = fabsf(center_sat);  // length(float), :63
+    float dx = 0.0f, dy = 0.0f, dz = 0.0f, influence_sum = 0.0f;
+    for (int k = 0; k <= samples; k++) {  // :47
+        const float4 tap = s_tap[k];
+        const Rgb c = sample_padded(origin, stride, fw, fh, uvx + tap.x, uvy + tap.y);  // :55
+        float len, inv;
+        safe_len_inv((c.x * c.x + c.y * c.y) + c.z * c.z, len, inv);
+        const float d = (cnx * (c.x * inv) + cny * (c.y * inv)) + cnz * (c.z * inv);
+        const float influence = tap.z * (gpow_whole<HUE>(0.5f + 0.5f * d, hue_n) * gpow_whole<8>(1.0f - fabsf(len - abs_center_sat), 8u));  // :57-64
+        influence_sum += influence;                                                                                                       // :66
+        dx += c.x * influence, dy += c.y * influence, dz += c.z * influence;                                                              // :67
+    }
+    const uint32_t r = dn_unorm8(dx / influence_sum), g = dn_unorm8(dy / influence_sum), b = dn_unorm8(dz / influence_sum);  // :70, :77
+    out[(size_t)oy * out_w + ox] = bgra ? (b | (g << 8) | (r << 16) | 0xff000000u) : (r | (g << 8) | (b << 16) | 0xff000000u);
+}
+
 }  // namespace
 
 cudaError_t launch_denoise(const uint32_t* image, float4* decoded, uint32_t width, uint32_t height, const vrt_denoise_params& params, uint32_t* out,
                            uint32_t out_width, uint32_t out_height, bool bgra, cudaStream_t stream, LaunchInfo* info) {
     const size_t n = (size_t)width * height;
-    decode_unorm_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(image, decoded, n);
-    float* table = reinterpret_cast<float*>(decoded + n);  // 3 x 256 floats behind the decoded image (kDenoiseScratchTail)
-    denoise_table_kernel<<<1, kDnMaxSamples + 1, 0, stream>>>((int)width, (int)height, params, table);
-    if (info) info->launches += 2;
     const dim3 block(kDnBlockX, kDnBlockY);
     const dim3 grid((out_width + kDnBlockX - 1) / kDnBlockX, (out_height + kDnBlockY - 1) / kDnBlockY);
     // largest sample offset in input texels (:51): |pixelMultiplier| * sqrt(samples) * 0.5, plus the bilinear footprint and slack
     const float reach = fabsf(params.pixel_multiplier) * sqrtf((float)params.samples) * 0.5f + 3.0f;
+    const float hue = params.inverse_hue_tolerance;
+    const bool padded = reach <= (float)kDenoisePad && hue >= 2.0f && hue <= 64.0f && hue == floorf(hue) && params.samples >= 0 && params.samples <= kDnMaxSamples;
+    if (padded) {
+        const int pw = (int)width + 2 * kDenoisePad, ph = (int)height + 2 * kDenoisePad;
+        float* table = reinterpret_cast<float*>(decoded + (size_t)pw * ph);  // kDenoiseScratchTail float4 behind the padded image: 3 x 256 floats, then 256 packed taps
+        float4* packed = decoded + (size_t)pw * ph + 192;
+        decode_unorm_padded_kernel<<<dim3((unsigned)((pw + 255) / 256), (unsigned)ph), 256, 0, stream>>>(image, decoded, (int)width, (int)height, kDenoisePad);
+        denoise_table_kernel<<<1, kDnMaxSamples + 1, 0, stream>>>((int)width, (int)height, params, table);
+        denoise_pack_table_kernel<<<1, kDnMaxSamples + 1, 0, stream>>>(table, packed, params.samples);
+        const float4* origin = decoded + (size_t)kDenoisePad * pw + kDenoisePad;
+        if (hue == 20.0f)
+            denoise_padded_kernel<20><<<grid, block, 0, stream>>>(origin, pw, (int)width, (int)height, params.samples, 20u, out, out_width, out_height, bgra ? 1u : 0u, packed);
+        else
+            denoise_padded_kernel<0><<<grid, block, 0, stream>>>(origin, pw, (int)width, (int)height, params.samples, (unsigned)hue, out, out_width, out_height, bgra ? 1u : 0u, packed);
+        if (info) info->launches += 4;
+        return cudaGetLastError();
+    }
+    decode_unorm_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(image, decoded, n);
+    float* table = reinterpret_cast<float*>(decoded + n);  // 3 x 256 floats behind the decoded image (kDenoiseScratchTail)
+    denoise_table_kernel<<<1, kDnMaxSamples + 1, 0, stream>>>((int)width, (int)height, params, table);
+    if (info) info->launches += 2;
     const bool near = reach < (float)(width < height ? width : height);  // false also for a NaN multiplier
     if (near)
         denoise_kernel<true><<<grid, block, 0, stream>>>(decoded, (int)width, (int)height, params, out, out_width, out_height, bgra ? 1u : 0u, table);

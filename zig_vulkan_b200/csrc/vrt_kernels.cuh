@@ -50,8 +50,11 @@ cudaError_t launch_trace_rays(const TraceParams& P, const vrt_ray* rays, vrt_ray
 cudaError_t launch_deinterleave(const uint32_t* gathered, uint32_t* frame, uint32_t width, uint32_t height, uint32_t world, uint32_t strips_max,
                                 cudaStream_t stream, LaunchInfo* info);
 // image.frag:31-79 over `image` (width x height RGBA8, linear / repeat sampling) -> out (out_width x out_height RGBA8 or BGRA8); vrt_denoise.cu.
-// decoded: width * height + kDenoiseScratchTail float4 of scratch (the UNORM-decoded image, then the per-launch sample table).
-constexpr size_t kDenoiseScratchTail = 192;  // 3 x 256 floats
+// decoded: denoise_scratch_float4(width, height) float4 of scratch (the UNORM-decoded image with its repeat border of kDenoisePad
+// texels, then the per-launch sample tables).
+constexpr int kDenoisePad = 16;
+constexpr size_t kDenoiseScratchTail = 192 + 256;  // 3 x 256 floats, then 256 packed taps
+inline size_t denoise_scratch_float4(uint32_t width, uint32_t height) { return ((size_t)width + 2 * kDenoisePad) * ((size_t)height + 2 * kDenoisePad) + kDenoiseScratchTail; }
 cudaError_t launch_denoise(const uint32_t* image, float4* decoded, uint32_t width, uint32_t height, const vrt_denoise_params& params, uint32_t* out,
                            uint32_t out_width, uint32_t out_height, bool bgra, cudaStream_t stream, LaunchInfo* info);
 // VRT_EXCHANGE_PEER_PUSH: copy the tiles P describes (as the trace launch would enumerate them) from P.fb into every P.peer_fb.

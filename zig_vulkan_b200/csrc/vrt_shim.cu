@@ -969,7 +969,7 @@ int vrt_denoise(vrt_ctx* ctx, const vrt_denoise_params* params, uint32_t out_wid
         }
         ctx->dn_width = out_width, ctx->dn_height = out_height;
     }
-    if (!ctx->d_dn_decoded && cudaMalloc(&ctx->d_dn_decoded, ((size_t)ctx->cfg.width * ctx->cfg.height + kDenoiseScratchTail) * sizeof(float4)) != cudaSuccess) {
+    if (!ctx->d_dn_decoded && cudaMalloc(&ctx->d_dn_decoded, denoise_scratch_float4(ctx->cfg.width, ctx->cfg.height) * sizeof(float4)) != cudaSuccess) {
         cudaGetLastError();
         return fail(ctx, VRT_E_OOM, "vrt_denoise: cannot allocate the %ux%u float4 scratch image", ctx->cfg.width, ctx->cfg.height);
     }
