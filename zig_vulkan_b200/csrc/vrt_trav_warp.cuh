@@ -39,6 +39,9 @@ constexpr unsigned kFullMask = 0xffffffffu;
 
 // -DVRT_TILE_STATS=1 (analysis builds only, tools/gpu_tilestats.py): per-warp counters of where a tile's instructions go —
 // rounds, step-loop iterations, brick phases, voxel-loop iterations — kept in shared memory, flushed per tile by the trace kernel.
+#ifndef VRT_PHASE_WAIT_ALL
+#define VRT_PHASE_WAIT_ALL 0  // A/B: 1 = round 1's policy, the brick phase starts only when no ray of the warp is marching any more
+#endif
 #ifndef VRT_TILE_STATS
 #define VRT_TILE_STATS 0
 #endif
@@ -160,7 +163,7 @@ VRT_DI int brick_hit_warp4(const TraceParams& P, const Ray& r, bool ignore_test,
 #if VRT_TILE_STATS
     {
         const uint32_t mx = __reduce_max_sync(lanes, my_iters);
-        if ((threadIdx.x & 31u) == (uint32_t)(__ffs((int)lanes) - 1)) warp_stats()[3] += mx, warp_stats()[6] += (uint32_t)__popc(__ballot_sync(__activemask(), found >= 0));
+        if ((threadIdx.x & 31u) == (uint32_t)(__ffs((int)lanes) - 1)) warp_stats()[3] += mx;
     }
 #endif
     if (found >= 0) {
@@ -429,6 +432,12 @@ VRT_DI bool grid_hit_warp(const TraceParams& P, const Ray& r, bool active, bool 
             VRT_STAT(0, 1u);                                           // rounds
             VRT_STAT(1, k);                                            // step-loop iterations
             VRT_STAT(4, (uint32_t)__popc(__ballot_sync(kFullMask, d != kIdle)));  // lanes marching in this round
+            VRT_STAT(6, (uint32_t)__popc(__ballot_sync(kFullMask, mode == kParked)));  // lanes waiting in it for the brick phase
+            // A round in which a ray parked is the last one before the brick phase: parked rays do not wait for the others to park
+            // too.  (Waiting for all of them — fewer, fuller brick phases — cost the expensive tiles 2-3x their rounds: each
+            // superstep lasted as long as its slowest ray, profiles/r02_tile_statistics_C3.txt.)  A scheduling choice only: every
+            // ray visits the same cells either way.
+            const bool to_bricks = !VRT_PHASE_WAIT_ALL && __any_sync(kFullMask, mode == kParked);
             const bool on = d != kIdle;
             if (COUNT) {
                 for (uint32_t i = 1; i < k; i++) {  // k-1 steps onto cells known to be empty and inside
@@ -462,6 +471,7 @@ VRT_DI bool grid_hit_warp(const TraceParams& P, const Ray& r, bool active, bool 
             const int before = idx;
             march_step(sx, sy, sz, fdx, fdy, fdz, fsx, fsy, fsz, idx, one);
             if (on) last_stride = idx - before;
+            if (to_bricks) break;
         }
         // ---- phase B: the parked rays test their bricks together (:329-342)
         const unsigned parked_lanes = __ballot_sync(kFullMask, mode == kParked);
