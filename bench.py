@@ -37,9 +37,8 @@ def parse_args():
                     help="N > 1: fused peer stores from the trace kernel (frame barrier = NCCL 4-byte all-reduce, or peer flag words: "
                          "peerflags), or an NCCL all-gather after it; auto = every combination of exchange and schedule is timed for a few "
                          "frames on this box and the fastest one runs the timed region")
-    ap.add_argument("--schedule", default="auto",
-                    help="tile order: static (bottom-up), lpt (cost-sorted, longest first), lpt+N (and the most expensive N permille of the tiles traced "
-                         "row by row on four warps), deal / shared (cost-sorted and dealt across / pulled by the ranks; peer exchange modes), auto")
+    ap.add_argument("--schedule", default="auto", choices=["auto", "static", "lpt", "deal", "shared"],
+                    help="tile order: static bottom-up, cost-sorted (longest first), or cost-sorted and dealt across the ranks (peer exchange modes)")
     ap.add_argument("--partition", default="interleave", choices=["interleave", "slab"], help="N > 1: 4-row strips round-robin, or one row slab per rank")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="only the headline measurement (no sweep / REF / C5 / denoise / explicit rays / edit frames)")
@@ -270,10 +269,7 @@ class Rig:
         if self.world > 1:
             ctx.comm_set_exchange({"allgather": ffi.VRT_EXCHANGE_ALLGATHER, "peer": ffi.VRT_EXCHANGE_PEER_STORE, "peerflags": ffi.VRT_EXCHANGE_PEER_FLAGS,
                                    "peerpush": ffi.VRT_EXCHANGE_PEER_PUSH, "peertiles": ffi.VRT_EXCHANGE_PEER_TILES}[exchange])
-        # "lpt+N": cost-sorted order with the most expensive N permille of the tiles traced row by row on four warps (vrt_set_tile_split)
-        name, _, permille = schedule.partition("+")
-        ctx.set_schedule({"static": ffi.VRT_SCHED_STATIC, "lpt": ffi.VRT_SCHED_LPT, "deal": ffi.VRT_SCHED_DEAL, "shared": ffi.VRT_SCHED_SHARED}[name], interval)
-        ctx.set_tile_split(int(permille) if permille else 0)
+        ctx.set_schedule({"static": ffi.VRT_SCHED_STATIC, "lpt": ffi.VRT_SCHED_LPT, "deal": ffi.VRT_SCHED_DEAL, "shared": ffi.VRT_SCHED_SHARED}[schedule], interval)
 
     def choose_mode(self, ctx, cam, sun, want_crc=None):
         """Exchange x schedule by measurement on this box: each candidate runs 4 + 12 flushed frames, the smallest max-over-ranks mean wins.
@@ -286,7 +282,7 @@ class Rig:
         exchanges = (["allgather", "peerflags"] if args.exchange == "auto" else [args.exchange]) if self.world > 1 else ["none"]
         cands = []
         for ex in exchanges:
-            for sc in (["static", "lpt", "lpt+30", "lpt+150", "deal"] if args.schedule == "auto" else [args.schedule]):  # (`shared` loses at every N: by name only)
+            for sc in (["static", "lpt", "deal"] if args.schedule == "auto" else [args.schedule]):  # (`shared` loses at every N: by name only)
                 if sc in ("deal", "shared") and (self.world == 1 or ex == "allgather" or not ctx.interleaved):
                     continue  # these need a peer exchange (a rank's tiles are scattered over the image) and are pointless on one GPU
                 cands.append((ex, sc))

@@ -262,11 +262,6 @@ int vrt_last_trace_launches(vrt_ctx* ctx, uint32_t* out);
                                the ranks finish together whatever the frame looks like.  Same requirements as DEAL; every rank must launch the
                                same frame. */
 int vrt_set_schedule(vrt_ctx* ctx, uint32_t mode, uint32_t interval /* frames between sorts; 0 = 8 */);
-/* VRT_SCHED_LPT only: the most expensive tiles of the sorted order — whole cost classes, at most permille / 1000 of the tiles — are
- * traced as four tickets each, one per row of 8 pixels (the warp's other 24 lanes idle).  A tile that would keep one warp busy for
- * most of a short launch (a 1080p frame on 4-8 GPUs: less than two tiles per resident warp) then runs on four warps side by side.
- * Costs throughput, buys latency; 0 (the default) = off.  The image is the same either way. */
-int vrt_set_tile_split(vrt_ctx* ctx, uint32_t permille);
 /* Debug / tests: read the per-tile costs of the last frame (clock ticks / 32, 0 = never traced), or install costs and sort them
  * into the order right away.  count <= tiles of the image = ceil(width/8) * ceil(height/4). */
 int vrt_sched_get_costs(vrt_ctx* ctx, uint16_t* costs_host, size_t count);

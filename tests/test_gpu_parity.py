@@ -377,47 +377,9 @@ def test_tile_schedules_trace_the_same_frame(materials):
             assert np.array_equal(ctx.trace_to_host(cam, sun), ref_img)
     got = ctx.sched_costs()
     assert got.shape[0] == n_tiles and (got > 0).all()
-    # the most expensive tiles traced row by row on four warps (vrt_set_tile_split): a few cost classes, most of the tiles, all of them;
-    # the frame (a caller-owned image here) is cleared in between so that a row nobody traced would show
-    import torch
-
-    class Cleared:
-        def __init__(self, c):
-            self.dev = torch.zeros(H * W * 4, dtype=torch.uint8, device="cuda")
-            c._check(c._l.vrt_attach_framebuffer(c.handle, self.dev.data_ptr(), self.dev.numel()))
-            self.c = c
-
-        def __call__(self):
-            self.c.sync()
-            self.dev.zero_()
-            torch.cuda.synchronize()
-
-    ctx.clear_framebuffer = Cleared(ctx)
-    for permille in (20, 500, 1000, 0):
-        ctx.set_tile_split(permille)
-        for costs in cost_sets:
-            ctx.sched_set_costs(costs)
-            for _ in range(4):  # frames 3 and 4 run on the kernel's own costs (re-sorted every 3rd frame)
-                ctx.clear_framebuffer()
-                assert np.array_equal(ctx.trace_to_host(cam, sun), ref_img), f"split {permille}"
     ctx.set_schedule(ffi.VRT_SCHED_STATIC)
     assert np.array_equal(ctx.trace_to_host(cam, sun), ref_img)
     ctx.close()
-    # ... and on a rank's interleaved strips (the multi-GPU partition), with the AOV-free tuned kernel
-    for r in range(3):
-        ctx = ffi.Context(W, H, len(grid.brick_indices), part=(r, 3))
-        ctx.upload_grid(grid, materials)
-        ctx.set_schedule(ffi.VRT_SCHED_LPT, 2)
-        ctx.set_tile_split(300)
-        ctx.clear_framebuffer = Cleared(ctx)
-        for _ in range(5):
-            ctx.clear_framebuffer()
-            ctx.trace(cam, sun)
-        img = ctx.read_framebuffer()
-        rows = np.arange(H)
-        own = (rows // 4) % 3 == r
-        assert np.array_equal(img[own], ref_img[own]), f"rank {r}"
-        ctx.close()
     for world in (2, 3, 8):
         total = np.zeros((H, W, 4), dtype=np.uint32)
         covered = np.zeros((H, W), dtype=np.int32)

@@ -27,28 +27,17 @@ t_static = best(full)
 full.set_schedule(ffi.VRT_SCHED_LPT, 2)
 t_lpt = best(full)
 costs = full.sched_costs()
-SPLITS = (30, 150, 400)  # vrt_set_tile_split: permille of the tiles (the most expensive) traced row by row
-t_split = {}
-for pm in SPLITS:
-    full.set_tile_split(pm)
-    t_split[pm] = best(full)
-full.set_tile_split(0)
-print("world 1: lpt with split " + "  ".join(f"{pm}: {t:.4f} ms" for pm, t in t_split.items()), flush=True)
 print(f"world 1: static {t_static:.4f} ms, lpt {t_lpt:.4f} ms; tile cost (ticks/32): median {np.median(costs):.0f} p99 {np.percentile(costs, 99):.0f} max {costs.max()}", flush=True)
 out["1"] = {"static": t_static, "lpt": t_lpt, "cost_median": float(np.median(costs)), "cost_p99": float(np.percentile(costs, 99)), "cost_max": int(costs.max())}
 full.close()
 for world in (2, 4, 8):
-    res = {"static": [], "lpt": [], **{f"lpt+{pm}": [] for pm in SPLITS}, "deal": []}
+    res = {"static": [], "lpt": [], "deal": []}
     for r in range(world):
         ctx = ffi.Context(wl.width, wl.height, len(grid.brick_indices), part=(r, world))
         ctx.upload_grid(grid, mats)
         res["static"].append(best(ctx))
         ctx.set_schedule(ffi.VRT_SCHED_LPT, 2)
         res["lpt"].append(best(ctx))
-        for pm in SPLITS:
-            ctx.set_tile_split(pm)
-            res[f"lpt+{pm}"].append(best(ctx))
-        ctx.set_tile_split(0)
         ctx.set_schedule(ffi.VRT_SCHED_DEAL, 1000)  # keep the order sorted from the full-frame costs (a real run exchanges costs every frame)
         ctx.sched_set_costs(costs)
         res["deal"].append(best(ctx))

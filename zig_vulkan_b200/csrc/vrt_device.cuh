@@ -274,11 +274,6 @@ struct TraceParams {
     // traces it (and into every peer's copy when the tiles of one frame are dealt across GPUs), the sort key of the next order.
     const uint32_t* tile_order;
     uint32_t order_offset, order_stride;
-    // Split of the most expensive tiles (cost-sorted order only): *split_heavy = H, written by the sort.  The first H tiles of the
-    // order are traced as four tickets each — one per row of 8 pixels, the other 24 lanes idle — so that the rays of a tile that
-    // would hold one warp for most of a short launch run on four warps side by side.  Tickets 0 .. 4H-1 are (order[t / 4], row
-    // t % 4), ticket t >= 4H is order[t - 3H].  NULL: no split.
-    const uint32_t* split_heavy;
     uint16_t* tile_cost;
     uint16_t* peer_cost[8];
     uint32_t n_cost_peers;  // entries of peer_cost in use (dealt schedules across GPUs)

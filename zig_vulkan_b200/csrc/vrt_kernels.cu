@@ -86,18 +86,13 @@ __global__ void __launch_bounds__(kTunedThreads, SIMPLE ? VRT_TUNED_BLOCKS : VRT
 #endif
 
     for (;;) {
-        // leading tiles of the order that are traced row by row (re-read per tile, under the ticket's latency, rather than held in a register)
-        const uint32_t n_split = P.split_heavy ? min(__ldg(P.split_heavy), tiles_total) : 0u;
         unsigned long long t = 0ull;
         if (lane == 0) t = draw_ticket(P);
         t = __shfl_sync(kFullMask, t, 0);
-        if (t >= (unsigned long long)tiles_total + 3ull * n_split) break;
-        uint32_t slot = (uint32_t)t, row = kTileH;  // row == kTileH: the whole tile
-        if (slot < 4u * n_split) row = slot & 3u, slot >>= 2;
-        else slot -= 3u * n_split;
+        if (t >= (unsigned long long)tiles_total) break;
         // Scheduled: the most expensive tiles of the previous frames first (vrt_sched.cu).  Otherwise bottom-up: in the reference's
         // convention image row 0 is up (sky); starting with the ground rows leaves the cheap sky tiles to fill the tail of the launch.
-        const uint32_t tile = P.tile_order ? __ldg(P.tile_order + P.order_offset + slot * P.order_stride) : tiles_total - 1u - slot;
+        const uint32_t tile = P.tile_order ? __ldg(P.tile_order + P.order_offset + (uint32_t)t * P.order_stride) : tiles_total - 1u - (uint32_t)t;
         const long long tick0 = P.tile_cost ? clock64() : 0ll;
 #if VRT_TILE_STATS
         if (lane < 8u) warp_stats()[lane] = 0u;
@@ -106,15 +101,13 @@ __global__ void __launch_bounds__(kTunedThreads, SIMPLE ? VRT_TUNED_BLOCKS : VRT
         const uint32_t px = (tile % tiles_x) * kTileW + lx;
         const uint32_t strip = tile / tiles_x;  // this launch's k-th strip of kTileH rows
         const uint32_t py = P.il_world ? (strip * P.il_world + P.il_rank) * kTileH + ly : P.row_begin + strip * kTileH + ly;
-        const bool mine = row == kTileH || ly == row;
-        const bool inside = mine && px < width && py < P.row_end;  // :156-159
+        const bool inside = px < width && py < P.row_end;  // :156-159
         const uint32_t texel = SIMPLE ? shade_pixel_warp_simple<BD>(P, px, py, inside) : shade_pixel_warp<BD, AOV>(P, px, py, inside, pc);
         const uint32_t out_row = P.il_gather ? (P.il_rank * P.il_strips_max + strip) * kTileH + ly : py;
 
         if (P.n_stage) {  // tile-major exchange: one fully coalesced 128-byte store per rank (NVLink packets 4x larger, 4x fewer)
             const size_t at = ((size_t)(py / kTileH) * tiles_x + tile % tiles_x) * 32u + lane;  // global tile id of this tile
-            if (mine)
-                for (uint32_t p = 0; p < P.n_stage; p++) P.stage[p][at] = texel;
+            for (uint32_t p = 0; p < P.n_stage; p++) P.stage[p][at] = texel;
         } else {
         // 128-bit framebuffer stores: lanes with lx in {0,4} gather the 4 texels to their right
         const uint32_t t1 = __shfl_down_sync(kFullMask, texel, 1);
@@ -122,7 +115,7 @@ __global__ void __launch_bounds__(kTunedThreads, SIMPLE ? VRT_TUNED_BLOCKS : VRT
         const uint32_t t3 = __shfl_down_sync(kFullMask, texel, 3);
         const bool vec = P.vec_store_ok && ((px & ~3u) + 3u < width);  // this lane's group of 4 texels is whole
         if (vec) {
-            if ((lx & 3u) == 0u && py < P.row_end && mine) {
+            if ((lx & 3u) == 0u && py < P.row_end) {
                 const uint4 v = make_uint4(texel, t1, t2, t3);
                 *reinterpret_cast<uint4*>(P.fb + (size_t)out_row * width + px) = v;
                 for (uint32_t p = 0; p < P.n_peers; p++) *reinterpret_cast<uint4*>(P.peer_fb[p] + (size_t)out_row * width + px) = v;
@@ -137,7 +130,7 @@ __global__ void __launch_bounds__(kTunedThreads, SIMPLE ? VRT_TUNED_BLOCKS : VRT
         if (lane < 8u && g_tile_stats) g_tile_stats[(size_t)tile * 8u + lane] = lane == 7u ? (uint32_t)((clock64() - tick0) >> 5) : warp_stats()[lane];
 #endif
         if (P.tile_cost) {  // what this tile cost: the sort key of the next frames' order (lane p also tells peer p)
-            const long long ticks = (clock64() - tick0) >> (row == kTileH ? 5 : 3);  // a row reports four times its own cost: the tile's, roughly
+            const long long ticks = (clock64() - tick0) >> 5;
             const uint16_t c = (uint16_t)(ticks > 65535ll ? 65535ll : (ticks < 1ll ? 1ll : ticks));
             if (lane == 0) P.tile_cost[tile] = c;
             if (lane < P.n_cost_peers) P.peer_cost[lane][tile] = c;

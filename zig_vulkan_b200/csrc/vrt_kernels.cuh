@@ -42,10 +42,8 @@ cudaError_t launch_build_accel(const TraceParams& P, uint4* cell_rec, uint8_t* d
 uint32_t trace_tile_space(const TraceParams& P);
 // Tile schedule (vrt_sched.cu): order[i] = n - 1 - i; stable sort of the tiles by cost, most expensive first.
 size_t sched_scratch_words(uint32_t n_tiles);
-// split_heavy: one device word, see TraceParams::split_heavy; split_limit: the most tiles the sort may mark for the split
-cudaError_t launch_sched_init(uint32_t* order, uint32_t n_tiles, uint32_t* split_heavy, cudaStream_t stream, LaunchInfo* info);
-cudaError_t launch_sched_sort(const uint16_t* cost, uint32_t n_tiles, uint32_t* order, uint32_t* scratch, uint32_t* split_heavy, uint32_t split_limit,
-                              cudaStream_t stream, LaunchInfo* info);
+cudaError_t launch_sched_init(uint32_t* order, uint32_t n_tiles, cudaStream_t stream, LaunchInfo* info);
+cudaError_t launch_sched_sort(const uint16_t* cost, uint32_t n_tiles, uint32_t* order, uint32_t* scratch, cudaStream_t stream, LaunchInfo* info);
 // Explicit-ray mode: GridHit on caller-supplied rays (device pointers).
 cudaError_t launch_trace_rays(const TraceParams& P, const vrt_ray* rays, vrt_ray_hit* hits, size_t count, cudaStream_t stream, LaunchInfo* info);
 // After the all-gather of an interleaved partition: rank-major strips -> row-major frame (width % 4 == 0).

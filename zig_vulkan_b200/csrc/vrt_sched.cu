@@ -35,9 +35,8 @@ __device__ __forceinline__ uint32_t cost_bin(uint32_t c) {
 
 // The cost arrays are NOT touched here: with a dealt schedule a faster peer may already be writing this frame's costs into them
 // (its first frame does not wait for this rank's set-up), and every tile's cost is written before the first sort reads it anyway.
-__global__ void __launch_bounds__(256) sched_init_kernel(uint32_t* __restrict__ order, uint32_t n, uint32_t* __restrict__ split_heavy) {
+__global__ void __launch_bounds__(256) sched_init_kernel(uint32_t* __restrict__ order, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0u) *split_heavy = 0u;  // no costs yet: nothing to split
     if (i >= n) return;
     order[i] = n - 1u - i;  // bottom-up: ground rows first (vrt_kernels.cu)
 }
@@ -105,15 +104,8 @@ __global__ void __launch_bounds__(1024) sched_scan_kernel(uint32_t* __restrict__
     }
 }
 // order[base(bin, blk) + rank of this tile among the block's tiles of the same bin, in tile order] = tile   (stable)
-// Block 0 also sets *split_heavy = the tiles of the most expensive bins that together stay within split_limit (the whole bins
-// only: the sorted order starts with exactly those tiles).
 __global__ void __launch_bounds__(kSortThreads) sched_scatter_kernel(const uint16_t* __restrict__ cost, uint32_t n, const uint32_t* __restrict__ base,
-                                                                     uint32_t* __restrict__ order, uint32_t* __restrict__ split_heavy, uint32_t split_limit) {
-    if (blockIdx.x == 0u && threadIdx.x < kBins) {
-        const uint32_t b = threadIdx.x;
-        const uint32_t before = base[b * gridDim.x], through = b + 1u < (uint32_t)kBins ? base[(b + 1u) * gridDim.x] : n;  // tiles in bins < b, <= b
-        if (before <= split_limit && (through > split_limit || b + 1u == (uint32_t)kBins)) *split_heavy = through <= split_limit ? through : before;
-    }
+                                                                     uint32_t* __restrict__ order) {
     __shared__ uint16_t warp_count[kSortThreads / 32][kBins];
     if (threadIdx.x < kBins)
         for (int w = 0; w < kSortThreads / 32; w++) warp_count[w][threadIdx.x] = 0;
@@ -142,20 +134,19 @@ __global__ void __launch_bounds__(kSortThreads) sched_scatter_kernel(const uint1
 
 size_t sched_scratch_words(uint32_t n_tiles) { return (size_t)kBins * ((n_tiles + kSortThreads - 1) / kSortThreads); }
 
-cudaError_t launch_sched_init(uint32_t* order, uint32_t n_tiles, uint32_t* split_heavy, cudaStream_t stream, LaunchInfo* info) {
+cudaError_t launch_sched_init(uint32_t* order, uint32_t n_tiles, cudaStream_t stream, LaunchInfo* info) {
     if (n_tiles == 0) return cudaSuccess;
-    sched_init_kernel<<<(n_tiles + 255) / 256, 256, 0, stream>>>(order, n_tiles, split_heavy);
+    sched_init_kernel<<<(n_tiles + 255) / 256, 256, 0, stream>>>(order, n_tiles);
     if (info) info->launches++;
     return cudaGetLastError();
 }
 
-cudaError_t launch_sched_sort(const uint16_t* cost, uint32_t n_tiles, uint32_t* order, uint32_t* scratch, uint32_t* split_heavy, uint32_t split_limit,
-                              cudaStream_t stream, LaunchInfo* info) {
+cudaError_t launch_sched_sort(const uint16_t* cost, uint32_t n_tiles, uint32_t* order, uint32_t* scratch, cudaStream_t stream, LaunchInfo* info) {
     if (n_tiles == 0) return cudaSuccess;
     const uint32_t nblk = (n_tiles + kSortThreads - 1) / kSortThreads;
     sched_hist_kernel<<<nblk, kSortThreads, 0, stream>>>(cost, n_tiles, scratch);
     sched_scan_kernel<<<1, 1024, 0, stream>>>(scratch, (uint32_t)kBins * nblk);
-    sched_scatter_kernel<<<nblk, kSortThreads, 0, stream>>>(cost, n_tiles, scratch, order, split_heavy, split_limit);
+    sched_scatter_kernel<<<nblk, kSortThreads, 0, stream>>>(cost, n_tiles, scratch, order);
     if (info) info->launches += 3;
     return cudaGetLastError();
 }

@@ -137,8 +137,6 @@ struct vrt_ctx {
 
     // tile schedule (vrt_sched.cu): costs live behind the frame ring + flags in the IPC allocation so that peers can write them
     uint32_t sched_mode = VRT_SCHED_STATIC, sched_interval = 8;
-    uint32_t split_permille = 0;      // VRT_SCHED_LPT: at most this share of the tiles (the most expensive) is traced row by row
-    uint32_t* d_split_heavy = nullptr;  // how many the last sort marked (TraceParams::split_heavy)
     uint32_t* d_order = nullptr;
     uint32_t* d_sched_scratch = nullptr;
     uint16_t* d_cost[2] = {nullptr, nullptr};
@@ -315,7 +313,6 @@ void fill_params(const vrt_ctx* c, const vrt_camera* cam, const vrt_sun* sun, Tr
         P.tile_order = c->d_order;
         P.tile_cost = c->d_cost[parity];
         P.order_offset = 0u, P.order_stride = 1u;
-        if (c->sched_mode == VRT_SCHED_LPT && c->split_permille) P.split_heavy = c->d_split_heavy;
         if (c->sched_mode == VRT_SCHED_DEAL || c->sched_mode == VRT_SCHED_SHARED) {
             // the whole image is one tile space: this rank takes every part_world-th entry of the order (DEAL), or whatever ticket its
             // warps draw from the ONE queue all ranks share — rank 0's, reached through the peer mapping (SHARED)
@@ -446,8 +443,6 @@ int vrt_init(vrt_ctx** out_ctx, const vrt_config* cfg) {
     ctx->d_cost[0] = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(ctx->d_fb_own) + 2 * ctx->fb_bytes + kPeerFlagBytes);
     ctx->d_cost[1] = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(ctx->d_cost[0]) + cost_bytes(ctx));
     INIT_CUDA(cudaMalloc(&ctx->d_order, (size_t)ctx->tiles_global * 4));
-    INIT_CUDA(cudaMalloc(&ctx->d_split_heavy, 4));
-    INIT_CUDA(cudaMemset(ctx->d_split_heavy, 0, 4));
     INIT_CUDA(cudaMalloc(&ctx->d_sched_scratch, sched_scratch_words(ctx->tiles_global) * 4));
     INIT_CUDA(cudaEventCreate(&ctx->ev_kernel_end));
     INIT_CUDA(cudaMalloc(&ctx->d_tile_counter, 16));
@@ -492,7 +487,7 @@ void vrt_deinit(vrt_ctx* ctx) {
     cudaFree(ctx->d_materials), cudaFree(ctx->d_statuses), cudaFree(ctx->d_brick_indices), cudaFree(ctx->d_occupancy);
     cudaFree(ctx->d_start_indices), cudaFree(ctx->d_material_indices), cudaFree(ctx->d_fb_own), cudaFree(ctx->d_aov);
     cudaFree(ctx->d_counters), cudaFree(ctx->d_cell_rec), cudaFree(ctx->d_dist), cudaFree(ctx->d_dist_tmp);
-    cudaFree(ctx->d_order), cudaFree(ctx->d_split_heavy), cudaFree(ctx->d_sched_scratch), cudaFree(ctx->d_status_stage), cudaFree(ctx->d_accel_delta);
+    cudaFree(ctx->d_order), cudaFree(ctx->d_sched_scratch), cudaFree(ctx->d_status_stage), cudaFree(ctx->d_accel_delta);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     for (int i = 0; i < 4; i++)
         if (ctx->ev_stage[i]) cudaEventDestroy(ctx->ev_stage[i]);
@@ -578,7 +573,6 @@ bool peer_mode(const vrt_ctx* c) {
            (c->exchange_mode == VRT_EXCHANGE_PEER_STORE || c->exchange_mode == VRT_EXCHANGE_PEER_FLAGS || c->exchange_mode == VRT_EXCHANGE_PEER_PUSH ||
             c->exchange_mode == VRT_EXCHANGE_PEER_TILES);
 }
-uint32_t split_limit(const vrt_ctx* c, uint32_t tiles) { return c->sched_mode == VRT_SCHED_LPT ? (uint32_t)((unsigned long long)tiles * c->split_permille / 1000ull) : 0u; }
 bool scattered(const vrt_ctx* c) { return c->sched_mode == VRT_SCHED_DEAL || c->sched_mode == VRT_SCHED_SHARED; }
 bool owns_fb(const vrt_ctx* c) { return c->d_fb == c->d_fb_own || c->d_fb == c->d_fb_ring1; }
 
@@ -662,7 +656,7 @@ int trace_frame(vrt_ctx* ctx, const vrt_camera* camera, const vrt_sun* sun, bool
         Q.tile_order = nullptr;
         const uint32_t space = trace_tile_space(Q);
         if (space != ctx->sched_tiles) {
-            VRT_CUDA(ctx, launch_sched_init(ctx->d_order, space, ctx->d_split_heavy, ctx->stream, &info));
+            VRT_CUDA(ctx, launch_sched_init(ctx->d_order, space, ctx->stream, &info));
             ctx->sched_tiles = space, ctx->sched_frames = 0;
             P.tile_cost = ctx->d_cost[0];
             if (scattered(ctx) && P.n_peers) {  // parity 0 again
@@ -723,7 +717,7 @@ int trace_frame(vrt_ctx* ctx, const vrt_camera* camera, const vrt_sun* sun, bool
         // every `interval` frames (and after the first): sort the costs this frame reported into the next frames' order.  Dealt
         // schedules sort AFTER the frame barrier, when every rank's costs of this frame have arrived: all ranks sort the same array.
         if (ctx->sched_frames % ctx->sched_interval == 0)
-            VRT_CUDA(ctx, launch_sched_sort(P.tile_cost, ctx->sched_tiles, ctx->d_order, ctx->d_sched_scratch, ctx->d_split_heavy, split_limit(ctx, ctx->sched_tiles), ctx->stream, &info));
+            VRT_CUDA(ctx, launch_sched_sort(P.tile_cost, ctx->sched_tiles, ctx->d_order, ctx->d_sched_scratch, ctx->stream, &info));
         ctx->sched_frames++;
     }
     if (!pipelined) {
@@ -1035,7 +1029,7 @@ int vrt_trace_rays(vrt_ctx* ctx, const vrt_ray* rays_device, vrt_ray_hit* hits_d
     fill_params(ctx, &cam, &sun, P);
     // the ray list is this context's own: its private queue, no tile schedule, no peers
     P.tile_counter = ctx->d_tile_counter, P.queue_world = 0u;
-    P.tile_order = nullptr, P.split_heavy = nullptr, P.tile_cost = nullptr, P.n_cost_peers = 0u, P.n_peers = 0u, P.n_stage = 0u;
+    P.tile_order = nullptr, P.tile_cost = nullptr, P.n_cost_peers = 0u, P.n_peers = 0u, P.n_stage = 0u;
     LaunchInfo info = {0u};
     if (ctx->accel_dirty || ctx->occ_dirty) {
         const int rcb = rebuild_accel(ctx, P, &info);
@@ -1152,13 +1146,6 @@ int vrt_set_schedule(vrt_ctx* ctx, uint32_t mode, uint32_t interval) {
     return VRT_OK;
 }
 
-int vrt_set_tile_split(vrt_ctx* ctx, uint32_t permille) {
-    if (!ctx) return VRT_E_INVALID;
-    if (permille > 1000u) return fail(ctx, VRT_E_INVALID, "vrt_set_tile_split: permille %u > 1000", permille);
-    ctx->split_permille = permille;  // takes effect at the next sort; until then the tiles marked by the last one stay split
-    return VRT_OK;
-}
-
 int vrt_sched_get_costs(vrt_ctx* ctx, uint16_t* costs_host, size_t count) {
     if (!ctx) return VRT_E_INVALID;
     if (!costs_host || count > ctx->tiles_global) return fail(ctx, VRT_E_INVALID, "vrt_sched_get_costs: at most %u tiles", ctx->tiles_global);
@@ -1180,7 +1167,7 @@ int vrt_sched_set_costs(vrt_ctx* ctx, const uint16_t* costs_host, size_t count) 
         if (rc != VRT_OK) return rc;
     }
     LaunchInfo info = {0u};
-    VRT_CUDA(ctx, launch_sched_sort(ctx->d_cost[0], (uint32_t)count, ctx->d_order, ctx->d_sched_scratch, ctx->d_split_heavy, split_limit(ctx, (uint32_t)count), ctx->stream, &info));
+    VRT_CUDA(ctx, launch_sched_sort(ctx->d_cost[0], (uint32_t)count, ctx->d_order, ctx->d_sched_scratch, ctx->stream, &info));
     ctx->sched_tiles = (uint32_t)count;
     ctx->sched_frames = 1;  // the order is in place: no re-initialisation, next sort at the next multiple of the interval
     return VRT_OK;

@@ -173,7 +173,6 @@ VRT_SYMBOLS = {
     "vrt_debug_force_accel_rebuild": (C.c_int, [_P]),
     "vrt_debug_tile_stats": (C.c_int, [_P, _P, _SZ]),
     "vrt_set_schedule": (C.c_int, [_P, C.c_uint32, C.c_uint32]),
-    "vrt_set_tile_split": (C.c_int, [_P, C.c_uint32]),
     "vrt_sched_get_costs": (C.c_int, [_P, _P, _SZ]),
     "vrt_sched_set_costs": (C.c_int, [_P, _P, _SZ]),
     "vrt_set_stream": (C.c_int, [_P, _P]),
@@ -785,9 +784,6 @@ class Context:
 
     def set_schedule(self, mode: int, interval: int = 0):
         self._check(self._l.vrt_set_schedule(self.handle, mode, interval))
-
-    def set_tile_split(self, permille: int):
-        self._check(self._l.vrt_set_tile_split(self.handle, permille))
 
     @property
     def n_tiles(self) -> int:
