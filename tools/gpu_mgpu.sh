@@ -1,9 +1,12 @@
 #!/bin/bash
-# Multi-GPU visit: tests/test_multi_gpu.py for every world size the box has, then the bench line at that N.  usage: tools/gpu_mgpu.sh N
+# Multi-GPU visit: tests/test_multi_gpu.py for every world size the box has, then the bench line at that N.
+# usage: [SKIP_TESTS=1] tools/gpu_mgpu.sh N
 N=$1
 mkdir -p gpurun_out
 nvidia-smi -L | head -8
-timeout -k 5 900 python -m pytest tests/test_multi_gpu.py -m gpu -x -q -rs > gpurun_out/pytest_mgpu_n$N.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_mgpu_n$N.log; tail -6 gpurun_out/pytest_mgpu_n$N.log
+if [ -z "$SKIP_TESTS" ]; then
+  timeout -k 5 900 python -m pytest tests/test_multi_gpu.py -m gpu -x -q -rs > gpurun_out/pytest_mgpu_n$N.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_mgpu_n$N.log; tail -6 gpurun_out/pytest_mgpu_n$N.log
+fi
 timeout -k 5 600 python bench.py --gpus $N > gpurun_out/bench_C3_n$N.json 2> gpurun_out/bench_n$N.err; echo "bench rc=$?"; tail -3 gpurun_out/bench_n$N.err
 python - <<PY
 import json
