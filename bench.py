@@ -420,6 +420,14 @@ def measure(rig, grid, mats, W, H, brick_dim, cam, sun, steps, warmup, with_e2e=
     rig.barrier()
     e2e_s = rig.reduce([time.perf_counter() - t0])[0]
     res["e2e_s"], res["latency_ms"] = e2e_s, lat_s / n_lat * 1e3
+    # what the in-stream L2 flush itself costs per frame (it is inside the e2e region and serial with the trace)
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record(rig.stream)
+    for i in range(20):
+        rig.flush.fill_(i & 0xFF)
+    f1.record(rig.stream)
+    f1.synchronize()
+    res["flush_ms"] = f0.elapsed_time(f1) / 20
     res["e2e_frame_ok"] = bool(np.array_equal(host_frames[(steps - 1) & 1].numpy().reshape(H, W, 4), img)) if rank == 0 else None
     if world > 1 and ctx.interleaved:
         res["e2e_host"] = e2e_host_assembled(rig, ctx, cam, sun, W, H, steps, img)
@@ -485,13 +493,14 @@ def e2e_record(m, rays, steps, n_pixels, world):
     """The headline: frames through the C ABI with host buffers.  N = 1: vrt_trace_to_host_async into pinned memory.  N > 1: the
     host-assembled exchange (every rank's strips over its own PCIe link into one shared pinned frame); the variant that first
     assembles the frame on every GPU over NVLink and then ships it through rank 0's link alone is reported beside it."""
-    funnel = {"value": rays * steps / m["e2e_s"] / 1e6, "ms_per_step": m["e2e_s"] / steps * 1e3, "frame_latency_ms": m["latency_ms"], "frame_ok": m["e2e_frame_ok"]}
+    funnel = {"value": rays * steps / m["e2e_s"] / 1e6, "ms_per_step": m["e2e_s"] / steps * 1e3, "frame_latency_ms": m["latency_ms"], "frame_ok": m["e2e_frame_ok"],
+              "l2_flush_ms_per_step": m.get("flush_ms")}
     how = ("vrt_trace_to_host_async per frame (camera+sun host structs in, RGBA8 frame into pinned host memory, 2 frames in flight), "
-           "L2 flush enqueued between frames inside the timed region; frame_latency_ms = blocking vrt_trace_to_host")
+           "L2 flush enqueued between frames inside the timed region (l2_flush_ms_per_step of every step is that fill); frame_latency_ms = blocking vrt_trace_to_host")
     h = m.get("e2e_host")
     if h:
         return {"value": rays * steps / h["seconds"] / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 128 * world, "d2h_bytes_per_step": n_pixels * 4,
-                "ms_per_step": h["seconds"] / steps * 1e3, "frame_ok": h["frame_ok"], "pinned": h["pinned"],
+                "ms_per_step": h["seconds"] / steps * 1e3, "frame_ok": h["frame_ok"], "pinned": h["pinned"], "l2_flush_ms_per_step": m.get("flush_ms"),
                 "how": "VRT_EXCHANGE_HOST: no device-side exchange; " + how.split(";")[0] + f"; each of the {world} ranks copies its own 4-row strips into ONE "
                        "frame in shared pinned host memory over its own PCIe link; timed until every rank's last copy has landed",
                 "via_rank0_after_device_exchange": funnel}
