@@ -16,10 +16,10 @@
 //   * Warp rounds.  The 32 rays of a tile look their cells up TOGETHER, reduce the distances found to the warp minimum
 //     k (redux.sync) and all take k steps: the step loop is warp-uniform (no per-lane counters, no divergence) and the
 //     lookup latency is paid once per round instead of once per ray.
-//   * Warp supersteps.  Phase A: the rays march in rounds until each is parked on a loaded brick or has left
-//     the grid.  Phase B: the parked rays run the voxel-level DDA together.
-//     The expensive brick entry (three divides, a 64-bit mask fetch) is therefore executed coherently instead of once
-//     per ray at 32 different times.
+//   * Warp supersteps.  Phase A: the rays march in rounds until one of them parks on a loaded brick (or all have left
+//     the grid).  Phase B, right after that round: the parked rays run the voxel-level DDA together — the rays of a tile
+//     mostly reach a surface in the same round, so the expensive brick entry (three divides, a 64-bit mask fetch) is still
+//     executed coherently instead of once per ray at 32 different times, and no ray waits for a slower one to park.
 //   * The 4^3 voxel mask of a brick and the start of its materials are one 128-bit load from a grid-indexed record (`cell_rec`) and the voxel DDA runs in
 //     registers on ONE packed integer (bounds guard + voxel index, brick_hit_warp4); 8^3 / 16^3 bricks keep the current 32-bit
 //     mask word in a register (brick_hit_warp_n).  The shader does a dependent brick_indices load plus one byte load per
