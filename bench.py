@@ -699,6 +699,16 @@ def single_gpu_extras(rig, line, ctx, wl, grid, mats, cam, sun):
     # the same frame restricted to what the simple path covers (1 sample, no bounce, point sun), for the per-ray comparison
     scam = scenes.camera(R["width"], R["height"], spp=1, max_bounce=0, origin=(0.0, -5.0, 14.0), euler_deg=(25.0, 0.0, 0.0))
     sms = trace_ms(rctx, scam, scenes.sun(True, 0.0), n=24, warm=9)
+    # ... and those same rays through the GENERAL path's code (an unused material entry of an unknown type switches the launch to it
+    # without changing a pixel, tests/test_gpu_parity.py::test_simple_and_general_shading_paths_agree): what the code path itself costs
+    gms = None
+    unused = next((i for i in range(len(mats) - 1, 0, -1) if not (rgrid.material_indices == i).any()), None)
+    if unused is not None:
+        gmats = mats.copy()
+        gmats[unused]["type"] = 4
+        rctx.upload_materials(0, gmats)
+        gms = trace_ms(rctx, scam, scenes.sun(True, 0.0), n=24, warm=9)
+        rctx.upload_materials(0, mats)
     sc = ffi.Context(R["width"], R["height"], len(rgrid.brick_indices), device=rig.local_rank, flags=ffi.VRT_FLAG_AOV | ffi.VRT_FLAG_BASELINE)
     sc.upload_grid(rgrid, mats)
     sc.trace(scam, scenes.sun(True, 0.0))
@@ -709,7 +719,12 @@ def single_gpu_extras(rig, line, ctx, wl, grid, mats, cam, sun):
     line["ref_default"] = {"workload": "reference default (main.zig:77-81,122-135): 128x64x128 bricks of 4^3 @0.5, 1024x576, spp 2, max_bounce 2, sun disc radius 5",
                            "rays_per_step": rrays, "ms_per_step": rmean, "mrays_s": rrays / (rmean * 1e-3) / 1e6, "ns_per_ray": rmean * 1e6 / rrays,
                            "simple_path_same_view": {"rays": srays, "ms": smean, "ns_per_ray": smean * 1e6 / srays},
-                           "general_over_simple_per_ray": (rmean / rrays) / (smean / srays)}
+                           "general_over_simple_per_ray": (rmean / rrays) / (smean / srays),
+                           "note": "general_over_simple_per_ray compares different rays (two samples, scattered bounce rays, a sun disc against one coherent "
+                                   "camera + sun ray per pixel); general_path_same_rays runs the simple configuration's rays through the general path's code"}
+    if gms:
+        gmean = sum(gms) / len(gms)
+        line["ref_default"]["general_path_same_rays"] = {"rays": srays, "ms": gmean, "ns_per_ray": gmean * 1e6 / srays, "over_simple_path": gmean / smean}
 
     # ---- the step after the path: the reference's present pass (image.frag) over the traced frame, same resolution
     dn = []
