@@ -160,11 +160,16 @@ cudaError_t launch_warp_kernel(const TraceParams& P, int num_sms, cudaStream_t s
         tiles_total = P.order_offset < tiles_total ? (tiles_total - P.order_offset + P.order_stride - 1u) / P.order_stride : 0u;
     if (tiles_total == 0) return cudaSuccess;
     const uint32_t warps_per_block = kTunedThreads / 32;
-    // Short launches (a rank's share of a frame split over 4-8 GPUs: fewer than ~5 tiles per resident warp) are as long as their most
+    // Short partitioned launches (a rank's share of a frame split over 4-8 GPUs: fewer than ~5 tiles per resident warp) are as long as their most
     // expensive tiles, whose time is a chain of dependent L2 round trips — half the resident warps leave those tiles twice the issue
     // slots and cost nothing when the SMs would run dry anyway: -8 % at 1/4 and 1/8 of a 1080p frame, +29 % on the whole frame
     // (profiles/r02_ab_resident_ctas_C3.txt).
-    if (SIMPLE && blocks_per_sm > 4 && (unsigned long long)tiles_total < 5ull * (unsigned long long)num_sms * (unsigned long long)blocks_per_sm * warps_per_block) blocks_per_sm = 4;
+    // Only for a rank's share of a frame (where it was measured): a small whole frame of a lighter scene lost 4 % to it (the bench's
+    // ref_default view, 9 216 tiles).
+    const bool partitioned = P.il_world > 1u || (P.tile_order && P.order_stride > 1u) || P.row_end - P.row_begin < P.cam.image_height;
+    if (SIMPLE && partitioned && blocks_per_sm > 4 &&
+        (unsigned long long)tiles_total < 5ull * (unsigned long long)num_sms * (unsigned long long)blocks_per_sm * warps_per_block)
+        blocks_per_sm = 4;
     uint32_t grid = (uint32_t)(num_sms * blocks_per_sm);  // one resident wave: a multiple of the SM count
     const uint32_t needed = (tiles_total + warps_per_block - 1) / warps_per_block;
     if (grid > needed) grid = needed;
