@@ -22,6 +22,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 POSE0 = dict(origin=(0.0, -10.0, 28.0), euler_deg=(25.0, 0.0, 0.0))   # the headline pose: 25 deg down onto the terrain, ~52 % of the pixels hit
+POSE0_DESC = "pose0 origin (0,-10,28) pitch 25deg"
 POSE_SURVEY = dict(origin=(0.0, -8.0, 0.0), euler_deg=(0.0, 0.0, 0.0))  # SURVEY.md 8(d)'s "pose 0": level view from above the grid centre
 L2_FLUSH_BYTES = 144 << 20  # > 126 MB L2
 
@@ -154,7 +155,7 @@ def time_oracle(wl, steps, warmup, budget_s=None):
         times.append(time.perf_counter() - t0)
         if budget_s is not None and time.perf_counter() - t_begin > budget_s:
             break
-    return rays, times, cores, kind
+    return rays, times, cores, kind, grid
 
 
 def run_reference(args):
@@ -167,14 +168,16 @@ def run_reference(args):
     if rank != 0:
         return
     wl = scenes.WORKLOADS[args.workload]
-    steps = min(args.steps, 60)
-    rays, times, cores, kind = time_oracle(wl, steps, min(args.warmup, 3), budget_s=150.0)
+    # exactly --steps timed frames after --warmup untimed ones, like the product arm (a C3 frame takes ~0.12 s on 16 threads: the
+    # default 200 + 20 is half a minute); the budget is a safety net for a slow box, far above what the driver's runs need
+    rays, times, cores, kind, grid = time_oracle(wl, args.steps, args.warmup, budget_s=900.0)
     total = sum(times)
     value = rays * len(times) / total / 1e6
     line = {
-        "impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": len(times), "warmup": min(args.warmup, 3),
+        "impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup,
         "ms_per_step": total / len(times) * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": {"workload": f"{wl.name}: {wl.description}", "pose": "pose0", "rays_per_step": rays},
+        "data": "synthetic", "config": {"workload": f"{wl.name}: {wl.description}", "pose": POSE0_DESC, "rays_per_step": int(rays),
+                                      "grid_bricks": len(grid.brick_indices), "active_bricks": grid.active_bricks},
         "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": kind,
                          "sample": f"{len(times)} full {wl.width}x{wl.height} frames, all rows, "
                                    + ("oracle/_ref/libref_shader.so (the reference's shader text, g++)" if kind == "reference" else "oracle/liboracle.so") + f" with {cores} threads"},
@@ -581,7 +584,7 @@ def main():
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
-                "workload": f"{wl.name}: {wl.description}", "pose": "pose0 origin (0,-10,28) pitch 25deg", "rays_per_step": int(rays),
+                "workload": f"{wl.name}: {wl.description}", "pose": POSE0_DESC, "rays_per_step": int(rays),
                 "grid_bricks": len(grid.brick_indices), "active_bricks": grid.active_bricks, "l2": f"flushed between steps ({L2_FLUSH_BYTES >> 20} MiB fill)",
                 "kernel": "baseline" if args.baseline_kernel else "tuned",
                 "partition": ("4-row strips round-robin" if ctx.interleaved else "row slabs") + f" over {world} ranks" if world > 1 else "whole frame",
@@ -621,7 +624,7 @@ def main():
             rig.set_mode(ctx, "none", m["schedule"])
         single_gpu_extras(rig, line, ctx, wl, grid, mats, cam, sun)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        crays, ctimes, cores, kind = time_oracle(wl, 12, 1, budget_s=20.0)
+        crays, ctimes, cores, kind, _ = time_oracle(wl, 12, 1, budget_s=20.0)
         best = min(ctimes)
         line["cpu_baseline"] = {"value": crays / best / 1e6, "unit": "Mrays/s", "cores": cores, "kind": kind,
                                 "sample": f"best of {len(ctimes)} full {W}x{H} frames of the same workload, "

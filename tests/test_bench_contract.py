@@ -23,9 +23,10 @@ def test_reference_arm_prints_one_contract_line():
     assert len(lines) == 1, lines
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "Mrays/s" and d["unit"] == "Mrays/s" and d["higher_is_better"] is True
-    assert d["n_gpus"] == 1 and d["steps"] == 2 and d["value"] > 0 and d["ms_per_step"] > 0
+    assert d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 1 and d["value"] > 0 and d["ms_per_step"] > 0  # exactly the K and W asked for
     assert d["vs_baseline"] is None and d["dtype"] == "f32" and d["data"] == "synthetic"
     assert d["config"]["workload"].startswith("C1") and d["config"]["rays_per_step"] == 256 * 256
+    assert set(d["config"]) == {"workload", "pose", "rays_per_step", "grid_bricks", "active_bricks"}  # the keys that name the workload in both arms
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["unit"] == "Mrays/s" and cb["sample"]
     # this container builds oracle/_ref from /root/reference (Makefile): the arm must then run the reference's shader text
