@@ -122,6 +122,31 @@ def test_full_path_trace_modes(materials, kernel):
     assert np.array_equal(img, ref_img)
 
 
+def test_reference_default_configuration(materials):
+    """The reference application's default configuration at its exact size (main.zig:77-81,122-135, Sun.zig:4-11): 128x64x128 bricks
+    of 4^3 at scale 0.5, 1024x576, spp 2, max_bounce 2, sun disc radius 5 — the workload `ref_default` of the bench line, on the
+    general shading path.  Frame and hit records against the oracle, and against the reference's own shader text where it was built."""
+    import os
+
+    R = scenes.REF_DEFAULT
+    grid = scenes.build_ref_default_grid()
+    cam = scenes.camera(R["width"], R["height"], spp=R["spp"], max_bounce=R["max_bounce"], origin=(0.0, -5.0, 14.0), euler_deg=(25.0, 0.0, 0.0))
+    sun = scenes.sun(True, R["sun_radius"])
+    sc = orc.OracleScene.from_grid(grid, materials)
+    ref_img, ref_aov, ref_cnt = sc.render(cam, sun, aov=True, threads=os.cpu_count() or 1)
+    assert ref_cnt["primary_hits"] > 100000 and ref_cnt["rays"] > 2 * R["width"] * R["height"]
+    img, aov, cnt = trace(grid, materials, cam, sun, ffi.VRT_FLAG_AOV)
+    assert_same(img, aov, ref_img, ref_aov)
+    assert cnt["rays"] == ref_cnt["rays"] and cnt["shadow_rays"] == ref_cnt["shadow_rays"]
+    img2, _, _ = trace(grid, materials, cam, sun, 0)  # the kernel the bench times
+    assert np.array_equal(img2, ref_img)
+    from oracle import ref
+
+    if ref.available():
+        rimg, _ = ref.render(sc, cam, sun, threads=os.cpu_count() or 1)
+        assert np.array_equal(rimg, ref_img)
+
+
 @pytest.mark.parametrize("sun_on", [True, False])
 def test_simple_and_general_shading_paths_agree(materials, sun_on):
     """The tuned kernel has a specialised shading path for max_bounce 1 / spp 1 / sun radius 0 / only lambert-metal-dielectric
