@@ -122,6 +122,22 @@ def test_full_path_trace_modes(materials, kernel):
     assert np.array_equal(img, ref_img)
 
 
+@pytest.mark.parametrize("kernel", [0, ffi.VRT_FLAG_BASELINE], ids=["tuned", "baseline"])
+@pytest.mark.parametrize("seed", range(40))
+def test_seeded_random_configurations(seed, kernel):
+    """The sweep of tests/random_configs.py (non-cubic grids, non-power-of-two scales, random material tables of every type, cameras
+    anywhere, 1-3 samples, 0-4 bounces, point / disc / no sun) — the same configurations the oracle is held to the reference's
+    shader text on (tests/test_ref_shader.py): frame, hit records and ray counts of both kernels against the oracle."""
+    from random_configs import random_configuration
+
+    c = random_configuration(seed)
+    img, aov, cnt = trace(c["grid"], c["materials"], c["cam"], c["sun"], kernel | ffi.VRT_FLAG_AOV)
+    assert_same(img, aov, c["image"], c["aov"])
+    assert cnt["rays"] == c["counters"]["rays"] and cnt["hits"] == c["counters"]["hits"]
+    img2, _, _ = trace(c["grid"], c["materials"], c["cam"], c["sun"], kernel)
+    assert np.array_equal(img2, c["image"])
+
+
 def test_reference_default_configuration(materials):
     """The reference application's default configuration at its exact size (main.zig:77-81,122-135, Sun.zig:4-11): 128x64x128 bricks
     of 4^3 at scale 0.5, 1024x576, spp 2, max_bounce 2, sun disc radius 5 — the workload `ref_default` of the bench line, on the

@@ -138,6 +138,20 @@ def test_full_path_trace_modes_match_reference_text(case):
     assert_hits_equal(aov, hits)
 
 
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("seed", range(40))
+def test_seeded_random_configurations_match_reference_text(seed):
+    """A seeded sweep nobody tuned by hand (tests/random_configs.py): non-cubic grids, non-power-of-two scales, random material tables
+    (every type, random fuzz / refraction index), cameras inside and outside the grid, 1-3 samples, 0-4 bounces, point / disc / no sun.
+    Oracle == the reference's shader text, frame and hit records, bit for bit."""
+    from random_configs import random_configuration
+
+    c = random_configuration(seed)
+    img, hits = ref.render(c["scene"], c["cam"], c["sun"], hits=True)
+    assert np.array_equal(img, c["image"]), f"{(img != c['image']).any(axis=2).sum()} pixels differ"
+    assert_hits_equal(c["aov"], hits)
+
+
 def test_custom_materials_and_ignore_rule():
     """Materials of every type incl. MAT_NONE (3) and an unknown type (the `default:` arm, :234-237), dielectric index = 1.0
     so that the ignore rule of :427 can fire for camera rays."""
