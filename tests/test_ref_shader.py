@@ -190,6 +190,26 @@ def test_present_pass_matches_reference_text():
             assert np.array_equal(ref.present(img, params, out_width=ow, out_height=oh), orc.denoise(img, params, out_width=ow, out_height=oh)), (params, ow, oh)
 
 
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("seed", range(24))
+def test_present_pass_seeded_random_parameters(seed):
+    """image.frag on random images (flat regions, noise, black and saturated texels), random push constants (whole and fractional
+    hue tolerance, small and large sample offsets, 0-80 samples) and random target sizes: oracle == the reference's text, byte for byte."""
+    rng = np.random.default_rng(500 + seed)
+    w, h = int(rng.integers(1, 70)), int(rng.integers(1, 50))
+    img = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+    if seed % 3 == 0:  # large flat areas: pow(1, n) and equal weights
+        img[: h // 2] = rng.integers(0, 256, 4, dtype=np.uint8)
+    if seed % 4 == 1:
+        img[rng.integers(0, h), rng.integers(0, w), :3] = 0  # a black texel: normalize(0) = NaN, as upstream
+        img[rng.integers(0, h), rng.integers(0, w), :3] = 255
+    params = (int(rng.integers(0, 81)), float(rng.choice([0.3, 0.6, 1.0, 1.7])), float(rng.choice([0.5, 1.5, 4.0, 9.0])),
+              float(rng.choice([1.0, 2.0, 3.0, 20.0, 64.0, 65.0, 2.5, 0.5, 30.25])))
+    ow, oh = (None, None) if seed % 2 else (int(rng.integers(1, 90)), int(rng.integers(1, 60)))
+    flags = ffi.VRT_DENOISE_BGRA if seed % 5 == 0 else 0
+    assert np.array_equal(ref.present(img, params, out_width=ow, out_height=oh, flags=flags), orc.denoise(img, params, out_width=ow, out_height=oh, flags=flags)), (params, w, h, ow, oh)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("kernel_flags", [0, ffi.VRT_FLAG_BASELINE], ids=["tuned", "baseline"])
 def test_cuda_matches_reference_text(kernel_flags):
